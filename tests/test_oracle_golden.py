@@ -1,0 +1,145 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bbob as ob
+from oracle import protein as op
+from oracle import rlepso as orl
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@pytest.fixture(scope='module', params=[10, 30])
+def suite(request):
+    dim = request.param
+    G = load(f'bbob_d{dim}.npz')
+    insts = {}
+    for suit in ('bbob', 'bbob-noisy'):
+        tr, te = ob.make_suite(suit, dim, 5.0, 'easy')
+        for I in tr + te:
+            insts[I.fid] = I
+    return dim, G, insts
+
+
+def test_instance_generation_matches_reference(suite):
+    dim, G, insts = suite
+    assert sorted(insts) == list(range(1, 25)) + list(range(101, 131))
+    for fid, I in insts.items():
+        assert str(G[f'name_{fid}']) == I.name
+        assert float(G[f'opt_{fid}']) == I.optimum          # bit-exact: same draws, same arithmetic
+        if dim == 10:
+            np.testing.assert_array_equal(G[f'shift_{fid}'], I.shift)
+            np.testing.assert_array_equal(G[f'R_{fid}'], I.R)
+            assert float(G[f'bias_{fid}']) == I.bias
+            for k in ('M2', 'y', 'C', 'w'):
+                if f'{k}_{fid}' in G.files:
+                    np.testing.assert_array_equal(G[f'{k}_{fid}'], getattr(I, k))
+
+
+def test_splits(suite):
+    dim, G, _ = suite
+    for suit in ('bbob', 'bbob-noisy'):
+        for diff in ('easy', 'difficult'):
+            _, te = ob.make_suite(suit, dim, 5.0, diff)
+            assert [I.name for I in te] == list(G[f'split_{diff}_{suit}'])
+
+
+def test_noise_free_fitness(suite):
+    dim, G, insts = suite
+    for fid, I in insts.items():
+        X = G[f'x_{fid}'].astype(np.float64)
+        F = ob.func_true(I, X)
+        ref = G[f'f_{fid}']
+        # same formulas, same libm: differences come only from summation order / array layout
+        np.testing.assert_allclose(F, ref, rtol=2e-13, atol=0, err_msg=f'fid {fid}')
+        cost, rcost = F - I.optimum, ref - float(G[f'opt_{fid}'])
+        np.testing.assert_allclose(cost, rcost, rtol=1e-9, atol=64 * np.spacing(abs(I.bias) + 1.0))
+
+
+def test_noisy_fitness(suite):
+    dim, G, insts = suite
+    for fid in range(101, 131):
+        I = insts[fid]
+        X = G[f'x_{fid}'].astype(np.float64)
+        np.random.seed(777 + fid)
+        F = ob.evaluate(I, X)
+        np.testing.assert_allclose(F, G[f'fn_{fid}'], rtol=2e-13, err_msg=f'fid {fid}')
+        np.random.seed(778 + fid)
+        F1 = np.array([ob.evaluate(I, X[k]) for k in range(4)])
+        np.testing.assert_allclose(F1, G[f'fn1_{fid}'], rtol=2e-13)
+
+
+def test_protein_energy():
+    G = load('protein.npz')
+    for pid in G['ids']:
+        I = op.ProteinInstance(str(pid), G[f'coor_init_{pid}'], G[f'q_{pid}'], G[f'e_{pid}'], G[f'r_{pid}'],
+                               G[f'basis_{pid}'], G[f'eigval_{pid}'])
+        E = op.evaluate(I, G[f'x_{pid}'].astype(np.float64))
+        np.testing.assert_allclose(E, G[f'energy_{pid}'], rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------- RLEPSO
+def _problem_for(fid, dim):
+    if fid.isdigit():
+        f = int(fid)
+        suit = 'bbob' if f < 100 else 'bbob-noisy'
+        tr, te = ob.make_suite(suit, dim, 5.0, 'easy')
+        I = [i for i in tr + te if i.fid == f][0]
+        ev = lambda x, draws: ob.apply_noise(I, ob.func_true(I, x), draws=draws)
+        return I, ev, I.optimum, -5.0, 5.0, ob.noise_draw_count(I)
+    G = load('protein.npz')
+    I = op.ProteinInstance(fid, G[f'coor_init_{fid}'], G[f'q_{fid}'], G[f'e_{fid}'], G[f'r_{fid}'],
+                           G[f'basis_{fid}'], G[f'eigval_{fid}'])
+    return I, (lambda x, draws: op.energy(I, x)), None, op.LB, op.UB, (0, 0)
+
+
+def _state_from(G, pre):
+    return orl.State(x=G[pre + 'x'], v=G[pre + 'v'], pbest_x=G[pre + 'pbest_x'], c_cost=G[pre + 'c_cost'],
+                     pbest=G[pre + 'pbest'], pni=G[pre + 'pni'].astype(np.int32), gbest_x=G[pre + 'gbest_x'],
+                     gbest_val=np.float32(G[pre + 'gbest_val']), gbest_idx=int(G[pre + 'gbest_idx']), no_improve=0,
+                     fes=int(G[pre + 'fes']), log_index=int(G[pre + 'log_index']),
+                     curve=[np.float32(c) for c in G[pre + 'curve']])
+
+
+def _cmp_state(S, G, pre, tag):
+    for k in ('x', 'v', 'pbest_x', 'gbest_x'):
+        np.testing.assert_array_equal(getattr(S, k), G[pre + k], err_msg=f'{tag} {k}')
+    for k in ('c_cost', 'pbest'):
+        np.testing.assert_allclose(getattr(S, k), G[pre + k], rtol=1e-6, atol=1e-10, err_msg=f'{tag} {k}')
+    np.testing.assert_array_equal(S.pni, G[pre + 'pni'].astype(np.int32), err_msg=f'{tag} pni')
+    assert S.gbest_idx == int(G[pre + 'gbest_idx']), tag
+    assert S.fes == int(G[pre + 'fes']), tag
+    assert S.log_index == int(G[pre + 'log_index']), tag
+    np.testing.assert_allclose(np.array(S.curve, dtype=np.float64), G[pre + 'curve'], rtol=1e-6, atol=1e-10)
+
+
+def test_rlepso_steps_match_reference():
+    G = load('rlepso.npz')
+    n_reinit = 0
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = orl.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S = orl.init_population(cfg, ev, optimum, lb, ub, orl.NumpyTape(cfg.NP, dim, nc))
+        _cmp_state(S, G, f'{key}/s0/', f'{key} init')
+        for t in range(1, int(G[f'{key}/n_steps']) + 1):
+            S = _state_from(G, f'{key}/s{t - 1}/')          # teacher forcing from the reference's state
+            S.pni = G[f'{key}/s{t}/pni_in']
+            np.random.seed(int(G[f'{key}/s{t}/seed']))
+            aux = {}
+            N, feat, reward, done = orl.update(cfg, S, G[f'{key}/s{t}/action'], ev, optimum, lb, ub,
+                                               orl.NumpyTape(cfg.NP, dim, nc), aux)
+            n_reinit += int(aux['reinit_mask'].any())
+            _cmp_state(N, G, f'{key}/s{t}/', f'{key} step {t}')
+            assert reward == int(G[f'{key}/s{t}/reward'])
+            assert done == bool(G[f'{key}/s{t}/done'])
+            np.testing.assert_array_equal(feat, G[f'{key}/s{t}/feature'])
+    assert n_reinit >= 5        # the re-initialisation branch is covered
