@@ -1,0 +1,151 @@
+/* metabox_b200.h -- C ABI of the B200-native MetaBBO rollout engine (libmbx.so).
+ *
+ * Drop-in boundary for the per-generation hot path of GMC-DRL/MetaBox (reference paths are relative
+ * to /root/reference/src).  The reference has no FFI: its boundary is the duck-typed Python plug-in
+ * API (docs/Customization.md:9-210).  Every entry point below names the reference method it
+ * replaces; the Python shims in metabox_b200/ keep those methods' names and meaning and bind this
+ * library through ctypes.
+ *
+ * Conventions
+ *   - plain C: integers, doubles, raw pointers.  No torch / C++ types.
+ *   - every `d_*` pointer is a DEVICE pointer owned by the caller; `h_*` pointers are HOST pointers.
+ *   - every launch goes to the caller's `stream` (a cudaStream_t passed as void*); entry points never
+ *     allocate device memory, never synchronise, and return 0 or a negative MBX_E* code;
+ *     mbx_last_error() gives the message of the last failure on the calling thread.
+ *   - "lane" = one (instance, run) population advanced in lockstep with the others; B = #lanes.
+ *   - population state is float32 in HBM, arithmetic is float64 in registers.
+ */
+#ifndef METABOX_B200_H
+#define METABOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBX_OK 0
+#define MBX_EINVAL -1   /* bad argument (shape, id, null pointer)            */
+#define MBX_ECUDA -2    /* CUDA runtime error (launch / attribute)           */
+#define MBX_EUNSUP -3   /* combination not compiled (e.g. dim > MBX_MAX_DIM) */
+
+#define MBX_MAX_DIM 64
+#define MBX_MAX_NP 128
+#define MBX_CURVE_LEN 51          /* n_logpoint + 1, tester.py:204-205 pads to 51 */
+
+/* problem kinds */
+#define MBX_KIND_BBOB 0
+#define MBX_KIND_PROTEIN 1
+/* noise kinds (problem/bbob.py:108-146) */
+#define MBX_NOISE_NONE 0
+#define MBX_NOISE_GAUSS 1
+#define MBX_NOISE_UNIFORM 2
+#define MBX_NOISE_CAUCHY 3
+
+/* One problem instance.  Built on the host by metabox_b200/pack.py from the instance constants that
+ * problem/bbob.py:31-45 + the per-class constructors (bbob.py:149-890) or
+ * problem/protein_docking.py:163-181 produce; `off` is the instance's offset (in doubles) into the
+ * constants buffer.  BBOB constants layout at `off`:
+ *     shift[D] | R[D*D] | M2[D*D] | cv0[D] | cv1[D] | cv2[D] | (Gallagher) y[P*D] | C[P*D] | w[P]
+ * protein layout at `off`:
+ *     coor_init[300] | basis[12*300] | inv_sqrt_eig[12] | q[100] | e4[100] (= e_i^(1/4)) | r[100]   */
+typedef struct MbxInstance {
+    int32_t kind;          /* MBX_KIND_*                                         */
+    int32_t base;          /* BBOB base shape 1..24 (noisy ids map to their base) */
+    int32_t dim;
+    int32_t noise;         /* MBX_NOISE_*                                        */
+    int32_t n_peaks;       /* Gallagher: 101 / 21, else 0                        */
+    int32_t has_optimum;   /* 0 for protein (`optimum is None`)                  */
+    int32_t fid;           /* reference function id (1..24, 101..130), 0 protein */
+    int32_t pad_;
+    double lb, ub, bias, optimum;
+    double bh_coef;        /* boundaryHandling(x) = bh_coef * pen(x)             */
+    double n_alpha, n_beta, n_p;   /* noise parameters                           */
+    double sc[8];          /* function-specific scalars, see pack.py             */
+    int64_t off;
+} MbxInstance;
+
+/* Scalars of one optimizer configuration (config.py:74-102 + optimizer constructors). */
+typedef struct MbxRunConfig {
+    int32_t kind;          /* MBX_KIND_* of every lane in the launch             */
+    int32_t NP;            /* population size                                    */
+    int32_t dim;
+    int32_t maxFEs;
+    int32_t n_logpoint;    /* 50 (bbob) / 5 (protein)                            */
+    int32_t log_interval;  /* maxFEs // n_logpoint                               */
+    int32_t use_tape;      /* 1: random numbers are read from MbxTape (parity tests); 0: Philox */
+    int32_t pad_;
+    uint64_t seed;         /* Philox key                                         */
+} MbxRunConfig;
+
+const char* mbx_last_error(void);
+int mbx_version(void);
+/* size in bytes of MbxInstance / MbxRunConfig as compiled (ABI check for the ctypes mirror) */
+int mbx_sizeof_instance(void);
+int mbx_sizeof_runconfig(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Problem.eval  -- replaces Basic_Problem.eval / func (problem/basic_problem.py:12-37) for the
+ * BBOB classes (problem/bbob.py:149-890, noise mixins :96-146) and Protein_Docking.func
+ * (problem/protein_docking.py:28-48).
+ *   d_inst      [n_inst] MbxInstance,  d_consts  f64 constants buffer
+ *   d_lane_inst [B] int32: instance index of each lane
+ *   d_x         [B, NP, D] candidates, float32 (x_is_f64 = 0) or float64 (x_is_f64 = 1)
+ *   d_out       [B, NP]  f(x) as float32 / float64 (same width as x); raw f(x) incl. bias, i.e. what
+ *               `problem.eval(x)` returns;  if subtract_optimum != 0 returns eval(x) - optimum
+ *   noise: when the instance is noisy, draws come from Philox(seed, lane, gen) unless d_noise_tape
+ *          is non-null: [B, 3, NP] float64 in the reference draw order (uniforms, then normals).   */
+int mbx_eval(int kind, const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+             const void* d_x, int x_is_f64, void* d_out, int B, int NP, int D, int subtract_optimum,
+             uint64_t seed, uint32_t gen, const double* d_noise_tape, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RLEPSO backbone (PSO family) -- replaces RLEPSO_Optimizer.init_population / update
+ * (optimizer/rlepso_optimizer.py:39-65, 173-263) for B lanes at once.
+ * State (all device, updated in place):
+ *   x, v, pbest_x [B,NP,D] f32 ; c_cost, pbest [B,NP] f32 ; pni [B,NP] i32 (per_no_improve)
+ *   gbest_x [B,D] f32 ; gbest_val [B] f32 ; gbest_idx, no_improve, fes, log_index, curve_len, gen [B] i32
+ *   curve [B, MBX_CURVE_LEN] f32 ; done [B] u8                                                    */
+typedef struct MbxRlepsoState {
+    float *x, *v, *pbest_x, *c_cost, *pbest;
+    int32_t* pni;
+    float *gbest_x, *gbest_val;
+    int32_t *gbest_idx, *no_improve, *fes, *log_index, *curve_len, *gen;
+    float* curve;
+    uint8_t* done;
+} MbxRlepsoState;
+
+/* Recorded random draws for parity tests (all device, float64 / int32, may be null when use_tape=0):
+ *   init_pos_u, init_vel_u, clpso_u, fdr_u, reinit_pos_u, reinit_vel_u [B,NP,D] ; tour [B,NP,D,2] i32
+ *   rand1, rand2, reinit_u [B,NP] ; noise [B,2,3,NP] (pass 0 = main evaluation, pass 1 = re-init)   */
+typedef struct MbxRlepsoTape {
+    const double *init_pos_u, *init_vel_u, *clpso_u, *fdr_u, *reinit_pos_u, *reinit_vel_u;
+    const int32_t* tour;
+    const double *rand1, *rand2, *reinit_u, *noise;
+} MbxRlepsoTape;
+
+int mbx_rlepso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxRlepsoState* st, const MbxRlepsoTape* tape,
+                    float* d_feature /* [B,1] fes/maxFEs */, int B, void* stream);
+
+/* d_action [B,35] f32 in [0,1] ; outputs d_feature [B,1] f32, d_reward [B] f32 (+1/-1), st->done.
+ * d_pci [NP] f64 = the CLPSO learning-probability table (rlepso_optimizer.py:24-25).
+ * Lanes whose done flag is already set are skipped (outputs untouched).
+ * d_dbg (optional, may be null): [B, NP, D] int32 FDR target indices for index-parity tests.       */
+int mbx_rlepso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxRlepsoState* st, const MbxRlepsoTape* tape,
+                    const double* d_pci, const float* d_action, float* d_feature, float* d_reward,
+                    int32_t* d_dbg, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
+ * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
+ *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */
+int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                      const MbxRunConfig* cfg, const double* d_tape_u, int n_tape_iter,
+                      float* d_curve, int32_t* d_curve_len, int32_t* d_fes, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METABOX_B200_H */

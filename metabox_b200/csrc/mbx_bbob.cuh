@@ -1,0 +1,445 @@
+// mbx_bbob.cuh -- device fitness functions: the 24 BBOB base shapes (+ noise models) and the
+// protein-docking energy, one thread per candidate, float64 arithmetic in the reference's operation
+// order (reference: problem/bbob.py:6-8,51-93,108-146,149-890; problem/protein_docking.py:28-48).
+//
+// Calling convention: the CTA has staged the instance constants in shared memory (`C`, layout
+// shift|R|M2|cv0|cv1|cv2, see MbxInstance) and the candidate is reachable through an accessor
+// X(d) -> double.  `zs` is a per-thread scratch column in shared memory: element k at zs[k*NT]
+// (bank-conflict free).  Loops containing libm calls are kept rolled (code size); D*D mat-vecs are
+// fully unrolled over d with the operand vector in registers and R rows broadcast from smem.
+#pragma once
+#include "mbx_common.cuh"
+
+struct XF32 {
+    const float* p;
+    __device__ __forceinline__ double operator()(int d) const { return (double)p[d]; }
+};
+struct XF64 {
+    const double* p;
+    __device__ __forceinline__ double operator()(int d) const { return p[d]; }
+};
+
+template <int D>
+struct ConstView {          // shared-memory views of one BBOB instance
+    const double *s, *R, *M2, *cv0, *cv1, *cv2;
+    __device__ __forceinline__ ConstView(const double* C)
+        : s(C), R(C + D), M2(C + D + D * D), cv0(C + D + 2 * D * D), cv1(C + 2 * D + 2 * D * D), cv2(C + 3 * D + 2 * D * D) {}
+    static constexpr int kDoubles = 4 * D + 2 * D * D;
+};
+
+__device__ __forceinline__ double t_osz(double x) {       // bbob.py:51-67
+    double ax = fabs(x);
+    double t = log(ax) / 0.1;
+    double c1 = x > 0. ? 1.0 : 0.55, c2 = x > 0. ? 0.79 : 0.31;
+    double r = pow(exp(t + 0.49 * (sin(c1 * t) + sin(c2 * t))), 0.1);
+    return x > 0. ? r : (x < 0. ? -r : x);
+}
+__device__ __forceinline__ double t_asy(double x, double beta, double frac) {   // bbob.py:70-82
+    return x > 0. ? pow(x, 1. + beta * frac * sqrt(x)) : x;
+}
+template <int D, class XA>
+__device__ __forceinline__ double pen_x(const XA& X, double ub) {               // bbob.py:85-93
+    double p = 0.;
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {
+        double t = fmax(0., fabs(X(d)) - ub);
+        p += t * t;
+    }
+    return p;
+}
+// zs[k] = sum_d M[k][d] * y[d]   (M row-major in smem, y in registers)
+template <int D, int NT>
+__device__ __forceinline__ void matvec(const double* __restrict__ M, const double (&y)[D], double* zs) {
+#pragma unroll 2
+    for (int k = 0; k < D; ++k) {
+        const double* row = M + k * D;
+        double a0 = 0., a1 = 0.;
+#pragma unroll
+        for (int d = 0; d + 1 < D; d += 2) {
+            a0 = fma(row[d], y[d], a0);
+            a1 = fma(row[d + 1], y[d + 1], a1);
+        }
+        if (D & 1) a0 = fma(row[D - 1], y[D - 1], a0);
+        zs[k * NT] = a0 + a1;
+    }
+}
+template <int D, int NT>
+__device__ __forceinline__ void load_col(double (&y)[D], const double* zs) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) y[d] = zs[d * NT];
+}
+template <int D, int NT>
+__device__ __forceinline__ double rastrigin_sum(const double* zs) {
+    double sc = 0., sq = 0.;
+#pragma unroll 1
+    for (int k = 0; k < D; ++k) {
+        double z = zs[k * NT];
+        sc += cos(6.283185307179586 * z);
+        sq += z * z;
+    }
+    return 10. * ((double)D - sc) + sq;
+}
+template <int D, int NT>
+__device__ __forceinline__ double rosen_sum(const double* zs) {
+    double f = 0.;
+#pragma unroll 1
+    for (int k = 0; k + 1 < D; ++k) {
+        double a = zs[k * NT], b = zs[(k + 1) * NT];
+        double u = a * a - b, w = a - 1.;
+        f += 100. * (u * u) + w * w;
+    }
+    return f;
+}
+
+// Noise-free f(x) incl. bias and boundary handling  (== BBOB_Basic_Problem.func)
+template <int D, int NT, class XA>
+__device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, const double* __restrict__ G,
+                            const XA& X, double* zs) {
+    ConstView<D> c(C);
+    const double bias = h.bias, ub = h.ub;
+    double y[D];
+    const int base = h.base;
+    double bh = 0.;
+    if (h.bh_coef != 0.) {
+        double p = pen_x<D>(X, ub);
+        bh = (h.bh_coef == 1.) ? p : h.bh_coef * p;
+    }
+    // ---------------------------------------------------------------- first linear map
+    if (base == 9 || base == 19) {                       // z = M2 x + 0.5   (bbob.py:434, :703)
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = X(d);
+        matvec<D, NT>(c.M2, y, zs);
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) zs[k * NT] += 0.5;
+    } else if (base == 5 || base == 20) {
+        // no rotation
+    } else if (base == 24) {                             // z = R (2 sign(s) x - mu0)   (bbob.py:885-886)
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = c.cv2[d] * X(d) - h.sc[0];
+        matvec<D, NT>(c.R, y, zs);
+    } else if (base == 8) {                              // R = I (bbob.py:362)
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) zs[d * NT] = X(d) - c.s[d];
+    } else if (base != 21 && base != 22) {               // z = R (x - s)   (bbob.py:6-8)
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = X(d) - c.s[d];
+        matvec<D, NT>(c.R, y, zs);
+    }
+    // ---------------------------------------------------------------- per-shape tails
+    switch (base) {
+    case 1: {                                            // Sphere bbob.py:156-159
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) { double z = zs[k * NT]; f += z * z; }
+        return f + bias + bh;
+    }
+    case 2: case 10: {                                   // Ellipsoidal bbob.py:220-226, 447-453
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) { double z = t_osz(zs[k * NT]); f += c.cv0[k] * (z * z); }
+        return f + bias + bh;
+    }
+    case 3: {                                            // Rastrigin bbob.py:240-243
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) zs[k * NT] = c.cv0[k] * t_asy(t_osz(zs[k * NT]), 0.2, c.cv1[k]);
+        return rastrigin_sum<D, NT>(zs) + bias;
+    }
+    case 4: {                                            // Buche-Rastrigin bbob.py:258-265
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            double z = t_osz(zs[k * NT]);
+            if (!(k & 1) && z > 0.) z *= 10.;
+            zs[k * NT] = z * c.cv0[k];
+        }
+        double r = rastrigin_sum<D, NT>(zs);
+        return r + 100. * pen_x<D>(X, ub) + bias;
+    }
+    case 5: {                                            // Linear slope bbob.py:281-287
+        double f = 0.;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            double x = X(d), z = x;
+            if (x * c.s[d] > ub * ub) z = (z > 0. ? 1. : (z < 0. ? -1. : 0.)) * ub;
+            double s = c.cv0[d];
+            f += ub * fabs(s) - z * s;
+        }
+        return f + bias;
+    }
+    case 6: {                                            // Attractive sector bbob.py:302-307
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            double z = zs[k * NT];
+            if (z * c.s[k] > 0.) z *= 100.;
+            f += z * z;
+        }
+        return pow(t_osz(f), 0.9) + bias;
+    }
+    case 7: {                                            // Step ellipsoidal bbob.py:320-325
+        double zh0 = fabs(zs[0]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double zh = zs[d * NT];
+            y[d] = fabs(zh) > 0.5 ? floor(0.5 + zh) : floor(0.5 + 10. * zh) / 10.;
+        }
+        matvec<D, NT>(c.M2, y, zs);
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) { double z = zs[k * NT]; f += c.cv0[k] * (z * z); }
+        return 0.1 * fmax(zh0 / 1e4, f) + bh + bias;
+    }
+    case 8: {                                            // Rosenbrock bbob.py:365-368
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) zs[k * NT] = h.sc[0] * zs[k * NT] + 1.;
+        return rosen_sum<D, NT>(zs) + bias + bh;
+    }
+    case 9:                                              // Rosenbrock rotated bbob.py:432-435
+        return rosen_sum<D, NT>(zs) + bias;
+    case 11: {                                           // Discus bbob.py:498-502
+        double z0 = t_osz(zs[0]);
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 1; k < D; ++k) { double z = t_osz(zs[k * NT]); f += z * z; }
+        return 1e6 * (z0 * z0) + f + bias;
+    }
+    case 12: {                                           // Bent cigar bbob.py:517-522
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * NT], 0.5, c.cv1[d]);
+        matvec<D, NT>(c.R, y, zs);
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 1; k < D; ++k) { double z = zs[k * NT]; f += 1e6 * (z * z); }
+        double z0 = zs[0];
+        return z0 * z0 + f + bias;
+    }
+    case 13: {                                           // Sharp ridge bbob.py:537-540
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 1; k < D; ++k) { double z = zs[k * NT]; f += z * z; }
+        double z0 = zs[0];
+        return z0 * z0 + 100. * sqrt(f) + bias;
+    }
+    case 14: {                                           // Different powers bbob.py:550-554
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) f += pow(fabs(zs[k * NT]), c.cv0[k]);
+        return pow(f, 0.5) + bias + bh;
+    }
+    case 15: {                                           // Rastrigin F15 bbob.py:597-602
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) zs[d * NT] = t_asy(t_osz(zs[d * NT]), 0.2, c.cv1[d]);
+        load_col<D, NT>(y, zs);
+        matvec<D, NT>(c.M2, y, zs);
+        return rastrigin_sum<D, NT>(zs) + bias;
+    }
+    case 16: {                                           // Weierstrass bbob.py:620-625
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) zs[d * NT] = t_osz(zs[d * NT]);
+        load_col<D, NT>(y, zs);
+        matvec<D, NT>(c.M2, y, zs);
+        double tot = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            double base2pi = 6.283185307179586 * (zs[k * NT] + 0.5);
+            double inner = 0., a = 1., b = 1.;
+#pragma unroll 1
+            for (int j = 0; j < 12; ++j) {
+                inner += a * cos(base2pi * b);
+                a *= 0.5; b *= 3.;
+            }
+            tot += inner;
+        }
+        double m = tot / (double)D - h.sc[0];
+        return 10. * (m * m * m) + (10. / (double)D) * pen_x<D>(X, ub) + bias;
+    }
+    case 17: case 18: {                                  // Schaffers bbob.py:639-645
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * NT], 0.5, c.cv1[d]);
+        matvec<D, NT>(c.M2, y, zs);
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k + 1 < D; ++k) {
+            double a = zs[k * NT], b = zs[(k + 1) * NT];
+            double s = sqrt(a * a + b * b);
+            double sn = sin(50. * pow(s, 0.2));
+            f += sqrt(s) * (sn * sn + 1.);
+        }
+        double m = (1. / (double)(D - 1)) * f;
+        return m * m + bh + bias;
+    }
+    case 19: {                                           // Griewank-Rosenbrock bbob.py:701-705
+        double f = 0.;
+#pragma unroll 1
+        for (int k = 0; k + 1 < D; ++k) {
+            double a = zs[k * NT], b = zs[(k + 1) * NT];
+            double u = a * a - b, w = 1. - a;
+            double s = 100. * (u * u) + w * w;
+            f += s / 4000. - cos(s);
+        }
+        double fac = h.sc[0];
+        return fac + fac * f / ((double)D - 1.) + bias + bh;
+    }
+    case 20: {                                           // Schwefel bbob.py:751-759
+        double f = 0., pen = 0., prev = 0.;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            double z0 = c.cv2[d] * X(d);
+            double z = z0;
+            if (d > 0) z += 0.25 * (prev - c.cv1[d - 1]);
+            prev = z0;
+            z = 100. * (c.cv0[d] * (z - c.cv1[d]) + c.cv1[d]);
+            f += z * sin(sqrt(fabs(z)));
+            double t = fmax(0., fabs(z / 100.) - ub);
+            pen += t * t;
+        }
+        return 4.189828872724339 - 0.01 * (f / (double)D) + 100. * pen + bias;
+    }
+    case 21: case 22: {                                  // Gallagher bbob.py:795-799
+        const int P = h.n_peaks;
+        const double* gy = G + ConstView<D>::kDoubles;
+        const double* gC = gy + P * D;
+        const double* gw = gC + P * D;
+        const double coef = -0.5 / (double)D;
+        double g = -1e300;
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = X(d) - __ldg(gy + p * D + d);
+            double acc = 0.;
+#pragma unroll 2
+            for (int k = 0; k < D; ++k) {
+                const double* row = c.R + k * D;
+                double a0 = 0., a1 = 0.;
+#pragma unroll
+                for (int d = 0; d + 1 < D; d += 2) {
+                    a0 = fma(row[d], y[d], a0);
+                    a1 = fma(row[d + 1], y[d + 1], a1);
+                }
+                if (D & 1) a0 = fma(row[D - 1], y[D - 1], a0);
+                double z = a0 + a1;
+                acc += __ldg(gC + p * D + k) * (z * z);
+            }
+            g = fmax(g, __ldg(gw + p) * exp(coef * acc));
+        }
+        double t = t_osz(10. - g);
+        return t * t + bias + bh;
+    }
+    case 23: {                                           // Katsuura bbob.py:855-866
+        double prod = 1.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            double z = zs[k * NT], acc = 0., p2 = 2.;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                double t = p2 * z;
+                acc += fabs(t - floor(t + 0.5)) / p2;
+                p2 *= 2.;
+            }
+            prod *= pow(1. + (double)(k + 1) * acc, h.sc[0]);
+        }
+        return prod * h.sc[1] - h.sc[1] + pen_x<D>(X, ub) + bias;
+    }
+    case 24: {                                           // Lunacek bbob.py:883-890
+        double s1 = 0., s2 = 0.;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            double xh = c.cv2[d] * X(d);
+            double a = xh - h.sc[0], b = xh - h.sc[2];
+            s1 += a * a; s2 += b * b;
+        }
+        double sc = 0.;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) sc += cos(6.283185307179586 * zs[k * NT]);
+        return fmin(s1, (double)D + h.sc[1] * s2) + 10. * ((double)D - sc) + 1e4 * pen_x<D>(X, ub) + bias;
+    }
+    }
+    return 0.;
+}
+
+// Noise models bbob.py:108-146.  u1,u2 uniforms / n1,n2 normals in the reference's draw order.
+__device__ __forceinline__ double bbob_noise(const MbxInstance& h, double ftrue, double d0, double d1, double d2) {
+    if (h.noise == MBX_NOISE_NONE) return ftrue;
+    double u = ftrue - h.optimum, v;
+    if (h.noise == MBX_NOISE_GAUSS) {
+        v = u * exp(h.n_beta * d0);
+    } else if (h.noise == MBX_NOISE_UNIFORM) {
+        double a = (h.n_beta == 1.) ? d0 : pow(d0, h.n_beta);
+        v = u * a * fmax(1., pow(1e9 / (u + 1e-99), h.n_alpha * (0.49 + 1. / (double)h.dim) * d1));
+    } else {
+        v = u + h.n_alpha * fmax(0., 1e3 + (d0 < h.n_p ? 1. : 0.) * d1 / (fabs(d2) + 1e-199));
+    }
+    return (u >= 1e-8) ? (v + h.optimum + 1.01 * 1e-8) : ftrue;
+}
+// Philox draws for one candidate of a noisy evaluation (numpy twin: oracle/rlepso.py philox_noise)
+__device__ __forceinline__ void noise_draws(const Philox& ph, int kind, uint32_t i, uint32_t gen, uint32_t lane, uint32_t tag,
+                                            double& d0, double& d1, double& d2) {
+    d0 = d1 = d2 = 0.;
+    if (kind == MBX_NOISE_NONE) return;
+    uint4 w = ph(i, gen, lane, tag);
+    if (kind == MBX_NOISE_GAUSS) { double t; box_muller(w.x, w.y, d0, t); }
+    else if (kind == MBX_NOISE_UNIFORM) { d0 = u01(w.x); d1 = u01(w.y); }
+    else { d0 = u01(w.x); box_muller(w.y, w.z, d1, d2); }
+}
+
+// ------------------------------------------------------------------------------------- protein
+// Protein_Docking.func protein_docking.py:28-48.  Constants in smem: coor_init[300] | basis[12*300] |
+// inv_sqrt_eig[12] | q[100] | e4[100] (= e_i^(1/4), so sqrt(e_ij) = e4_i*e4_j) | r[100].
+// ONE WARP per candidate: the 300 coordinates are built cooperatively into a per-warp smem block
+// (SoA cx|cy|cz|p2, 400 doubles), then the 4950 unordered atom pairs are strided over the 32 lanes
+// (rows i and 99-i are paired so every lane-step is useful) and the partial sums are combined with a
+// shuffle reduction.  The reference sums all ordered pairs; the matrix is symmetric and the diagonal
+// is masked out (d = 0.1 < 0.11), so energy = 2 * sum_{i<j} / 100.
+#define MBX_PROT_ATOMS 100
+#define MBX_PROT_DOUBLES (300 + 12 * 300 + 12 + 300)
+#define MBX_PROT_WARP_SCRATCH 400
+template <class XA>
+__device__ double protein_energy_warp(const double* __restrict__ C, const XA& X, double* ws, int lane) {
+    const double* coor0 = C;
+    const double* basis = C + 300;
+    const double* ise = C + 300 + 3600;
+    const double* q = ise + 12;
+    const double* e4 = q + 100;
+    const double* r = e4 + 100;
+    double xs[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) xs[k] = X(k) * ise[k];
+    __syncwarp();
+    for (int a = lane; a < 300; a += 32) {
+        double acc = 0.;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc = fma(xs[k], basis[k * 300 + a], acc);
+        int atom = a / 3, comp = a - atom * 3;
+        ws[comp * 100 + atom] = acc + coor0[a];
+    }
+    __syncwarp();
+    for (int a = lane; a < 100; a += 32) {
+        double x = ws[a], y = ws[100 + a], z = ws[200 + a];
+        ws[300 + a] = x * x + y * y + z * z;
+    }
+    __syncwarp();
+    double part = 0.;
+#pragma unroll 1
+    for (int p = lane; p < 4950; p += 32) {
+        int cidx = p / 99, t = p - cidx * 99;
+        int i, j;
+        if (t < 99 - cidx) { i = cidx; j = cidx + 1 + t; }
+        else { i = 99 - cidx; j = i + 1 + (t - (99 - cidx)); }
+        double p3 = fma(ws[i], ws[j], fma(ws[100 + i], ws[100 + j], ws[200 + i] * ws[200 + j]));
+        double d = sqrt(ws[300 + i] - 2. * p3 + ws[300 + j] + 0.01);
+        bool near = (d > 0.11) && (d < 7.0);
+        bool far = (d > 7.0) && (d < 9.0);
+        if (near || far) {
+            double rr = (r[i] + r[j]) / 2.;
+            double t1 = rr / d;
+            double t2 = t1 * t1, t6 = t2 * t2 * t2;
+            double coeff = (q[i] * q[j]) / (4. * d) + (e4[i] * e4[j]) * (t6 * t6 - t6);
+            double term = 10. * coeff;
+            if (far) { double g = 9. - d; term = term * (g * g * (-12. + 2. * d) / 8.); }
+            part += term;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncwarp();
+    return 2. * part / (double)MBX_PROT_ATOMS;
+}

@@ -1,0 +1,90 @@
+// mbx_capi.cu -- the extern "C" boundary declared in include/metabox_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include "mbx_launch.h"
+
+static thread_local char g_err[512] = "";
+
+void mbx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define MBX_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            mbx_set_error(__VA_ARGS__); \
+            return MBX_EINVAL;          \
+        }                               \
+    } while (0)
+
+extern "C" {
+
+const char* mbx_last_error(void) { return g_err; }
+int mbx_version(void) { return 100; }
+int mbx_sizeof_instance(void) { return (int)sizeof(MbxInstance); }
+int mbx_sizeof_runconfig(void) { return (int)sizeof(MbxRunConfig); }
+
+int mbx_eval(int kind, const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const void* d_x,
+             int x_is_f64, void* d_out, int B, int NP, int D, int subtract_optimum, uint64_t seed, uint32_t gen,
+             const double* d_noise_tape, void* stream) {
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && d_x && d_out, "mbx_eval: null pointer");
+    MBX_REQUIRE(B >= 0 && NP >= 0 && D > 0 && D <= MBX_MAX_DIM, "mbx_eval: bad shape B=%d NP=%d D=%d", B, NP, D);
+    if (B == 0 || NP == 0) return MBX_OK;                       // empty input: nothing to do
+    MBX_REQUIRE(B <= 65535, "mbx_eval: B=%d exceeds gridDim.y; split the call", B);
+    return mbx_launch_eval(kind, D, x_is_f64, d_inst, d_consts, d_lane_inst, d_x, d_out, B, NP, subtract_optimum, seed, gen,
+                           d_noise_tape, (cudaStream_t)stream);
+}
+
+static int check_cfg(const char* who, const MbxRunConfig* cfg, int B) {
+    MBX_REQUIRE(cfg, "%s: null config", who);
+    MBX_REQUIRE(cfg->NP >= 5 && cfg->NP <= MBX_MAX_NP, "%s: NP=%d outside [5,%d]", who, cfg->NP, MBX_MAX_NP);
+    MBX_REQUIRE(cfg->dim > 0 && cfg->dim <= MBX_MAX_DIM, "%s: dim=%d", who, cfg->dim);
+    MBX_REQUIRE(cfg->maxFEs > 0 && cfg->n_logpoint > 0 && cfg->n_logpoint + 1 <= MBX_CURVE_LEN && cfg->log_interval > 0,
+                "%s: bad maxFEs/n_logpoint/log_interval", who);
+    MBX_REQUIRE(B >= 0, "%s: B=%d", who, B);
+    return MBX_OK;
+}
+
+int mbx_rlepso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxRlepsoState* st, const MbxRlepsoTape* tape, float* d_feature, int B, void* stream) {
+    int rc = check_cfg("mbx_rlepso_init", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_feature, "mbx_rlepso_init: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_pos_u && tape->init_vel_u), "mbx_rlepso_init: use_tape without tape");
+    if (B == 0) return MBX_OK;
+    return mbx_launch_rlepso_init(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_feature, B, (cudaStream_t)stream);
+}
+
+int mbx_rlepso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxRlepsoState* st, const MbxRlepsoTape* tape, const double* d_pci, const float* d_action,
+                    float* d_feature, float* d_reward, int32_t* d_dbg, int B, void* stream) {
+    int rc = check_cfg("mbx_rlepso_step", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_pci && d_action && d_feature && d_reward,
+                "mbx_rlepso_step: null pointer");
+    MBX_REQUIRE(cfg->NP % 5 == 0, "mbx_rlepso_step: NP=%d must be a multiple of the 5 coefficient groups", cfg->NP);
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->clpso_u && tape->fdr_u && tape->tour && tape->rand1 && tape->rand2 &&
+                                   tape->reinit_u && tape->reinit_pos_u && tape->reinit_vel_u),
+                "mbx_rlepso_step: use_tape without a complete tape");
+    if (B == 0) return MBX_OK;
+    return mbx_launch_rlepso_step(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_pci, d_action, d_feature,
+                                  d_reward, d_dbg, B, (cudaStream_t)stream);
+}
+
+int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                      const double* d_tape_u, int n_tape_iter, float* d_curve, int32_t* d_curve_len, int32_t* d_fes, int B,
+                      void* stream) {
+    int rc = check_cfg("mbx_random_search", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && d_curve && d_curve_len && d_fes, "mbx_random_search: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (d_tape_u && n_tape_iter * cfg->NP >= cfg->maxFEs),
+                "mbx_random_search: tape shorter than the episode");
+    if (B == 0) return MBX_OK;
+    return mbx_launch_rs(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, d_tape_u, n_tape_iter, d_curve, d_curve_len, d_fes, B,
+                         (cudaStream_t)stream);
+}
+
+}  // extern "C"

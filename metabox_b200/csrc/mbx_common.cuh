@@ -1,0 +1,90 @@
+// mbx_common.cuh -- shared device helpers: Philox4x32-10, block reductions, smem staging.
+// Compiled with -fmad=false: every a*b+c written in source stays two IEEE operations (bit-identical
+// to the numpy ufunc chain of the reference); fused multiply-adds are requested explicitly with fma().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/metabox_b200.h"
+
+#define MBX_NT 128                 // threads per CTA for the population kernels (one CTA = one lane)
+
+// ---- draw-group tags (numpy twin: oracle/rng.py) -------------------------------------------------
+#define MBX_TAG_INIT 1u
+#define MBX_TAG_PD 2u
+#define MBX_TAG_P 3u
+#define MBX_TAG_REINIT 4u
+#define MBX_TAG_NOISE 5u
+#define MBX_TAG_NOISE2 6u
+#define MBX_TAG_LDE_P 7u
+#define MBX_TAG_LDE_PD 8u
+#define MBX_TAG_LDE_REJ 9u
+#define MBX_TAG_DDQN 10u
+#define MBX_TAG_DDQN_D 11u
+#define MBX_GEN_INIT 0xFFFFFFFFu
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    // counter = (index, generation, lane, tag)
+    __device__ __forceinline__ uint4 operator()(uint32_t idx, uint32_t gen, uint32_t lane, uint32_t tag) const {
+        uint32_t c0 = idx, c1 = gen, c2 = lane, c3 = tag, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+__device__ __forceinline__ double u01(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+__device__ __forceinline__ int bounded(uint32_t w, int high) { return (int)__umulhi(w, (uint32_t)high); }
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& n0, double& n1) {
+    double ua = ((double)wa + 1.0) * (1.0 / 4294967296.0);
+    double ub = (double)wb * (1.0 / 4294967296.0);
+    double r = sqrt(-2.0 * log(ua));
+    double t = 6.283185307179586 * ub;
+    double s, c;
+    sincos(t, &s, &c);
+    n0 = r * c; n1 = r * s;
+}
+
+// (value, index) lexicographic minimum == np.argmin first-occurrence rule
+__device__ __forceinline__ void argmin_pair(float& v, int& i, float ov, int oi) {
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void warp_argmin(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        argmin_pair(v, i, ov, oi);
+    }
+}
+// block-wide argmin over NT threads; sbuf needs NT/32 floats + NT/32 ints; result valid in all threads
+template <int NT>
+__device__ __forceinline__ void block_argmin(float& v, int& i, float* sv, int* si) {
+    warp_argmin(v, i);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { sv[w] = v; si[w] = i; }
+    __syncthreads();
+    v = sv[0]; i = si[0];
+#pragma unroll
+    for (int k = 1; k < NT / 32; ++k) argmin_pair(v, i, sv[k], si[k]);
+}
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float* sv) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sv[w] = v;
+    __syncthreads();
+    v = sv[0];
+#pragma unroll
+    for (int k = 1; k < NT / 32; ++k) v = fmaxf(v, sv[k]);
+    return v;
+}

@@ -1,0 +1,88 @@
+// mbx_eval.cuh -- CTA-cooperative evaluation of a tile of candidates + constant staging.
+// Shared by the stand-alone eval kernel and the fused optimizer kernels.
+#pragma once
+#include "mbx_bbob.cuh"
+
+template <int D, int KIND>
+struct EvalTraits {
+    static constexpr int kConstDoubles = (KIND == MBX_KIND_PROTEIN) ? MBX_PROT_DOUBLES : ConstView<D>::kDoubles;
+    // scratch doubles a CTA of MBX_NT threads needs while evaluating
+    static constexpr int kScratchDoubles =
+        (KIND == MBX_KIND_PROTEIN) ? (MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : D * MBX_NT;
+};
+
+// cooperative copy of the instance header + constants into shared memory
+template <int D, int KIND>
+__device__ __forceinline__ void stage_instance(const MbxInstance* __restrict__ inst, const double* __restrict__ consts,
+                                               MbxInstance* sh, double* sC) {
+    const int n = EvalTraits<D, KIND>::kConstDoubles;
+    const double* src = consts + inst->off;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sC[k] = __ldg(src + k);
+    const int* hs = reinterpret_cast<const int*>(inst);
+    int* hd = reinterpret_cast<int*>(sh);
+    for (int k = threadIdx.x; k < (int)(sizeof(MbxInstance) / 4); k += blockDim.x) hd[k] = hs[k];
+}
+
+// Evaluate candidates [0,n) of a shared-memory tile (row-major [n][D], element type TX) and write
+// cost = f(x) (- optimum) with noise into out (float32 if OUT32 else float64).  All threads of the
+// CTA must call this (it contains barriers for the protein path only through __syncwarp).
+//   noise_tape : per-candidate draws [3][stride] (d0,d1,d2) or nullptr -> Philox(seed, lane, gen, tag)
+template <int D, int KIND, class TX, class TO>
+__device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double* sC, const double* gC,
+                                              const TX* tile, int n, int row0, double* scratch, TO* out,
+                                              bool subtract_opt, const Philox& ph, uint32_t gen, uint32_t lane,
+                                              uint32_t tag, const double* noise_tape, int tape_stride,
+                                              const unsigned char* only_mask = nullptr) {
+    if (KIND == MBX_KIND_PROTEIN) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        double* ws = scratch + w * MBX_PROT_WARP_SCRATCH;
+        for (int i = w; i < n; i += (MBX_NT >> 5)) {
+            if (only_mask && !only_mask[i]) continue;
+            double e;
+            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l); }
+            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l); }
+            if (l == 0) out[i] = (TO)e;
+        }
+    } else {
+        const int i = threadIdx.x;
+        if (i < n && !(only_mask && !only_mask[i])) {
+            double f;
+            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; f = bbob_true<D, MBX_NT>(h, sC, gC, X, scratch + i); }
+            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; f = bbob_true<D, MBX_NT>(h, sC, gC, X, scratch + i); }
+            if (h.noise != MBX_NOISE_NONE) {
+                double d0, d1, d2;
+                if (noise_tape) {
+                    d0 = noise_tape[row0 + i]; d1 = noise_tape[tape_stride + row0 + i]; d2 = noise_tape[2 * tape_stride + row0 + i];
+                } else {
+                    noise_draws(ph, h.noise, (uint32_t)(row0 + i), gen, lane, tag, d0, d1, d2);
+                }
+                f = bbob_noise(h, f, d0, d1, d2);
+            }
+            if (subtract_opt && h.has_optimum) f = f - h.optimum;
+            out[i] = (TO)f;
+        }
+    }
+}
+
+// =====================================================================================================
+// shared-memory plan of the population kernels
+// =====================================================================================================
+template <int D, int KIND>
+struct PopSmem {
+    static constexpr int NPMAX = MBX_MAX_NP;
+    static constexpr int kConst = EvalTraits<D, KIND>::kConstDoubles;
+    static constexpr int kRegionA = (EvalTraits<D, KIND>::kScratchDoubles > NPMAX * D) ? EvalTraits<D, KIND>::kScratchDoubles : NPMAX * D;
+    // byte offsets
+    static constexpr size_t oHdr = 0;
+    static constexpr size_t oConst = sizeof(MbxInstance);
+    static constexpr size_t oA = oConst + sizeof(double) * kConst;           // px64 / eval scratch
+    static constexpr size_t oPer = oA + sizeof(double) * kRegionA;           // 10 per-particle double arrays
+    static constexpr size_t oGx = oPer + sizeof(double) * 10 * NPMAX;        // gbest_x as double [D]
+    static constexpr size_t oXs = oGx + sizeof(double) * MBX_MAX_DIM;        // new positions f32 [NP*D]
+    static constexpr size_t oF = oXs + sizeof(float) * NPMAX * D;            // 4 per-particle float arrays
+    static constexpr size_t oI = oF + sizeof(float) * 4 * NPMAX;             // 2 per-particle int arrays
+    static constexpr size_t oTgt = oI + sizeof(int) * 2 * NPMAX;             // FDR targets u8 [NP*D] + masks u8 [2*NP]
+    static constexpr size_t oRed = oTgt + NPMAX * D + 2 * NPMAX;             // reduction scratch
+    static constexpr size_t kBytes = ((oRed + 64 + 15) / 16) * 16;
+};
+

@@ -1,0 +1,28 @@
+// mbx_launch.h -- host-side glue shared by the .cu translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/metabox_b200.h"
+
+void mbx_set_error(const char* fmt, ...);
+
+#define MBX_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            mbx_set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return MBX_ECUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+int mbx_launch_eval(int kind, int D, int x_is_f64, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                    const void* x, void* out, int B, int NP, int subtract_opt, uint64_t seed, uint32_t gen,
+                    const double* noise_tape, cudaStream_t st);
+int mbx_launch_rs(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                  const double* tape_u, int n_tape_iter, float* curve, int32_t* curve_len, int32_t* fes, int B, cudaStream_t st);
+int mbx_launch_rlepso_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlepsoState* s, const MbxRlepsoTape* tape, float* feature, int B,
+                           cudaStream_t st);
+int mbx_launch_rlepso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci,
+                           const float* action, float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st);

@@ -1,0 +1,352 @@
+// mbx_rlepso.cu -- fused RLEPSO generation (PSO family): velocity components (CLPSO tournament, FDR
+// argmin, gbest, pbest) -> clip -> position -> fitness -> pbest/gbest -> patience -> stochastic
+// re-initialisation -> cost-curve log, one CTA per lane, state float32 in HBM / float64 in registers.
+// Reference: optimizer/rlepso_optimizer.py:39-65 (init_population), :76-132 (velocity parts,
+// coefficients), :134-168 (re-init), :173-263 (update).  numpy twin: oracle/rlepso.py.
+#include "mbx_eval.cuh"
+#include "mbx_launch.h"
+
+#define FDR_IB 4      // particles per thread in the FDR scan (register blocking over i)
+
+template <int D, int KIND>
+struct RlepsoViews {
+    using L = PopSmem<D, KIND>;
+    MbxInstance* h;
+    double *sC, *A, *pf64, *cw, *c1, *c2, *c3, *c4, *cm, *r1, *r2, *ur, *gx;
+    float *xs, *pf32, *nc, *cc, *tmpf;
+    int *pni, *tmpi;
+    unsigned char *tgt, *mask, *better;
+    float* redv;
+    int* redi;
+    __device__ __forceinline__ RlepsoViews(unsigned char* s) {
+        h = reinterpret_cast<MbxInstance*>(s + L::oHdr);
+        sC = reinterpret_cast<double*>(s + L::oConst);
+        A = reinterpret_cast<double*>(s + L::oA);
+        double* per = reinterpret_cast<double*>(s + L::oPer);
+        const int N = L::NPMAX;
+        pf64 = per; cw = per + N; c1 = per + 2 * N; c2 = per + 3 * N; c3 = per + 4 * N; c4 = per + 5 * N;
+        cm = per + 6 * N; r1 = per + 7 * N; r2 = per + 8 * N; ur = per + 9 * N;
+        gx = reinterpret_cast<double*>(s + L::oGx);
+        xs = reinterpret_cast<float*>(s + L::oXs);
+        float* f = reinterpret_cast<float*>(s + L::oF);
+        pf32 = f; nc = f + N; cc = f + 2 * N; tmpf = f + 3 * N;
+        int* ii = reinterpret_cast<int*>(s + L::oI);
+        pni = ii; tmpi = ii + N;
+        tgt = s + L::oTgt; mask = tgt + N * D; better = mask + N;
+        redv = reinterpret_cast<float*>(s + L::oRed);
+        redi = reinterpret_cast<int*>(s + L::oRed + 32);
+    }
+};
+
+// cost-curve protocol shared by all optimizers (rlepso_optimizer.py:241-261)
+__device__ __forceinline__ bool log_and_done(const MbxRunConfig& cfg, bool has_opt, int fes, float gbest, int& log_index,
+                                             int& clen, float* curve) {
+    if (fes >= log_index * cfg.log_interval) {
+        log_index += 1;
+        if (clen < MBX_CURVE_LEN) curve[clen] = gbest;
+        clen = min(clen + 1, MBX_CURVE_LEN);
+    }
+    bool done = has_opt ? (fes >= cfg.maxFEs || (double)gbest <= 1e-8) : (fes >= cfg.maxFEs);
+    if (done) {
+        if (clen >= cfg.n_logpoint + 1) curve[clen - 1] = gbest;
+        else { curve[clen] = gbest; clen += 1; }
+    }
+    return done;
+}
+
+// =====================================================================================================
+template <int D, int KIND>
+__global__ void __launch_bounds__(MBX_NT)
+rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
+                   MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, float* __restrict__ feature) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RlepsoViews<D, KIND> V(smem_raw);
+    const int b = blockIdx.x, NP = cfg.NP, tid = threadIdx.x;
+    const MbxInstance* gi = inst + lane_inst[b];
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    __syncthreads();
+    const MbxInstance& h = *V.h;
+    Philox ph(cfg.seed);
+    const double lb = h.lb, ub = h.ub, vmax = 0.1 * (ub - lb);
+    const size_t base = (size_t)b * NP * D;
+    for (int e = tid; e < NP * D; e += MBX_NT) {
+        double up, uv;
+        if (cfg.use_tape) { up = T.init_pos_u[base + e]; uv = T.init_vel_u[base + e]; }
+        else { uint4 w = ph((uint32_t)e, MBX_GEN_INIT, (uint32_t)b, MBX_TAG_INIT); up = u01(w.x); uv = u01(w.y); }
+        float p = (float)(lb + (ub - lb) * up);
+        float v = (float)(-vmax + (vmax - (-vmax)) * uv);
+        V.xs[e] = p;
+        S.x[base + e] = p; S.pbest_x[base + e] = p; S.v[base + e] = v;
+    }
+    __syncthreads();
+    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, MBX_GEN_INIT, (uint32_t)b,
+                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP);
+    __syncthreads();
+    float v = INFINITY; int ix = tid;
+    if (tid < NP) {
+        v = V.nc[tid];
+        S.c_cost[(size_t)b * NP + tid] = v; S.pbest[(size_t)b * NP + tid] = v; S.pni[(size_t)b * NP + tid] = 0;
+    }
+    block_argmin<MBX_NT>(v, ix, V.redv, V.redi);
+    for (int d = tid; d < D; d += MBX_NT) S.gbest_x[(size_t)b * D + d] = V.xs[ix * D + d];
+    if (tid == 0) {
+        S.gbest_val[b] = v; S.gbest_idx[b] = ix; S.no_improve[b] = 0; S.fes[b] = NP; S.log_index[b] = 1;
+        S.curve[(size_t)b * MBX_CURVE_LEN] = v; S.curve_len[b] = 1; S.gen[b] = 0; S.done[b] = 0;
+        feature[b] = (float)((double)NP / (double)cfg.maxFEs);
+    }
+}
+
+// =====================================================================================================
+template <int D, int KIND>
+__global__ void __launch_bounds__(MBX_NT)
+rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
+                   MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, const double* __restrict__ pci,
+                   const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
+                   int32_t* __restrict__ dbg) {
+    const int b = blockIdx.x;
+    if (S.done[b]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RlepsoViews<D, KIND> V(smem_raw);
+    const int NP = cfg.NP, tid = threadIdx.x;
+    const MbxInstance* gi = inst + lane_inst[b];
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
+    const uint32_t gen = (uint32_t)S.gen[b];
+    Philox ph(cfg.seed);
+    double* px64 = V.A;
+    // ---- P0: stage pbest_x (as f64), per-particle scalars, coefficients (:112-132) -----------------------
+    for (int e = tid; e < NP * D; e += MBX_NT) px64[e] = (double)S.pbest_x[base + e];
+    for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
+    if (tid < NP) {
+        const int i = tid;
+        float pf = S.pbest[pb + i];
+        V.pf32[i] = pf; V.pf64[i] = (double)pf; V.cc[i] = S.c_cost[pb + i];
+        int pni = S.pni[pb + i];
+        V.pni[i] = pni;
+        const int per = NP / 5;
+        int g = i / per; if (g > 4) g = 4;
+        const float* a = action + (size_t)b * 35 + g * 5;           // stride 5, width 7 (overlapping windows)
+        float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6];
+        float cmf = a0 * 0.01f;
+        float w = a1 * 0.8f + 0.1f;
+        float ssum = a3 + a4; ssum = ssum + a5; ssum = ssum + a6; ssum = ssum + 1e-5f;
+        float scale = 1.f / ssum; scale = scale * a2; scale = scale * 8.f;
+        V.cm[i] = (double)cmf * (double)pni;
+        V.cw[i] = (double)w;
+        V.c1[i] = (double)(scale * a3); V.c2[i] = (double)(scale * a4);
+        V.c3[i] = (double)(scale * a5); V.c4[i] = (double)(scale * a6);
+        if (cfg.use_tape) { V.r1[i] = T.rand1[pb + i]; V.r2[i] = T.rand2[pb + i]; V.ur[i] = T.reinit_u[pb + i]; }
+        else { uint4 w4 = ph((uint32_t)i, gen, (uint32_t)b, MBX_TAG_P); V.r1[i] = u01(w4.x); V.r2[i] = u01(w4.y); V.ur[i] = u01(w4.z); }
+    }
+    __syncthreads();
+    const MbxInstance& h = *V.h;
+    const double lb = h.lb, ub = h.ub, vmax = 0.1 * (ub - lb);
+    // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5)   (:97-103) ------------------
+    // a/b < a'/b'  <=>  a*b' < a'*b  (b,b' > 0): exact cross-multiplication in f64, first minimum kept.
+    {
+        const int nblk = (NP + FDR_IB - 1) / FDR_IB;
+        for (int w = tid; w < nblk * D; w += MBX_NT) {
+            const int ib = w / D, d = w - ib * D;
+            double pxi[FDR_IB], pfi[FDR_IB], ab[FDR_IB], bb[FDR_IB];
+            int jb[FDR_IB];
+            const double px0 = px64[d], pf0 = V.pf64[0];
+#pragma unroll
+            for (int k = 0; k < FDR_IB; ++k) {
+                int i = min(ib * FDR_IB + k, NP - 1);
+                pxi[k] = px64[i * D + d]; pfi[k] = V.pf64[i];
+                ab[k] = pf0 - pfi[k]; bb[k] = fabs(px0 - pxi[k]) + 1e-5; jb[k] = 0;
+            }
+#pragma unroll 2
+            for (int j = 1; j < NP; ++j) {
+                const double pxj = px64[j * D + d], pfj = V.pf64[j];
+#pragma unroll
+                for (int k = 0; k < FDR_IB; ++k) {
+                    double a = pfj - pfi[k];
+                    double bq = fabs(pxj - pxi[k]) + 1e-5;
+                    if (a * bb[k] < ab[k] * bq) { ab[k] = a; bb[k] = bq; jb[k] = j; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FDR_IB; ++k) {
+                int i = ib * FDR_IB + k;
+                if (i < NP) V.tgt[i * D + d] = (unsigned char)jb[k];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- P2: velocity + position, element-wise over (i,d)   (:76-95, :105-109, :179-195) ---------------
+    for (int e = tid; e < NP * D; e += MBX_NT) {
+        const int i = e / D, d = e - i * D;
+        double ru, fu; int t0, t1;
+        if (cfg.use_tape) {
+            ru = T.clpso_u[base + e]; fu = T.fdr_u[base + e];
+            t0 = T.tour[(base + e) * 2]; t1 = T.tour[(base + e) * 2 + 1];
+        } else {
+            uint4 w = ph((uint32_t)e, gen, (uint32_t)b, MBX_TAG_PD);
+            ru = u01(w.x); t0 = bounded(w.y, NP); t1 = bounded(w.z, NP); fu = u01(w.w);
+        }
+        const double x = (double)S.x[base + e], v = (double)S.v[base + e], pxi = px64[e];
+        const int tsel = (V.pf32[t1] < V.pf32[t0]) ? t1 : t0;          // argmin of the 2 picks, tie -> first
+        const double own = (ru > pci[i]) ? pxi : px64[tsel * D + d];
+        const double v_clpso = ru * (own - x);
+        const int tg = V.tgt[e];
+        if (dbg) dbg[base + e] = tg;
+        const double v_fdr = fu * (px64[tg * D + d] - pxi);
+        const double v_pbest = V.r1[i] * (pxi - x);
+        const double v_gbest = V.r2[i] * (V.gx[d] - x);
+        double nv = V.cw[i] * v + V.c1[i] * v_clpso + V.c2[i] * v_fdr + V.c3[i] * v_gbest + V.c4[i] * v_pbest;
+        nv = fmin(fmax(nv, -vmax), vmax);
+        double nx = fmin(fmax(x + nv, lb), ub);
+        const float nx32 = (float)nx;
+        V.xs[e] = nx32;
+        S.x[base + e] = nx32; S.v[base + e] = (float)nv;
+    }
+    __syncthreads();
+    // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
+    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)b,
+                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP);
+    __syncthreads();
+    // ---- P4: pbest / gbest / patience / re-init mask (:200-238) ------------------------------------------
+    int fes = S.fes[b] + NP;
+    float gbest = S.gbest_val[b];
+    const float pre_gbest = gbest;
+    float v = INFINITY; int ix = tid;
+    bool mymask = false;
+    if (tid < NP) {
+        const int i = tid;
+        const float ncv = V.nc[i];
+        v = ncv;
+        const bool bt = ncv < V.pf32[i];
+        V.better[i] = bt;
+        if (bt) { V.pf32[i] = ncv; S.pbest[pb + i] = ncv; }
+        S.c_cost[pb + i] = ncv;
+        int pni = (ncv < V.cc[i]) ? 0 : V.pni[i] + 1;
+        V.pni[i] = pni;
+        V.cc[i] = ncv;
+        mymask = V.ur[i] < V.cm[i] * 0.01 * (double)pni;
+        V.mask[i] = mymask;
+    }
+    const int any_mask = __syncthreads_or(mymask ? 1 : 0);
+    for (int e = tid; e < NP * D; e += MBX_NT)
+        if (V.better[e / D]) S.pbest_x[base + e] = V.xs[e];
+    block_argmin<MBX_NT>(v, ix, V.redv, V.redi);
+    int gidx = -1;
+    if (v < gbest) { gbest = v; gidx = ix; }
+    if (gidx >= 0 && !any_mask)
+        for (int d = tid; d < D; d += MBX_NT) S.gbest_x[(size_t)b * D + d] = V.xs[gidx * D + d];
+    // ---- P5: stochastic re-initialisation (:134-168) -- rare ------------------------------------------------
+    if (any_mask) {
+        // gbest_x of the main pass must be captured before xs rows are overwritten
+        if (gidx >= 0 && tid < D) V.gx[tid] = (double)V.xs[gidx * D + tid];
+        __syncthreads();
+        for (int e = tid; e < NP * D; e += MBX_NT) {
+            const int i = e / D;
+            if (!V.mask[i]) continue;
+            double up, uv;
+            if (cfg.use_tape) { up = T.reinit_pos_u[base + e]; uv = T.reinit_vel_u[base + e]; }
+            else { uint4 w = ph((uint32_t)e, gen, (uint32_t)b, MBX_TAG_REINIT); up = u01(w.x); uv = u01(w.y); }
+            const float p = (float)(lb + (ub - lb) * up);
+            const float vv = (float)(-vmax + (vmax - (-vmax)) * uv);
+            V.xs[e] = p; S.x[base + e] = p; S.v[base + e] = vv;
+        }
+        __syncthreads();
+        // all NP are re-evaluated by the reference; for a noise-free instance the unmasked costs are
+        // unchanged by construction, so only masked rows are recomputed there.
+        const bool noisy = (h.noise != MBX_NOISE_NONE);
+        float* c2 = V.tmpf;
+        if (tid < NP) c2[tid] = V.nc[tid];
+        __syncthreads();
+        cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, c2, true, ph, gen, (uint32_t)b,
+                                             MBX_TAG_NOISE2,
+                                             cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP + 3 * NP : nullptr, NP,
+                                             noisy ? nullptr : V.mask);
+        __syncthreads();
+        int nmask = 0;
+        float v2 = INFINITY; int ix2 = tid;
+        if (tid < NP) {
+            const int i = tid;
+            const float cv = c2[i];
+            v2 = cv;
+            const bool bt = cv < V.pf32[i];
+            V.better[i] = bt;
+            if (bt) { V.pf32[i] = cv; S.pbest[pb + i] = cv; }
+            S.c_cost[pb + i] = cv;
+        }
+        nmask = __syncthreads_count(tid < NP && V.mask[tid]);
+        fes += nmask;                                                   // only sum(mask) is charged (:141-143)
+        for (int e = tid; e < NP * D; e += MBX_NT)
+            if (V.better[e / D]) S.pbest_x[base + e] = V.xs[e];
+        block_argmin<MBX_NT>(v2, ix2, V.redv, V.redi);
+        if (v2 < gbest) {
+            gbest = v2; gidx = ix2;
+            for (int d = tid; d < D; d += MBX_NT) S.gbest_x[(size_t)b * D + d] = V.xs[ix2 * D + d];
+        } else if (gidx >= 0) {
+            for (int d = tid; d < D; d += MBX_NT) S.gbest_x[(size_t)b * D + d] = (float)V.gx[d];
+        }
+    }
+    if (tid < NP) S.pni[pb + tid] = V.pni[tid];
+    // ---- P6: bookkeeping (:225-228, :241-261) ----------------------------------------------------------------
+    if (tid == 0) {
+        if (gidx >= 0) { S.gbest_val[b] = gbest; S.gbest_idx[b] = gidx; }
+        int lg = S.log_index[b], clen = S.curve_len[b];
+        bool done = log_and_done(cfg, h.has_optimum != 0, fes, gbest, lg, clen, S.curve + (size_t)b * MBX_CURVE_LEN);
+        S.log_index[b] = lg; S.curve_len[b] = clen; S.fes[b] = fes; S.gen[b] = (int)gen + 1;
+        S.no_improve[b] = (gbest < pre_gbest) ? 0 : S.no_improve[b] + 1;
+        S.done[b] = done ? 1 : 0;
+        feature[b] = (float)((double)fes / (double)cfg.maxFEs);
+        reward[b] = (gbest < pre_gbest) ? 1.f : -1.f;
+    }
+}
+
+// =====================================================================================================
+template <int D, int KIND>
+static int launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                         const MbxRlepsoState* s, const MbxRlepsoTape* tape, float* feature, int B, cudaStream_t st) {
+    auto kern = rlepso_init_kernel<D, KIND>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PopSmem<D, KIND>::kBytes));
+        attr_done = true;
+    }
+    MbxRlepsoTape t{};
+    if (tape) t = *tape;
+    kern<<<B, MBX_NT, PopSmem<D, KIND>::kBytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, feature);
+    MBX_CUDA(cudaGetLastError());
+    return MBX_OK;
+}
+template <int D, int KIND>
+static int launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                         const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci, const float* action,
+                         float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
+    auto kern = rlepso_step_kernel<D, KIND>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PopSmem<D, KIND>::kBytes));
+        attr_done = true;
+    }
+    MbxRlepsoTape t{};
+    if (tape) t = *tape;
+    kern<<<B, MBX_NT, PopSmem<D, KIND>::kBytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
+    MBX_CUDA(cudaGetLastError());
+    return MBX_OK;
+}
+
+#define MBX_DISPATCH(FN, ...)                                                                         \
+    if (cfg->dim == 10 && kind == MBX_KIND_BBOB) return FN<10, MBX_KIND_BBOB>(__VA_ARGS__);           \
+    if (cfg->dim == 30 && kind == MBX_KIND_BBOB) return FN<30, MBX_KIND_BBOB>(__VA_ARGS__);           \
+    if (cfg->dim == 12 && kind == MBX_KIND_PROTEIN) return FN<12, MBX_KIND_PROTEIN>(__VA_ARGS__);
+
+int mbx_launch_rlepso_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlepsoState* s, const MbxRlepsoTape* tape, float* feature, int B,
+                           cudaStream_t st) {
+    MBX_DISPATCH(launch_init_t, inst, consts, lane_inst, cfg, s, tape, feature, B, st)
+    mbx_set_error("mbx_rlepso_init: (kind=%d, dim=%d) is not compiled", kind, cfg->dim);
+    return MBX_EUNSUP;
+}
+int mbx_launch_rlepso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci,
+                           const float* action, float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
+    MBX_DISPATCH(launch_step_t, inst, consts, lane_inst, cfg, s, tape, pci, action, feature, reward, dbg, B, st)
+    mbx_set_error("mbx_rlepso_step: (kind=%d, dim=%d) is not compiled", kind, cfg->dim);
+    return MBX_EUNSUP;
+}
