@@ -74,7 +74,7 @@ typedef struct MbxRunConfig {
     int32_t n_logpoint;    /* 50 (bbob) / 5 (protein)                            */
     int32_t log_interval;  /* maxFEs // n_logpoint                               */
     int32_t use_tape;      /* 1: random numbers are read from MbxTape (parity tests); 0: Philox */
-    int32_t pad_;
+    int32_t lane_base;     /* Philox lane id of lane 0 (global lane index when a sweep is sharded) */
     uint64_t seed;         /* Philox key                                         */
 } MbxRunConfig;
 

@@ -32,7 +32,7 @@ INSTANCE_DTYPE = np.dtype([('kind', '<i4'), ('base', '<i4'), ('dim', '<i4'), ('n
 
 class MbxRunConfig(C.Structure):
     _fields_ = [('kind', C.c_int32), ('NP', C.c_int32), ('dim', C.c_int32), ('maxFEs', C.c_int32),
-                ('n_logpoint', C.c_int32), ('log_interval', C.c_int32), ('use_tape', C.c_int32), ('pad_', C.c_int32),
+                ('n_logpoint', C.c_int32), ('log_interval', C.c_int32), ('use_tape', C.c_int32), ('lane_base', C.c_int32),
                 ('seed', C.c_uint64)]
 
 

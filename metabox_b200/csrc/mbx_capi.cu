@@ -30,9 +30,9 @@ int mbx_sizeof_runconfig(void) { return (int)sizeof(MbxRunConfig); }
 int mbx_eval(int kind, const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const void* d_x,
              int x_is_f64, void* d_out, int B, int NP, int D, int subtract_optimum, uint64_t seed, uint32_t gen,
              const double* d_noise_tape, void* stream) {
-    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && d_x && d_out, "mbx_eval: null pointer");
     MBX_REQUIRE(B >= 0 && NP >= 0 && D > 0 && D <= MBX_MAX_DIM, "mbx_eval: bad shape B=%d NP=%d D=%d", B, NP, D);
     if (B == 0 || NP == 0) return MBX_OK;                       // empty input: nothing to do
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && d_x && d_out, "mbx_eval: null pointer");
     MBX_REQUIRE(B <= 65535, "mbx_eval: B=%d exceeds gridDim.y; split the call", B);
     return mbx_launch_eval(kind, D, x_is_f64, d_inst, d_consts, d_lane_inst, d_x, d_out, B, NP, subtract_optimum, seed, gen,
                            d_noise_tape, (cudaStream_t)stream);
@@ -52,6 +52,7 @@ int mbx_rlepso_init(const MbxInstance* d_inst, const double* d_consts, const int
                     const MbxRlepsoState* st, const MbxRlepsoTape* tape, float* d_feature, int B, void* stream) {
     int rc = check_cfg("mbx_rlepso_init", cfg, B);
     if (rc) return rc;
+    if (B == 0) return MBX_OK;
     MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_feature, "mbx_rlepso_init: null pointer");
     MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_pos_u && tape->init_vel_u), "mbx_rlepso_init: use_tape without tape");
     if (B == 0) return MBX_OK;
@@ -63,6 +64,7 @@ int mbx_rlepso_step(const MbxInstance* d_inst, const double* d_consts, const int
                     float* d_feature, float* d_reward, int32_t* d_dbg, int B, void* stream) {
     int rc = check_cfg("mbx_rlepso_step", cfg, B);
     if (rc) return rc;
+    if (B == 0) return MBX_OK;
     MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_pci && d_action && d_feature && d_reward,
                 "mbx_rlepso_step: null pointer");
     MBX_REQUIRE(cfg->NP % 5 == 0, "mbx_rlepso_step: NP=%d must be a multiple of the 5 coefficient groups", cfg->NP);
@@ -79,6 +81,7 @@ int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const i
                       void* stream) {
     int rc = check_cfg("mbx_random_search", cfg, B);
     if (rc) return rc;
+    if (B == 0) return MBX_OK;
     MBX_REQUIRE(d_inst && d_consts && d_lane_inst && d_curve && d_curve_len && d_fes, "mbx_random_search: null pointer");
     MBX_REQUIRE(!cfg->use_tape || (d_tape_u && n_tape_iter * cfg->NP >= cfg->maxFEs),
                 "mbx_random_search: tape shorter than the episode");

@@ -105,12 +105,12 @@ random_search_kernel(const MbxInstance* __restrict__ inst, const double* __restr
         for (int e = threadIdx.x; e < NP * D; e += MBX_NT) {
             double u;
             if (cfg.use_tape) u = tape_u[(((size_t)b * n_tape_iter + it) * NP) * D + e];
-            else u = u01(ph((uint32_t)e, (uint32_t)it, (uint32_t)b, MBX_TAG_INIT).x);
+            else u = u01(ph((uint32_t)e, (uint32_t)it, (uint32_t)(cfg.lane_base + b), MBX_TAG_INIT).x);
             xs[e] = (float)(lb + (ub - lb) * u);
         }
         __syncthreads();
         cta_eval_tile<D, KIND, float, float>(h, sC, consts + gi->off, xs, NP, 0, scratch, cost, true, ph, (uint32_t)it,
-                                             (uint32_t)b, MBX_TAG_NOISE, nullptr, 0);
+                                             (uint32_t)(cfg.lane_base + b), MBX_TAG_NOISE, nullptr, 0);
         __syncthreads();
         float v = threadIdx.x < NP ? cost[threadIdx.x] : INFINITY;
         int ix = threadIdx.x;

@@ -72,14 +72,14 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     for (int e = tid; e < NP * D; e += MBX_NT) {
         double up, uv;
         if (cfg.use_tape) { up = T.init_pos_u[base + e]; uv = T.init_vel_u[base + e]; }
-        else { uint4 w = ph((uint32_t)e, MBX_GEN_INIT, (uint32_t)b, MBX_TAG_INIT); up = u01(w.x); uv = u01(w.y); }
+        else { uint4 w = ph((uint32_t)e, MBX_GEN_INIT, (uint32_t)(cfg.lane_base + b), MBX_TAG_INIT); up = u01(w.x); uv = u01(w.y); }
         float p = (float)(lb + (ub - lb) * up);
         float v = (float)(-vmax + (vmax - (-vmax)) * uv);
         V.xs[e] = p;
         S.x[base + e] = p; S.pbest_x[base + e] = p; S.v[base + e] = v;
     }
     __syncthreads();
-    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, MBX_GEN_INIT, (uint32_t)b,
+    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, MBX_GEN_INIT, (uint32_t)(cfg.lane_base + b),
                                          MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP);
     __syncthreads();
     float v = INFINITY; int ix = tid;
@@ -136,7 +136,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         V.c1[i] = (double)(scale * a3); V.c2[i] = (double)(scale * a4);
         V.c3[i] = (double)(scale * a5); V.c4[i] = (double)(scale * a6);
         if (cfg.use_tape) { V.r1[i] = T.rand1[pb + i]; V.r2[i] = T.rand2[pb + i]; V.ur[i] = T.reinit_u[pb + i]; }
-        else { uint4 w4 = ph((uint32_t)i, gen, (uint32_t)b, MBX_TAG_P); V.r1[i] = u01(w4.x); V.r2[i] = u01(w4.y); V.ur[i] = u01(w4.z); }
+        else { uint4 w4 = ph((uint32_t)i, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_P); V.r1[i] = u01(w4.x); V.r2[i] = u01(w4.y); V.ur[i] = u01(w4.z); }
     }
     __syncthreads();
     const MbxInstance& h = *V.h;
@@ -182,7 +182,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             ru = T.clpso_u[base + e]; fu = T.fdr_u[base + e];
             t0 = T.tour[(base + e) * 2]; t1 = T.tour[(base + e) * 2 + 1];
         } else {
-            uint4 w = ph((uint32_t)e, gen, (uint32_t)b, MBX_TAG_PD);
+            uint4 w = ph((uint32_t)e, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_PD);
             ru = u01(w.x); t0 = bounded(w.y, NP); t1 = bounded(w.z, NP); fu = u01(w.w);
         }
         const double x = (double)S.x[base + e], v = (double)S.v[base + e], pxi = px64[e];
@@ -203,7 +203,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     }
     __syncthreads();
     // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
-    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)b,
+    cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                          MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP);
     __syncthreads();
     // ---- P4: pbest / gbest / patience / re-init mask (:200-238) ------------------------------------------
@@ -244,7 +244,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             if (!V.mask[i]) continue;
             double up, uv;
             if (cfg.use_tape) { up = T.reinit_pos_u[base + e]; uv = T.reinit_vel_u[base + e]; }
-            else { uint4 w = ph((uint32_t)e, gen, (uint32_t)b, MBX_TAG_REINIT); up = u01(w.x); uv = u01(w.y); }
+            else { uint4 w = ph((uint32_t)e, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_REINIT); up = u01(w.x); uv = u01(w.y); }
             const float p = (float)(lb + (ub - lb) * up);
             const float vv = (float)(-vmax + (vmax - (-vmax)) * uv);
             V.xs[e] = p; S.x[base + e] = p; S.v[base + e] = vv;
@@ -256,7 +256,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         float* c2 = V.tmpf;
         if (tid < NP) c2[tid] = V.nc[tid];
         __syncthreads();
-        cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, c2, true, ph, gen, (uint32_t)b,
+        cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, c2, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                              MBX_TAG_NOISE2,
                                              cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP + 3 * NP : nullptr, NP,
                                              noisy ? nullptr : V.mask);

@@ -1,0 +1,245 @@
+"""Optimizer layer: batched engines (B lanes in lockstep on one GPU) and single-problem drop-in twins of
+the reference's backbone optimizers.
+
+Reference interface (`src/optimizer/learnable_optimizer.py:16-30`, `basic_optimizer.py:10-15`,
+docs/Customization.md:125-210):
+    Learnable_Optimizer.__init__(config) / init_population(problem) -> state /
+    update(action, problem) -> (state, reward, is_done); public attrs fes, cost, log_index, log_interval.
+    Basic_Optimizer.run_episode(problem) -> {'cost', 'fes'}
+
+`*_Engine` classes own device state for B lanes and call the C ABI; `*_Optimizer` classes wrap an engine
+with B = 1 and the reference's exact signatures / return types so `PBO_Env`, agents and testers written
+for the reference run unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .problem import InstancePack
+
+
+class Learnable_Optimizer:
+    def __init__(self, config):
+        self.__config = config
+
+    def init_population(self, problem):
+        raise NotImplementedError
+
+    def update(self, action, problem):
+        raise NotImplementedError
+
+
+class Basic_Optimizer:
+    def __init__(self, config):
+        self.__config = config
+
+    def run_episode(self, problem):
+        raise NotImplementedError
+
+
+def _run_config(kind, NP, dim, maxFEs, n_logpoint, log_interval, use_tape, seed, lane_base=0):
+    return _lib.MbxRunConfig(kind=kind, NP=NP, dim=dim, maxFEs=int(maxFEs), n_logpoint=int(n_logpoint),
+                             log_interval=int(log_interval), use_tape=int(use_tape), lane_base=int(lane_base), seed=int(seed) & (2 ** 64 - 1))
+
+
+def _tape_struct(cls, tape, device, int_fields=()):
+    """dict of numpy/torch arrays -> (ctypes struct, keep-alive list)."""
+    import torch
+    st, keep = cls(), []
+    if tape:
+        for name, _ in cls._fields_:
+            a = tape.get(name)
+            if a is None:
+                continue
+            dt = torch.int32 if name in int_fields else torch.float64
+            t = torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a).to(device=device, dtype=dt).contiguous()
+            keep.append(t)
+            setattr(st, name, t.data_ptr())
+    return st, keep
+
+
+# ======================================================================================== RLEPSO
+def rlepso_pci(NP):
+    """CLPSO learning-probability table, rlepso_optimizer.py:24-25."""
+    idx = np.array(list(range(NP)))
+    return 0.05 + 0.45 * np.exp(10 * idx / (NP - 1)) / (np.exp(10) - 1)
+
+
+class RLEPSO_Engine:
+    """B lanes of the RLEPSO backbone (rlepso_optimizer.py:39-263) on one GPU."""
+    NP = 100
+    ACTION_DIM = 35
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None,
+                 lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)        # global id of lane 0: keeps Philox streams placement independent
+        self.NP = int(NP or RLEPSO_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.x, self.v, self.pbest_x = z(B, NPn, D), z(B, NPn, D), z(B, NPn, D)
+        self.c_cost, self.pbest = z(B, NPn), z(B, NPn)
+        self.pni = z(B, NPn, dt=i32)
+        self.gbest_x, self.gbest_val = z(B, D), z(B)
+        self.gbest_idx, self.no_improve, self.fes, self.log_index, self.curve_len, self.gen = (z(B, dt=i32) for _ in range(6))
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, 1), z(B)
+        self.pci = torch.from_numpy(rlepso_pci(self.NP)).to(dev)
+        self._state = _lib.MbxRlepsoState(*[t.data_ptr() for t in (
+            self.x, self.v, self.pbest_x, self.c_cost, self.pbest, self.pni, self.gbest_x, self.gbest_val, self.gbest_idx,
+            self.no_improve, self.fes, self.log_index, self.curve_len, self.gen, self.curve, self.done)])
+
+    def _cfg(self, use_tape):
+        return _run_config(self.pack.kind, self.NP, self.dim, self.maxFEs, self.n_logpoint, self.log_interval, use_tape,
+                           self.seed, self.lane_base)
+
+    def init_population(self, tape=None):
+        """-> feature [B,1] float32 (fes/maxFEs).  `tape`: dict of recorded draws (parity tests)."""
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxRlepsoTape, tape, self.device, ('tour',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_rlepso_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                            _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rlepso_init')
+        return self.feature
+
+    def update(self, action, tape=None, dbg=None):
+        """action [B,35] float32 device tensor -> (feature [B,1], reward [B], done [B] uint8), all on device.
+        Never synchronises; safe to capture in a CUDA graph (tape=None)."""
+        import torch
+        if action.shape != (self.B, self.ACTION_DIM):
+            raise AssertionError('actions size is not right!')           # rlepso_optimizer.py:113
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxRlepsoTape, tape, self.device, ('tour',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_rlepso_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.pci),
+                                            _lib.ptr(action), _lib.ptr(self.feature), _lib.ptr(self.reward), _lib.ptr(dbg),
+                                            self.B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rlepso_step')
+        return self.feature, self.reward, self.done
+
+    # ---- results in the reference's format -----------------------------------------------------
+    def cost_curves(self, pad=True):
+        """list (len B) of python lists of gbest samples; padded to 51 like tester.py:204-205."""
+        cur = self.curve.cpu().numpy().astype(np.float64)
+        ln = self.curve_len.cpu().numpy()
+        out = []
+        for b in range(self.B):
+            c = list(cur[b, :ln[b]])
+            if pad:
+                while len(c) < _lib.CURVE_LEN:
+                    c.append(c[-1])
+            out.append(c)
+        return out
+
+    def load_state(self, b, **arrays):
+        """Teacher forcing for parity tests: overwrite lane b's state from numpy arrays."""
+        import torch
+        for k, a in arrays.items():
+            t = getattr(self, k)
+            t[b] = torch.as_tensor(np.asarray(a)).to(device=self.device, dtype=t.dtype)
+
+    def read_state(self, b):
+        keys = ('x', 'v', 'pbest_x', 'c_cost', 'pbest', 'pni', 'gbest_x', 'gbest_val', 'gbest_idx', 'fes', 'log_index',
+                'curve_len', 'curve', 'done', 'gen')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class RLEPSO_Optimizer(Learnable_Optimizer):
+    """Drop-in for `RLEPSO_Optimizer` (rlepso_optimizer.py:5-263): one problem, numpy in / numpy out."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        config.w_decay = True
+        config.NP = 100
+        self.__config = config
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self.name = 'EPSO'
+        self._engine = None
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = RLEPSO_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, cfg.NP)
+        feat = self._engine.init_population()
+        self._sync()
+        return feat[0].cpu().numpy().astype(np.float64)
+
+    def _sync(self):
+        e = self._engine
+        self.fes = int(e.fes[0].item())
+        self.log_index = int(e.log_index[0].item())
+        self.cost = e.cost_curves(pad=False)[0]
+
+    def update(self, action, problem):
+        import torch
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1))
+        if a.shape[-1] != 35:
+            raise AssertionError('actions size is not right!')
+        feat, reward, done = self._engine.update(a.to(self._engine.device))
+        self._sync()
+        return feat[0].cpu().numpy().astype(np.float64), int(reward[0].item()), bool(done[0].item())
+
+
+# ======================================================================================== Random search
+class Random_search(Basic_Optimizer):
+    """Drop-in for `Random_search` (random_search.py:5-59); `run_lanes` runs many episodes at once."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.__config = config
+        self.__NP = 100
+        self.log_interval = config.log_interval
+        self.cost, self.log_index = None, None
+
+    def run_lanes(self, pack, lane_inst, seed=0, tape_u=None):
+        import torch
+        cfg = self.__config
+        B = len(lane_inst)
+        dev = pack.device
+        curve = torch.zeros(B, _lib.CURVE_LEN, dtype=torch.float32, device=dev)
+        clen = torch.zeros(B, dtype=torch.int32, device=dev)
+        fes = torch.zeros(B, dtype=torch.int32, device=dev)
+        li = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        rc_cfg = _run_config(pack.kind, self.__NP, pack.dim, cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, tape_u is not None, seed)
+        n_it, tp = 0, None
+        if tape_u is not None:
+            tp = torch.as_tensor(tape_u, dtype=torch.float64).to(dev).contiguous()
+            n_it = tp.shape[1]
+        with torch.cuda.device(dev):
+            rc = _lib.lib().mbx_random_search(_lib.ptr(pack.headers), _lib.ptr(pack.consts), _lib.ptr(li), C.byref(rc_cfg),
+                                              _lib.ptr(tp), n_it, _lib.ptr(curve), _lib.ptr(clen), _lib.ptr(fes), B,
+                                              _lib.stream_ptr())
+        _lib.check(rc, 'mbx_random_search')
+        cur, ln = curve.cpu().numpy().astype(np.float64), clen.cpu().numpy()
+        return [{'cost': list(cur[b, :ln[b]]), 'fes': int(f)} for b, f in enumerate(fes.cpu().numpy())]
+
+    def run_episode(self, problem):
+        problem.reset()
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        res = self.run_lanes(pack, [problem._index], seed)[0]
+        self.cost = res['cost']
+        return res

@@ -249,9 +249,12 @@ class Protein_Docking(Basic_Problem):
         return self.problem_id
 
     def const_block(self):
-        # sqrt(e_ij) with e_ij = sqrt(e_i e_j) (protein_docking.py:179, :42)  ==  e_i^(1/4) * e_j^(1/4)
+        # sqrt(e_ij) with e_ij = sqrt(e_i e_j) (protein_docking.py:179, :42)  ==  |e_i|^(1/4) * |e_j|^(1/4);
+        # the shipped epsilons are all negative, so e_i e_j > 0 (mixed signs would be NaN in the reference too)
+        if not (np.all(self.e_vec >= 0) or np.all(self.e_vec <= 0)):
+            raise ValueError('protein epsilons of mixed sign: sqrt(e_i*e_j) is undefined')
         return np.concatenate([self.coor_init.reshape(-1), self.basis.reshape(-1), 1.0 / np.sqrt(self.eigval),
-                               self.q_vec, np.sqrt(np.sqrt(self.e_vec)), self.r_vec])
+                               self.q_vec, np.sqrt(np.sqrt(np.abs(self.e_vec))), self.r_vec])
 
     def header(self, off):
         h = np.zeros((), dtype=_lib.INSTANCE_DTYPE)
@@ -442,6 +445,6 @@ class Protein_Docking_Dataset(_Dataset):
 def synthetic_protein(seed, problem_id=None):
     """Synthetic complex with the shape of the shipped data (for benchmarks without the data set)."""
     g = np.random.RandomState(seed)
-    return Protein_Docking(g.normal(size=(100, 3)) * 9.0, g.uniform(-0.8, 0.8, size=100), g.uniform(0.02, 0.2, size=100),
+    return Protein_Docking(g.normal(size=(100, 3)) * 9.0, g.uniform(-0.8, 0.8, size=100), -g.uniform(0.02, 0.25, size=100),
                            g.uniform(1.0, 2.2, size=100), g.normal(size=(12, 300)) / np.sqrt(300),
                            np.sort(g.uniform(0.02, 2.0, size=12)), problem_id or f'SYN{seed}')

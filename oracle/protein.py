@@ -82,7 +82,7 @@ def synthetic_instance(seed, problem_id=None) -> ProteinInstance:
     g = np.random.RandomState(seed)
     coor = g.normal(size=(N_ATOMS, 3)) * 9.0
     q = g.uniform(-0.8, 0.8, size=N_ATOMS)
-    e = g.uniform(0.02, 0.2, size=N_ATOMS)
+    e = -g.uniform(0.02, 0.25, size=N_ATOMS)      # shipped epsilons are negative (e.g. -0.2384 ... -0.0486)
     r = g.uniform(1.0, 2.2, size=N_ATOMS)
     basis = g.normal(size=(DIM, 3 * N_ATOMS)) / np.sqrt(3 * N_ATOMS)
     eig = np.sort(g.uniform(0.02, 2.0, size=DIM))
