@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- candidate evaluations / second of the MetaBBO rollout hot path.
+
+Workload (BASELINE.json metric "candidate evals/sec on BBOB dim=30 pop=100"): complete RLEPSO rollouts
+(`agent.rollout_episode(PBO_Env(problem, RLEPSO_Optimizer))`) on all 24 BBOB functions, dim 30, pop 100,
+maxFEs 60000, `--runs` independent runs per function per GPU (default 256 -> 6144 lanes per GPU, weak
+scaling).  One bench *step* = one complete sweep of all lanes (init_population + every generation until
+every lane is done + the final all-gather of cost curves).  evals are counted with the reference's `fes`
+accounting.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--runs R]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (see the contract in DESIGN.md section 7).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, NP, MAXFES = 30, 100, 60000
+BYTES_PER_EVAL = 24 * DIM + 24          # algorithmic bytes of one PSO-step evaluation: 744 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--runs', type=int, default=256, help='runs per function per GPU')
+    ap.add_argument('--cpu-gens', type=int, default=40, help='generations per lane in one CPU sample step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def policy_weights():
+    """Shipped RLEPSO policy (extracted from the reference pickle into tests/golden/agents.npz); random init of
+    the same architecture when the fixture is absent."""
+    p = os.path.join(ROOT, 'tests', 'golden', 'agents.npz')
+    if os.path.exists(p):
+        G = np.load(p)
+        return {k[len('rlepso/'):]: np.asarray(G[k]) for k in G.files if k.startswith('rlepso/')}, 'reference RLEPSO_Agent.pkl (bbob_easy)'
+    return None, 'random init'
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle port (the reference is pure Python and cannot
+    travel to the GPU box, so `oracle/` -- pinned against it by tests/golden -- is what runs), on all host
+    cores, each step a bounded sample: 24 functions x 1 run x `--cpu-gens` generations."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import agents as oag, rollout as orr
+    w_np, wsrc = policy_weights()
+    w = {k: torch.as_tensor(v) for k, v in w_np.items()} if w_np else oag.random_rlepso_weights()
+    cores = os.cpu_count() or 1
+    procs = min(cores, 24)
+    fids = list(range(1, 25))
+    for _ in range(args.warmup):
+        orr.timed_sample(DIM, MAXFES, w, fids, 2, procs)
+    tot_fes, tot_s = 0, 0.0
+    for k in range(args.steps):
+        fes, s = orr.timed_sample(DIM, MAXFES, w, fids, args.cpu_gens, procs, seed0=100 * k)
+        tot_fes += fes; tot_s += s
+    v = tot_fes / tot_s
+    sample = f'24 BBOB fns x 1 run x first {args.cpu_gens} generations (dim {DIM}, pop {NP}) per step'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'candidate evals/sec on BBOB dim=30 pop=100', 'value': v, 'unit': 'evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * tot_s / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'RLEPSO rollouts, BBOB 24 fns, dim 30, pop 100, maxFEs 60000 (bounded CPU sample)',
+                   'policy': wsrc},
+        'cpu_baseline': {'value': v, 'unit': 'evals/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    from metabox_b200 import agent as magent, problem as mp, sweep as msweep, _lib
+    _lib.lib()
+
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', DIM, 5)
+    problems = tr.data + te.data
+    pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
+    actor = magent.RLEPSO_Actor().to(dev).eval()
+    w_np, wsrc = policy_weights()
+    if w_np:
+        magent.load_reference_weights(actor, w_np)
+    inst, run = msweep.lane_table(len(problems), args.runs)
+    n_local = len(inst)
+    lane_base = rank * n_local                                # weak scaling: every rank gets its own 24 x runs lanes
+    seed = 20261017
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_sweep(sw):
+        res = sw.run()
+        rows = msweep.gather_results(res, world)               # the single collective of the sweep
+        return res, rows
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------------------
+    sw = msweep.RLEPSO_Sweep(pack, inst, actor, MAXFES, 50, seed=seed, lane_base=lane_base, time_kernels=True)
+    for _ in range(args.warmup):
+        one_sweep(sw)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    fes_total, launches, k_ms, k_n, k_fes = 0, 0, 0.0, 0, 0
+    for _ in range(args.steps):
+        res, rows = one_sweep(sw)
+        ms, n = sw.kernel_ms()                                 # syncs; events were recorded inside the sweep
+        k_ms += ms; k_n += n
+        f = int(res['fes'].sum().item())
+        fes_total += f; k_fes += f - n_local * NP              # evaluations charged inside the step kernels
+        launches += sw.launches
+    t1.record()
+    barrier()
+    ms_total = t0.elapsed_time(t1)
+    tt = torch.tensor([ms_total, float(fes_total)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, fes_all = float(mx[0]), float(sm[1])
+    else:
+        fes_all = float(fes_total)
+    value = fes_all / (ms_total / 1000.0)
+
+    # ---- e2e: host buffers in, host rows out, through the public sweep API ---------------------------------
+    h_hdr = torch.from_numpy(np.frombuffer(pack.h_headers.tobytes(), dtype=np.uint8).copy()).pin_memory()
+    h_cst = torch.from_numpy(pack.h_consts).pin_memory()
+    h_lane = torch.from_numpy(inst).pin_memory()
+    n_rows = n_local * world
+    h_rows = torch.empty(n_rows, 53, dtype=torch.float32).pin_memory()
+    h2d = h_hdr.numel() + h_cst.numel() * 8 + h_lane.numel() * 4
+    d2h = h_rows.numel() * 4
+
+    def e2e_step():
+        pk = mp.InstancePack.from_pinned(problems, h_hdr, h_cst, dev)
+        lanes = h_lane.to(dev, non_blocking=True)
+        s2 = msweep.RLEPSO_Sweep(pk, lanes, actor, MAXFES, 50, seed=seed, lane_base=lane_base)
+        res = s2.run()
+        rows = msweep.gather_results(res, world)
+        h_rows.copy_(rows, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(h_rows[:, 51].sum())
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e_fes = 0.0
+    for _ in range(args.steps):
+        e_fes += e2e_step()
+    e1.record()
+    barrier()
+    e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_ms = float(t[0])
+    e2e_value = e_fes / (e_ms / 1000.0)        # h_rows holds all ranks' lanes
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (k_fes * BYTES_PER_EVAL) / (k_ms / 1000.0) / 1e9 if k_ms > 0 else None
+        out = {
+            'metric': 'candidate evals/sec on BBOB dim=30 pop=100', 'value': value, 'unit': 'evals/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'RLEPSO rollouts, BBOB 24 fns x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
+                                   'one step = one complete sweep (init + all generations + all-gather)',
+                       'lanes_per_gpu': n_local, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
+                       'l2': f'per-GPU state {n_local * (3 * NP * DIM + 3 * NP) * 4 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)',
+                       'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'kernel': 'rlepso_step_kernel<30,BBOB>', 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,
+                         'kernel_share_of_step': k_ms / ms_total if ms_total else None, 'peak_source': peak_src,
+                         'note': 'algorithmic bytes = 744 B/eval x evals charged in the launch; the kernel is FP64-ALU bound '
+                                 '(FDR argmin: 3000 cross-multiplied comparisons per candidate), see DESIGN.md section 5'},
+            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'gpu_launches': int(launches), 'clocks': clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # the oracle port, timed in a fresh process (no CUDA context, so its fork pool is safe)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
+                                    '--warmup', '1', '--cpu-gens', str(args.cpu_gens)], capture_output=True, text=True,
+                                   timeout=600, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1', 'CUDA_VISIBLE_DEVICES': ''})
+                out['cpu_baseline'] = json.loads(r.stdout.strip().splitlines()[-1])['cpu_baseline']
+            except Exception as ex:                              # never lose the GPU line over the baseline
+                out['cpu_baseline'] = {'value': None, 'unit': 'evals/s', 'cores': 0, 'kind': 'port', 'sample': f'failed: {ex}'}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

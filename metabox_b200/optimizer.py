@@ -86,7 +86,10 @@ class RLEPSO_Engine:
         self.log_interval = int(log_interval or maxFEs // n_logpoint)
         self.seed = int(seed)
         dev, B, NPn, D = self.device, self.B, self.NP, self.dim
-        self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
         f32, i32 = torch.float32, torch.int32
         z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
         self.x, self.v, self.pbest_x = z(B, NPn, D), z(B, NPn, D), z(B, NPn, D)

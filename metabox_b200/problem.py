@@ -297,6 +297,19 @@ class InstancePack:
         for k, p in enumerate(self.problems):
             p._pack, p._index = self, k
 
+    @classmethod
+    def from_pinned(cls, problems, h_headers_u8, h_consts, device):
+        """Upload an already packed table (pinned host tensors: headers as uint8 bytes, float64 constants)
+        with asynchronous H2D copies on the current stream; no evaluation, no synchronisation."""
+        self = cls.__new__(cls)
+        self.problems = list(problems)
+        self.kind, self.dim = self.problems[0].kind, self.problems[0].dim
+        self.device = device
+        self.h_headers, self.h_consts = None, None
+        self.headers = h_headers_u8.to(device, non_blocking=True)
+        self.consts = h_consts.to(device, non_blocking=True)
+        return self
+
     def _upload_headers(self):
         import torch
         raw = np.frombuffer(self.h_headers.tobytes(), dtype=np.uint8).copy()
