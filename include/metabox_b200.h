@@ -138,6 +138,45 @@ int mbx_rlepso_step(const MbxInstance* d_inst, const double* d_consts, const int
                     int32_t* d_dbg, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LDE backbone (DE family, whole population per step) -- replaces LDE_Optimizer.init_population /
+ * update / __get_feature (optimizer/lde_optimizer.py:132-140, 159-198, 145-157) for B lanes at once.
+ * State (all device, updated in place); the population is kept sorted by cost (ascending, stable):
+ *   pop [B,NP,D] f32 ; fit [B,NP] f32 ; hist_sum [B,5] f64 (column sums of past_histo) ; hist_cnt [B] i32
+ *   gbest [B] f32 ; fes, log_index, curve_len, gen [B] i32 ; curve [B, MBX_CURVE_LEN] f32 ; done [B] u8   */
+typedef struct MbxLdeState {
+    float *pop, *fit;
+    double* hist_sum;
+    int32_t* hist_cnt;
+    float* gbest;
+    int32_t *fes, *log_index, *curve_len, *gen;
+    float* curve;
+    uint8_t* done;
+} MbxLdeState;
+
+/* Recorded draws for parity tests (device; null when use_tape=0):
+ *   init_u, cross_u [B,NP,D] f64 ; pbest_idx, r1, r2, jrand [B,NP] i32 (r1/r2 = final donor indices after the
+ *   reference's rejection loop, lde_optimizer.py:109-123) ; noise [B,3,NP] f64                            */
+typedef struct MbxLdeTape {
+    const double* init_u;
+    const int32_t *pbest_idx, *r1, *r2;
+    const double* cross_u;
+    const int32_t* jrand;
+    const double* noise;
+} MbxLdeTape;
+
+/* d_feature [B, NP+10] f32 = sorted min-max-normalised fitness | 5-bin histogram | mean past histogram */
+int mbx_lde_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                 const MbxRunConfig* cfg, const MbxLdeState* st, const MbxLdeTape* tape, float* d_feature, int B,
+                 void* stream);
+
+/* d_action [B, 2*NP] f32 (scale factors | crossover rates) ; outputs d_feature, d_reward [B] f32
+ * ((bsf - bsf_next)/bsf), st->done.  Finished lanes are skipped.
+ * d_dbg (optional): [B, NP*(D+1)] f32 = trial vectors [NP,D] then trial costs [NP] (index-parity tests). */
+int mbx_lde_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                 const MbxRunConfig* cfg, const MbxLdeState* st, const MbxLdeTape* tape, const float* d_action,
+                 float* d_feature, float* d_reward, float* d_dbg, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

@@ -72,6 +72,10 @@ SIGNATURES = {
                                   C.POINTER(MbxRlepsoTape), _P, C.c_int, _P]),
     'mbx_rlepso_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxRlepsoState),
                                   C.POINTER(MbxRlepsoTape), _P, _P, _P, _P, _P, C.c_int, _P]),
+    'mbx_lde_init': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxLdeState), C.POINTER(MbxLdeTape), _P,
+                               C.c_int, _P]),
+    'mbx_lde_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxLdeState), C.POINTER(MbxLdeTape), _P, _P,
+                               _P, _P, C.c_int, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
 OPTIONAL_SIGNATURES = {}

@@ -26,3 +26,9 @@ int mbx_launch_rlepso_init(int kind, const MbxInstance* inst, const double* cons
 int mbx_launch_rlepso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                            const MbxRunConfig* cfg, const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci,
                            const float* action, float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st);
+int mbx_launch_lde_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                        const MbxRunConfig* cfg, const MbxLdeState* s, const MbxLdeTape* tape, float* feature, int B,
+                        cudaStream_t st);
+int mbx_launch_lde_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                        const MbxRunConfig* cfg, const MbxLdeState* s, const MbxLdeTape* tape, const float* action,
+                        float* feature, float* reward, float* dbg, int B, cudaStream_t st);

@@ -246,3 +246,129 @@ class Random_search(Basic_Optimizer):
         res = self.run_lanes(pack, [problem._index], seed)[0]
         self.cost = res['cost']
         return res
+
+
+# ======================================================================================== LDE
+class LDE_Engine:
+    """B lanes of the LDE backbone (lde_optimizer.py:132-198) on one GPU.  The reference fixes NP = 50
+    (lde_optimizer.py:10, lde_agent.py:37); any NP <= 128 is accepted here (BASELINE config C4 asks for 100)."""
+    NP = 50
+    BINS = 5
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None,
+                 lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)
+        self.NP = int(NP or LDE_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.pop, self.fit = z(B, NPn, D), z(B, NPn)
+        self.hist_sum = z(B, self.BINS, dt=torch.float64)
+        self.hist_cnt = z(B, dt=i32)
+        self.gbest = z(B)
+        self.fes, self.log_index, self.curve_len, self.gen = (z(B, dt=i32) for _ in range(4))
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, NPn + 2 * self.BINS), z(B)
+        self._state = _lib.MbxLdeState(*[t.data_ptr() for t in (
+            self.pop, self.fit, self.hist_sum, self.hist_cnt, self.gbest, self.fes, self.log_index, self.curve_len,
+            self.gen, self.curve, self.done)])
+
+    def _cfg(self, use_tape):
+        return _run_config(self.pack.kind, self.NP, self.dim, self.maxFEs, self.n_logpoint, self.log_interval, use_tape,
+                           self.seed, self.lane_base)
+
+    _INT_FIELDS = ('pbest_idx', 'r1', 'r2', 'jrand')
+
+    def init_population(self, tape=None):
+        """-> feature [B, NP+10] float32 (sorted normalised fitness | histogram | mean past histogram)."""
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxLdeTape, tape, self.device, self._INT_FIELDS)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_lde_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                         C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                         _lib.stream_ptr())
+        _lib.check(rc, 'mbx_lde_init')
+        return self.feature
+
+    def update(self, action, tape=None, dbg=None):
+        """action [B, 2*NP] float32 device tensor -> (feature [B,NP+10], reward [B], done [B] uint8) on device."""
+        import torch
+        if tuple(action.shape) != (self.B, 2 * self.NP):
+            raise ValueError(f'LDE action must be [B, 2*NP] = {(self.B, 2 * self.NP)}, got {tuple(action.shape)}')
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxLdeTape, tape, self.device, self._INT_FIELDS)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_lde_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                         C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(action),
+                                         _lib.ptr(self.feature), _lib.ptr(self.reward), _lib.ptr(dbg), self.B,
+                                         _lib.stream_ptr())
+        _lib.check(rc, 'mbx_lde_step')
+        return self.feature, self.reward, self.done
+
+    cost_curves = RLEPSO_Engine.cost_curves
+    load_state = RLEPSO_Engine.load_state
+
+    def read_state(self, b):
+        keys = ('pop', 'fit', 'hist_sum', 'hist_cnt', 'gbest', 'fes', 'log_index', 'curve_len', 'curve', 'done', 'gen')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class LDE_Optimizer(Learnable_Optimizer):
+    """Drop-in for `LDE_Optimizer` (lde_optimizer.py:6-198): one problem, numpy in / numpy out, BATCH_SIZE = 1
+    leading axis on state / reward like the reference."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        config.NP = 50
+        config.BINS = 5
+        config.P_INI = 1
+        config.P_NUM_MIN = 2
+        config.P_MIN = config.P_NUM_MIN / config.NP
+        self.__config = config
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self.gbest_cost = None
+        self._engine = None
+
+    def get_best(self):
+        return self.gbest_cost
+
+    def _sync(self):
+        e = self._engine
+        self.fes = int(e.fes[0].item())
+        self.log_index = int(e.log_index[0].item())
+        self.cost = e.cost_curves(pad=False)[0]
+        self.gbest_cost = float(e.gbest[0].item())
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = LDE_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, cfg.NP)
+        feat = self._engine.init_population()
+        self._sync()
+        return feat.cpu().numpy().astype(np.float64)
+
+    def update(self, action, problem):
+        import torch
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1))
+        feat, reward, done = self._engine.update(a.to(self._engine.device))
+        self._sync()
+        return feat.cpu().numpy().astype(np.float64), reward.cpu().numpy().astype(np.float64), bool(done[0].item())

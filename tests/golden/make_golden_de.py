@@ -60,4 +60,63 @@ def gen_agents():
     print('agents done', {k: v.shape for k, v in out.items() if hasattr(v, 'shape') and k.startswith(('rlepso/', 'lde/'))})
 
 
-SECTIONS = dict(agents=gen_agents)
+# ------------------------------------------------------------------------------------------ LDE
+LDE_CASES = [  # (key, fid or protein id, dim, maxFEs or None, n_steps)
+    ('f1_d10', 1, 10, None, 5), ('f15_d10', 15, 10, None, 5), ('f8_d30', 8, 30, None, 4), ('f20_d10', 20, 10, None, 3),
+    ('f102_d10', 102, 10, None, 4), ('f130_d10', 130, 10, None, 3), ('f1_d10_short', 1, 10, 400, 7),
+    ('prot_1R0R_1', '1R0R_1', 12, 1000, 4),
+]
+
+
+def _f32r(a):
+    return np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def _lde_get(opt):
+    return dict(pop=opt._LDE_Optimizer__pop[0].astype(np.float32), fit=opt._LDE_Optimizer__fit[0].astype(np.float32),
+                past_histo=opt._LDE_Optimizer__past_histo[0].copy(), gbest=np.float64(opt.gbest_cost),
+                fes=np.int64(opt.fes), log_index=np.int64(opt.log_index), curve=np.array(opt.cost, dtype=np.float64))
+
+
+def gen_lde():
+    """Teacher-forced `LDE_Optimizer.init_population/update` (lde_optimizer.py:132-198) on F32Problem proxies."""
+    import make_golden as mg
+    from optimizer import LDE_Optimizer
+    out = dict(meta=str(META), cases=np.array([c[0] for c in LDE_CASES]))
+    ga = np.random.RandomState(777)
+    for key, fid, dim, maxFEs, n_steps in LDE_CASES:
+        if isinstance(fid, str):
+            inner = mg.protein_instance(fid); cfg = mg.ref_config(12, maxFEs, 5)
+        else:
+            inner = mg.bbob_instance(fid, dim); cfg = mg.ref_config(dim, maxFEs)
+        prob = _refenv.F32Problem(inner)
+        opt = LDE_Optimizer(cfg)
+        prob.reset()
+        seed0 = 2000 + len(key) * 11
+        np.random.seed(seed0); torch.manual_seed(seed0)
+        feat = opt.init_population(prob)
+        opt._LDE_Optimizer__pop = _f32r(opt._LDE_Optimizer__pop)
+        for k, v in dict(fid=np.array(str(fid)), dim=np.int64(dim), maxFEs=np.int64(cfg.maxFEs),
+                         n_logpoint=np.int64(cfg.n_logpoint), seed0=np.int64(seed0), n_steps=np.int64(n_steps)).items():
+            out[f'{key}/{k}'] = v
+        for k, v in _lde_get(opt).items():
+            out[f'{key}/s0/{k}'] = v
+        out[f'{key}/s0/feature'] = np.asarray(feat, dtype=np.float64)[0]
+        for t in range(1, n_steps + 1):
+            action = ga.rand(1, 100).astype(np.float32)
+            if t == 2:
+                action[0, :50] *= 1.8                     # sf > 1 never comes from the policy (clip) but drives trials out of bounds
+            seed = seed0 + t
+            np.random.seed(seed); torch.manual_seed(seed)
+            feat, reward, done = opt.update(action, prob)
+            opt._LDE_Optimizer__pop = _f32r(opt._LDE_Optimizer__pop)
+            out[f'{key}/s{t}/action'] = action[0]; out[f'{key}/s{t}/seed'] = np.int64(seed)
+            out[f'{key}/s{t}/feature'] = np.asarray(feat, dtype=np.float64)[0]
+            out[f'{key}/s{t}/reward'] = np.float64(np.asarray(reward).reshape(-1)[0]); out[f'{key}/s{t}/done'] = np.bool_(done)
+            for k, v in _lde_get(opt).items():
+                out[f'{key}/s{t}/{k}'] = v
+    np.savez_compressed(os.path.join(HERE, 'lde.npz'), **out)
+    print('lde done')
+
+
+SECTIONS = dict(agents=gen_agents, lde=gen_lde)

@@ -143,3 +143,55 @@ def test_rlepso_steps_match_reference():
             assert done == bool(G[f'{key}/s{t}/done'])
             np.testing.assert_array_equal(feat, G[f'{key}/s{t}/feature'])
     assert n_reinit >= 5        # the re-initialisation branch is covered
+
+
+# ----------------------------------------------------------------------------------------- LDE
+def _lde_state_from(G, pre):
+    from oracle import lde as ol
+    ph = G[pre + 'past_histo']
+    return ol.State(pop=G[pre + 'pop'], fit=G[pre + 'fit'], hist_sum=ph.sum(0), hist_cnt=ph.shape[0],
+                    gbest=np.float32(G[pre + 'gbest']), fes=int(G[pre + 'fes']), log_index=int(G[pre + 'log_index']),
+                    curve=[np.float32(c) for c in G[pre + 'curve']])
+
+
+def _lde_cmp(S, feat, G, pre, tag):
+    np.testing.assert_array_equal(S.pop, G[pre + 'pop'], err_msg=f'{tag} pop')
+    np.testing.assert_allclose(S.fit, G[pre + 'fit'], rtol=1e-6, atol=1e-10, err_msg=f'{tag} fit')
+    ph = G[pre + 'past_histo']
+    np.testing.assert_array_equal(S.hist_sum, ph.sum(0), err_msg=f'{tag} histogram sum')
+    assert S.hist_cnt == ph.shape[0] and S.fes == int(G[pre + 'fes']) and S.log_index == int(G[pre + 'log_index']), tag
+    np.testing.assert_allclose(np.array(S.curve, dtype=np.float64), G[pre + 'curve'], rtol=1e-6, atol=1e-10)
+    ref = G[pre + 'feature']
+    NP = S.fit.shape[0]
+    np.testing.assert_allclose(feat[:NP], ref[:NP], rtol=1e-5, atol=1e-9, err_msg=f'{tag} normalised fitness')
+    np.testing.assert_array_equal(feat[NP:NP + 5], ref[NP:NP + 5], err_msg=f'{tag} histogram')
+    np.testing.assert_allclose(feat[NP + 5:], ref[NP + 5:], rtol=1e-14, err_msg=f'{tag} mean past histogram')
+
+
+def test_lde_steps_match_reference():
+    """The real LDE_Optimizer (teacher-forced on float32-representable state, seeded np.random + torch) vs the
+    oracle replaying the same draws: populations bit-exact, survivor selection / sort order / histograms exact."""
+    import torch
+    from oracle import lde as ol
+    G = load('lde.npz')
+    n_done = 0
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = ol.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        s0 = int(G[f'{key}/seed0'])
+        np.random.seed(s0); torch.manual_seed(s0)
+        S, feat = ol.init_population(cfg, ev, optimum, lb, ub, ol.NumpyTape(cfg.NP, dim, nc))
+        _lde_cmp(S, feat, G, f'{key}/s0/', f'{key} init')
+        for t in range(1, int(G[f'{key}/n_steps']) + 1):
+            S = _lde_state_from(G, f'{key}/s{t - 1}/')
+            s = int(G[f'{key}/s{t}/seed'])
+            np.random.seed(s); torch.manual_seed(s)
+            aux = {}
+            N, feat, reward, done = ol.update(cfg, S, G[f'{key}/s{t}/action'], ev, optimum, lb, ub,
+                                              ol.NumpyTape(cfg.NP, dim, nc), aux)
+            _lde_cmp(N, feat, G, f'{key}/s{t}/', f'{key} step {t}')
+            np.testing.assert_allclose(reward, float(G[f'{key}/s{t}/reward']), rtol=1e-5, atol=1e-12)
+            assert done == bool(G[f'{key}/s{t}/done'])
+            n_done += int(done)
+    assert n_done >= 1
