@@ -119,4 +119,78 @@ def gen_lde():
     print('lde done')
 
 
-SECTIONS = dict(agents=gen_agents, lde=gen_lde)
+# ------------------------------------------------------------------------------------------ DE-DDQN
+DEDDQN_CASES = [  # (key, fid or protein id, dim, maxFEs or None, n_steps)
+    ('f1_d10', 1, 10, None, 330), ('f15_d10', 15, 10, None, 260), ('f9_d30', 9, 30, None, 120),
+    ('f103_d10', 103, 10, None, 130), ('f1_d10_short', 1, 10, 150, 50), ('prot_1R0R_1', '1R0R_1', 12, 1000, 110),
+]
+
+
+def _dd_round(opt):
+    for nm in ('_DE_DDQN_Optimizer__X', '_DE_DDQN_Optimizer__X_gbest', '_DE_DDQN_Optimizer__X_prebest'):
+        a = getattr(opt, nm)
+        np.copyto(a, _f32r(a))                                    # in place: keeps the reference's view aliasing intact
+
+
+def _dd_scalars(opt):
+    g = lambda n: getattr(opt, '_DE_DDQN_Optimizer__' + n)
+    return np.array([g('pointer'), g('gen'), g('stagcount'), opt.fes, opt.log_index], dtype=np.int64), \
+        np.array([g('c_gbest'), g('c_gworst'), g('c_prebest')], dtype=np.float64)
+
+
+def gen_deddqn():
+    """`DE_DDQN_Optimizer.init_population/update` (de_ddqn_optimizer.py:46-220) on F32Problem proxies, run
+    continuously with its state rounded to float32 in place after every step; random actions 0..3."""
+    import make_golden as mg
+    from optimizer import DE_DDQN_Optimizer
+    out = dict(meta=str(META), cases=np.array([c[0] for c in DEDDQN_CASES]))
+    ga = np.random.RandomState(31337)
+    for key, fid, dim, maxFEs, n_steps in DEDDQN_CASES:
+        if isinstance(fid, str):
+            inner = mg.protein_instance(fid); cfg = mg.ref_config(12, maxFEs, 5)
+        else:
+            inner = mg.bbob_instance(fid, dim); cfg = mg.ref_config(dim, maxFEs)
+        prob = _refenv.F32Problem(inner)
+        opt = DE_DDQN_Optimizer(cfg)
+        prob.reset()
+        seed0 = 3000 + len(key) * 13
+        np.random.seed(seed0)
+        feat = opt.init_population(prob)
+        _dd_round(opt)
+        g = lambda n: getattr(opt, '_DE_DDQN_Optimizer__' + n)
+        for k, v in dict(fid=np.array(str(fid)), dim=np.int64(dim), maxFEs=np.int64(cfg.maxFEs),
+                         n_logpoint=np.int64(cfg.n_logpoint), seed0=np.int64(seed0)).items():
+            out[f'{key}/{k}'] = v
+        out[f'{key}/X0'] = g('X').astype(np.float32); out[f'{key}/cost0'] = g('cost').astype(np.float32)
+        feats, rewards, dones, ints, flts, rows, rcost, rs, acts, gb, pbx = [np.asarray(feat)], [], [], [], [], [], [], [g('r').copy()], [], [], []
+        i0, f0 = _dd_scalars(opt); ints.append(i0); flts.append(f0)
+        snaps = {}
+        for t in range(1, n_steps + 1):
+            action = int(ga.randint(0, 4))
+            p = g('pointer')
+            np.random.seed(seed0 + t)
+            feat, reward, done = opt.update(action, prob)
+            _dd_round(opt)
+            i1, f1 = _dd_scalars(opt)
+            acts.append(action); feats.append(np.asarray(feat)); rewards.append(reward); dones.append(done)
+            ints.append(i1); flts.append(f1); rows.append(g('X')[p].astype(np.float32)); rcost.append(g('cost')[p])
+            rs.append(g('r').copy()); gb.append(g('X_gbest').astype(np.float32)); pbx.append(g('X_prebest').astype(np.float32))
+            if t % 50 == 0 or t == n_steps:
+                snaps[t] = (g('X').astype(np.float32), g('cost').astype(np.float32))
+            if done:
+                break
+        out[f'{key}/n_steps'] = np.int64(len(acts))
+        out[f'{key}/action'] = np.array(acts, dtype=np.int64); out[f'{key}/feature'] = np.stack(feats)
+        out[f'{key}/reward'] = np.array(rewards, dtype=np.float64); out[f'{key}/done'] = np.array(dones)
+        out[f'{key}/ints'] = np.stack(ints); out[f'{key}/flts'] = np.stack(flts)
+        out[f'{key}/row'] = np.stack(rows); out[f'{key}/row_cost'] = np.array(rcost, dtype=np.float64)
+        out[f'{key}/r'] = np.stack(rs); out[f'{key}/X_gbest'] = np.stack(gb); out[f'{key}/X_prebest'] = np.stack(pbx)
+        out[f'{key}/curve'] = np.array(opt.cost, dtype=np.float64)
+        out[f'{key}/snap_steps'] = np.array(sorted(snaps), dtype=np.int64)
+        for t, (X, c) in snaps.items():
+            out[f'{key}/snapX_{t}'] = X; out[f'{key}/snapC_{t}'] = c
+    np.savez_compressed(os.path.join(HERE, 'deddqn.npz'), **out)
+    print('deddqn done')
+
+
+SECTIONS = dict(agents=gen_agents, lde=gen_lde, deddqn=gen_deddqn)

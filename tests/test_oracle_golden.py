@@ -195,3 +195,52 @@ def test_lde_steps_match_reference():
             assert done == bool(G[f'{key}/s{t}/done'])
             n_done += int(done)
     assert n_done >= 1
+
+
+# ----------------------------------------------------------------------------------------- DE-DDQN
+def _dd_cmp(S, feat, G, key, t, tag):
+    ints, flts = G[f'{key}/ints'][t], G[f'{key}/flts'][t]
+    assert [S.pointer, S.gen, S.stagcount, S.fes, S.log_index] == list(ints), f'{tag}: pointer/gen/stagcount/fes/log_index'
+    np.testing.assert_allclose([S.c_gbest, S.c_gworst, S.c_prebest], flts, rtol=1e-6, atol=1e-10, err_msg=tag)
+    np.testing.assert_array_equal(S.r, G[f'{key}/r'][t], err_msg=f'{tag} r')
+    ref = G[f'{key}/feature'][t]
+    np.testing.assert_allclose(feat, ref, rtol=2e-5, atol=1e-9, err_msg=f'{tag} features')
+
+
+def test_deddqn_steps_match_reference():
+    """The real DE_DDQN_Optimizer run continuously (state rounded to float32 after each step) vs the oracle on the
+    same seeds and actions: replaced rows / gbest / prebest bit-exact, all 99 features, credit history, window."""
+    from oracle import deddqn as od
+    G = load('deddqn.npz')
+    n_total = n_gen2 = n_evict = n_done = 0
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = od.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        s0 = int(G[f'{key}/seed0'])
+        np.random.seed(s0)
+        S, feat = od.init_population(cfg, ev, optimum, lb, ub, od.NumpyTape(cfg.NP, dim, nc))
+        np.testing.assert_array_equal(S.X, G[f'{key}/X0'])
+        np.testing.assert_allclose(S.cost, G[f'{key}/cost0'], rtol=1e-6, atol=1e-10)
+        _dd_cmp(S, feat, G, key, 0, f'{key} init')
+        snaps = set(int(t) for t in G[f'{key}/snap_steps'])
+        for t in range(1, int(G[f'{key}/n_steps']) + 1):
+            p = S.pointer
+            np.random.seed(s0 + t)
+            aux = {}
+            S, feat, reward, done = od.update(cfg, S, int(G[f'{key}/action'][t - 1]), ev, optimum, lb, ub,
+                                              od.NumpyTape(cfg.NP, dim, nc), aux)
+            tag = f'{key} step {t}'
+            _dd_cmp(S, feat, G, key, t, tag)
+            np.testing.assert_array_equal(S.X[p], G[f'{key}/row'][t - 1], err_msg=f'{tag} row')
+            np.testing.assert_allclose(S.cost[p], G[f'{key}/row_cost'][t - 1], rtol=1e-6, atol=1e-10)
+            np.testing.assert_array_equal(S.X_gbest, G[f'{key}/X_gbest'][t - 1], err_msg=f'{tag} X_gbest')
+            np.testing.assert_array_equal(S.prebest(), G[f'{key}/X_prebest'][t - 1], err_msg=f'{tag} X_prebest')
+            np.testing.assert_allclose(reward, G[f'{key}/reward'][t - 1], rtol=1e-5, atol=1e-12)
+            assert done == bool(G[f'{key}/done'][t - 1]), tag
+            if t in snaps:
+                np.testing.assert_array_equal(S.X, G[f'{key}/snapX_{t}'], err_msg=f'{tag} X snapshot')
+                np.testing.assert_allclose(S.cost, G[f'{key}/snapC_{t}'], rtol=1e-6, atol=1e-10)
+            n_total += 1; n_gen2 += int(S.gen >= 3); n_evict += int(S.win_len >= od.W_); n_done += int(done)
+        np.testing.assert_allclose(np.array(S.curve, dtype=np.float64), G[f'{key}/curve'], rtol=1e-6, atol=1e-10)
+    assert n_total >= 900 and n_gen2 >= 100 and n_evict >= 300 and n_done >= 1
