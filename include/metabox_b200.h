@@ -177,6 +177,47 @@ int mbx_lde_step(const MbxInstance* d_inst, const double* d_consts, const int32_
                  float* d_feature, float* d_reward, float* d_dbg, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DE-DDQN backbone (DE family, ONE individual per step) -- replaces DE_DDQN_Optimizer.init_population /
+ * update / __get_state (optimizer/de_ddqn_optimizer.py:46-74, 131-220, 76-129) for B lanes at once.
+ * State (all device, updated in place):
+ *   X [B,NP,D] f32 ; cost [B,NP] f32 ; X_gbest, X_prebest [B,D] f32 ; c3 [B,3] f32 = c_gbest, c_gworst, c_prebest
+ *   ints [B,8] i32 = pointer, gen, stagcount, prebest_row (>=0 while X_prebest is the reference's *view* of that
+ *                    row of X, else -1), gbest_rebound, window length, next window sequence number, error flag
+ *   r [B,5] i32 (indices for the next mutation) ; n_tot [B,4,10] i32 ; n_succ [B,4,4,10] i32 ;
+ *   om_sum, om_max [B,4,4,10] f64 (slot 0 = current generation; the reference's maxlen-10 deques)
+ *   win [B,50,8] f64 rows = (action, om0..om3, trial_cost, sequence number, 0): the OM_W window, unordered slots
+ *   fes, log_index, curve_len [B] i32 ; curve [B, MBX_CURVE_LEN] f32 ; done [B] u8                         */
+typedef struct MbxDdqnState {
+    float *X, *cost, *X_gbest, *X_prebest, *c3;
+    int32_t *ints, *r, *n_tot, *n_succ;
+    double *om_sum, *om_max, *win;
+    int32_t *fes, *log_index, *curve_len;
+    float* curve;
+    uint8_t* done;
+} MbxDdqnState;
+
+/* Recorded draws for parity tests: init_u [B,NP,D] f64 ; r5 [B,5] i32 (this call's `randint(0,NP,5)`) ;
+ * noise [B,3,n] f64 with n = NP for init and n = 1 for a step.                                           */
+typedef struct MbxDdqnTape {
+    const double* init_u;
+    const int32_t* r5;
+    const double* noise;
+} MbxDdqnTape;
+
+/* d_feature [B,99] f32 */
+int mbx_deddqn_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxDdqnState* st, const MbxDdqnTape* tape, float* d_feature, int B,
+                    void* stream);
+
+/* d_action [B] i32 in 0..3 (rand/1, rand/2, rand-to-best/2, cur-to-rand/1) ; outputs d_feature [B,99] f32,
+ * d_reward [B] f32 (max(parent - trial, 0)), st->done.  A lane given an action outside 0..3 is left untouched
+ * and its ints[7] error flag is set (the reference raises ValueError('Action error')).
+ * d_dbg (optional): [B, D+1] f32 = trial vector then trial cost.                                           */
+int mbx_deddqn_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxDdqnState* st, const MbxDdqnTape* tape, const int32_t* d_action,
+                    float* d_feature, float* d_reward, float* d_dbg, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

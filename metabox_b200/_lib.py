@@ -58,6 +58,15 @@ class MbxLdeTape(C.Structure):
     _fields_ = [(n, _P) for n in ('init_u', 'pbest_idx', 'r1', 'r2', 'cross_u', 'jrand', 'noise')]
 
 
+class MbxDdqnState(C.Structure):
+    _fields_ = [(n, _P) for n in ('X', 'cost', 'X_gbest', 'X_prebest', 'c3', 'ints', 'r', 'n_tot', 'n_succ', 'om_sum',
+                                  'om_max', 'win', 'fes', 'log_index', 'curve_len', 'curve', 'done')]
+
+
+class MbxDdqnTape(C.Structure):
+    _fields_ = [(n, _P) for n in ('init_u', 'r5', 'noise')]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/metabox_b200.h declares
@@ -76,6 +85,10 @@ SIGNATURES = {
                                C.c_int, _P]),
     'mbx_lde_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxLdeState), C.POINTER(MbxLdeTape), _P, _P,
                                _P, _P, C.c_int, _P]),
+    'mbx_deddqn_init': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxDdqnState), C.POINTER(MbxDdqnTape), _P,
+                                  C.c_int, _P]),
+    'mbx_deddqn_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxDdqnState), C.POINTER(MbxDdqnTape), _P,
+                                  _P, _P, _P, C.c_int, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
 OPTIONAL_SIGNATURES = {}

@@ -99,6 +99,28 @@ int mbx_lde_step(const MbxInstance* d_inst, const double* d_consts, const int32_
                                (cudaStream_t)stream);
 }
 
+int mbx_deddqn_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxDdqnState* st, const MbxDdqnTape* tape, float* d_feature, int B, void* stream) {
+    int rc = check_cfg("mbx_deddqn_init", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_feature, "mbx_deddqn_init: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_u && tape->r5), "mbx_deddqn_init: use_tape without tape");
+    return mbx_launch_deddqn_init(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_feature, B, (cudaStream_t)stream);
+}
+
+int mbx_deddqn_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxDdqnState* st, const MbxDdqnTape* tape, const int32_t* d_action, float* d_feature,
+                    float* d_reward, float* d_dbg, int B, void* stream) {
+    int rc = check_cfg("mbx_deddqn_step", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_action && d_feature && d_reward, "mbx_deddqn_step: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->r5), "mbx_deddqn_step: use_tape without tape");
+    return mbx_launch_deddqn_step(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_action, d_feature, d_reward, d_dbg,
+                                  B, (cudaStream_t)stream);
+}
+
 int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
                       const double* d_tape_u, int n_tape_iter, float* d_curve, int32_t* d_curve_len, int32_t* d_fes, int B,
                       void* stream) {

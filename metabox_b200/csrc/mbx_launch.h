@@ -32,3 +32,9 @@ int mbx_launch_lde_init(int kind, const MbxInstance* inst, const double* consts,
 int mbx_launch_lde_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                         const MbxRunConfig* cfg, const MbxLdeState* s, const MbxLdeTape* tape, const float* action,
                         float* feature, float* reward, float* dbg, int B, cudaStream_t st);
+int mbx_launch_deddqn_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxDdqnState* s, const MbxDdqnTape* tape, float* feature, int B,
+                           cudaStream_t st);
+int mbx_launch_deddqn_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxDdqnState* s, const MbxDdqnTape* tape, const int32_t* action,
+                           float* feature, float* reward, float* dbg, int B, cudaStream_t st);

@@ -372,3 +372,127 @@ class LDE_Optimizer(Learnable_Optimizer):
         feat, reward, done = self._engine.update(a.to(self._engine.device))
         self._sync()
         return feat.cpu().numpy().astype(np.float64), reward.cpu().numpy().astype(np.float64), bool(done[0].item())
+
+
+# ======================================================================================== DE-DDQN
+class DE_DDQN_Engine:
+    """B lanes of the DE-DDQN backbone (de_ddqn_optimizer.py:46-220) on one GPU: one individual per step."""
+    NP = 100
+    N_FEAT = 99
+    GEN_MAX, W, WS = 10, 50, 8
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None,
+                 lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)
+        self.NP = int(NP or DE_DDQN_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, f64, i32 = torch.float32, torch.float64, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.X, self.cost = z(B, NPn, D), z(B, NPn)
+        self.X_gbest, self.X_prebest, self.c3 = z(B, D), z(B, D), z(B, 3)
+        self.ints, self.r = z(B, 8, dt=i32), z(B, 5, dt=i32)
+        self.n_tot, self.n_succ = z(B, 4, self.GEN_MAX, dt=i32), z(B, 4, 4, self.GEN_MAX, dt=i32)
+        self.om_sum, self.om_max = z(B, 4, 4, self.GEN_MAX, dt=f64), z(B, 4, 4, self.GEN_MAX, dt=f64)
+        self.win = z(B, self.W, self.WS, dt=f64)
+        self.fes, self.log_index, self.curve_len = (z(B, dt=i32) for _ in range(3))
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, self.N_FEAT), z(B)
+        self._state = _lib.MbxDdqnState(*[t.data_ptr() for t in (
+            self.X, self.cost, self.X_gbest, self.X_prebest, self.c3, self.ints, self.r, self.n_tot, self.n_succ,
+            self.om_sum, self.om_max, self.win, self.fes, self.log_index, self.curve_len, self.curve, self.done)])
+
+    def _cfg(self, use_tape):
+        return _run_config(self.pack.kind, self.NP, self.dim, self.maxFEs, self.n_logpoint, self.log_interval, use_tape,
+                           self.seed, self.lane_base)
+
+    def init_population(self, tape=None):
+        """-> feature [B,99] float32."""
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxDdqnTape, tape, self.device, ('r5',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_deddqn_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                            _lib.stream_ptr())
+        _lib.check(rc, 'mbx_deddqn_init')
+        return self.feature
+
+    def update(self, action, tape=None, dbg=None):
+        """action [B] int32 device tensor (0..3) -> (feature [B,99], reward [B], done [B] uint8) on device."""
+        import torch
+        if tuple(action.shape) != (self.B,):
+            raise ValueError(f'DE-DDQN action must be [B] = {(self.B,)}, got {tuple(action.shape)}')
+        if action.dtype != torch.int32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.int32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxDdqnTape, tape, self.device, ('r5',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_deddqn_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(action),
+                                            _lib.ptr(self.feature), _lib.ptr(self.reward), _lib.ptr(dbg), self.B,
+                                            _lib.stream_ptr())
+        _lib.check(rc, 'mbx_deddqn_step')
+        return self.feature, self.reward, self.done
+
+    cost_curves = RLEPSO_Engine.cost_curves
+    load_state = RLEPSO_Engine.load_state
+
+    def read_state(self, b):
+        keys = ('X', 'cost', 'X_gbest', 'X_prebest', 'c3', 'ints', 'r', 'n_tot', 'n_succ', 'om_sum', 'om_max', 'win', 'fes',
+                'log_index', 'curve_len', 'curve', 'done')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class DE_DDQN_Optimizer(Learnable_Optimizer):
+    """Drop-in for `DE_DDQN_Optimizer` (de_ddqn_optimizer.py:8-220): one problem, python int action in,
+    numpy float64[99] state out."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        config.F = 0.5
+        config.Cr = 1.0
+        config.NP = 100
+        config.gen_max = 10
+        config.W = 50
+        self.__config = config
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self._engine = None
+
+    def _sync(self):
+        e = self._engine
+        self.fes = int(e.fes[0].item())
+        self.log_index = int(e.log_index[0].item())
+        self.cost = e.cost_curves(pad=False)[0]
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = DE_DDQN_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, cfg.NP)
+        feat = self._engine.init_population()
+        self._sync()
+        return feat[0].cpu().numpy().astype(np.float64)
+
+    def update(self, action, problem):
+        import torch
+        if int(action) not in (0, 1, 2, 3):
+            raise ValueError('Action error')                              # de_ddqn_optimizer.py:153
+        a = torch.tensor([int(action)], dtype=torch.int32, device=self._engine.device)
+        feat, reward, done = self._engine.update(a)
+        self._sync()
+        return feat[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())
