@@ -26,8 +26,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DIM, NP, MAXFES = 30, 100, 60000
-BYTES_PER_EVAL = 24 * DIM + 24          # algorithmic bytes of one PSO-step evaluation: 744 B
+DIM, MAXFES = 30, 60000
+# workload -> (suite, difficulty/subset, NP, algorithmic bytes per evaluation, description)
+WORKLOADS = {
+    'rlepso': dict(suit='bbob', subset='all', NP=100, bytes_per_eval=24 * DIM + 24, kernel='rlepso_step_kernel<30,BBOB>',
+                   desc='RLEPSO rollouts, BBOB 24 fns'),
+    'lde': dict(suit='bbob-noisy', subset='all', NP=100, bytes_per_eval=8 * DIM + 20.4, kernel='lde_step_kernel<30,BBOB>',
+                desc='LDE rollouts, BBOB-noisy 30 fns'),
+    'deddqn': dict(suit='bbob', subset='difficult-test', NP=100, bytes_per_eval=32 * DIM + 404,
+                   kernel='deddqn_step_kernel<30,BBOB>', desc='DE-DDQN rollouts, BBOB difficult test set 18 fns'),
+}
+METRIC = 'candidate evals/sec on BBOB dim=30 pop=100'
 
 
 def parse():
@@ -36,10 +45,18 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--runs', type=int, default=256, help='runs per function per GPU')
-    ap.add_argument('--cpu-gens', type=int, default=40, help='generations per lane in one CPU sample step')
+    ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
+                    help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3')
+    ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256; deddqn 64)')
+    ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
+    a = ap.parse_args()
+    if a.runs is None:
+        a.runs = 64 if a.workload == 'deddqn' else 256
+    if a.cpu_gens is None:
+        a.cpu_gens = 1500 if a.workload == 'deddqn' else 40
+    return a
 
 
 # ---------------------------------------------------------------------------------------------- helpers
@@ -88,50 +105,86 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def policy_weights():
-    """Shipped RLEPSO policy (extracted from the reference pickle into tests/golden/agents.npz); random init of
-    the same architecture when the fixture is absent."""
+def policy_weights(workload):
+    """Shipped policies (extracted from the reference pickles into tests/golden/agents.npz).  The shipped LDE policy
+    only fits NP = 50 (lde_agent.py:37); the NP = 100 workload uses a randomly initialised policy of the right width."""
     p = os.path.join(ROOT, 'tests', 'golden', 'agents.npz')
-    if os.path.exists(p):
-        G = np.load(p)
-        return {k[len('rlepso/'):]: np.asarray(G[k]) for k in G.files if k.startswith('rlepso/')}, 'reference RLEPSO_Agent.pkl (bbob_easy)'
-    return None, 'random init'
+    if workload == 'lde' or not os.path.exists(p):
+        return None, 'random init (seed 0)'
+    G = np.load(p)
+    pre = workload + '/'
+    return {k[len(pre):]: np.asarray(G[k]) for k in G.files if k.startswith(pre)}, f'reference {workload} agent pickle (bbob_easy)'
+
+
+def suite_fids(workload):
+    W = WORKLOADS[workload]
+    if W['suit'] == 'bbob-noisy':
+        return list(range(101, 131))
+    if W['subset'] == 'difficult-test':
+        return [f for f in range(1, 25) if f not in (1, 5, 6, 10, 15, 20)]       # bbob.py:918, difficulty='difficult'
+    return list(range(1, 25))
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's CPU implementation of the path = the oracle port (the reference is pure Python and cannot
     travel to the GPU box, so `oracle/` -- pinned against it by tests/golden -- is what runs), on all host
-    cores, each step a bounded sample: 24 functions x 1 run x `--cpu-gens` generations."""
+    cores, each step a bounded sample: every function x 1 run x `--cpu-gens` generations."""
     if rank != 0:
         return
     import torch
     from oracle import agents as oag, rollout as orr
-    w_np, wsrc = policy_weights()
-    w = {k: torch.as_tensor(v) for k, v in w_np.items()} if w_np else oag.random_rlepso_weights()
+    W = WORKLOADS[args.workload]
+    w_np, wsrc = policy_weights(args.workload)
+    if w_np:
+        w = {k: torch.as_tensor(v) for k, v in w_np.items()}
+    else:
+        w = oag.random_rlepso_weights() if args.workload == 'rlepso' else None
     cores = os.cpu_count() or 1
-    procs = min(cores, 24)
-    fids = list(range(1, 25))
+    fids = suite_fids(args.workload)
+    procs = min(cores, len(fids))
+    kw = dict(NP=W['NP']) if args.workload == 'lde' else {}
     for _ in range(args.warmup):
-        orr.timed_sample(DIM, MAXFES, w, fids, 2, procs)
+        orr.timed_sample(DIM, MAXFES, w, fids, 2, procs, suit=W['suit'], algo=args.workload, **kw)
     tot_fes, tot_s = 0, 0.0
     for k in range(args.steps):
-        fes, s = orr.timed_sample(DIM, MAXFES, w, fids, args.cpu_gens, procs, seed0=100 * k)
+        fes, s = orr.timed_sample(DIM, MAXFES, w, fids, args.cpu_gens, procs, suit=W['suit'], seed0=100 * k,
+                                  algo=args.workload, **kw)
         tot_fes += fes; tot_s += s
     v = tot_fes / tot_s
-    sample = f'24 BBOB fns x 1 run x first {args.cpu_gens} generations (dim {DIM}, pop {NP}) per step'
+    unit = 'steps' if args.workload == 'deddqn' else 'generations'
+    sample = f'{len(fids)} fns x 1 run x first {args.cpu_gens} {unit} (dim {DIM}, pop {W["NP"]}) per step'
     print(json.dumps({
-        'impl': 'reference', 'metric': 'candidate evals/sec on BBOB dim=30 pop=100', 'value': v, 'unit': 'evals/s',
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'evals/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * tot_s / max(1, args.steps),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'RLEPSO rollouts, BBOB 24 fns, dim 30, pop 100, maxFEs 60000 (bounded CPU sample)',
-                   'policy': wsrc},
+        'config': {'workload': f'{W["desc"]}, dim {DIM}, pop {W["NP"]}, maxFEs {MAXFES} (bounded CPU sample)', 'policy': wsrc},
         'cpu_baseline': {'value': v, 'unit': 'evals/s', 'cores': procs, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def build_policy(workload, dev, NP):
+    import torch
+    from metabox_b200 import agent as magent
+    torch.manual_seed(0)
+    net = {'rlepso': magent.RLEPSO_Actor, 'deddqn': magent.DE_DDQN_Net}[workload]() if workload != 'lde' else magent.LDE_PolicyNet(NP=NP)
+    w_np, wsrc = policy_weights(workload)
+    if w_np:
+        magent.load_reference_weights(net, w_np)
+    return net.to(dev).eval(), wsrc
+
+
+def make_sweep(workload, pack, lanes, net, seed, lane_base, NP, **kw):
+    from metabox_b200 import sweep as msweep
+    if workload == 'rlepso':
+        return msweep.RLEPSO_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
+    if workload == 'lde':
+        return msweep.LDE_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, NP=NP, **kw)
+    return msweep.DE_DDQN_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
@@ -148,20 +201,20 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    from metabox_b200 import agent as magent, problem as mp, sweep as msweep, _lib
+    from metabox_b200 import problem as mp, sweep as msweep, _lib
     _lib.lib()
+    W = WORKLOADS[args.workload]
+    NP = W['NP']
 
-    tr, te = mp.BBOB_Dataset.get_datasets('bbob', DIM, 5)
-    problems = tr.data + te.data
+    tr, te = mp.BBOB_Dataset.get_datasets(W['suit'], DIM, 5, difficulty='difficult' if W['subset'] == 'difficult-test' else 'easy')
+    problems = te.data if W['subset'] == 'difficult-test' else tr.data + te.data
     pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
-    actor = magent.RLEPSO_Actor().to(dev).eval()
-    w_np, wsrc = policy_weights()
-    if w_np:
-        magent.load_reference_weights(actor, w_np)
+    net, wsrc = build_policy(args.workload, dev, NP)
     inst, run = msweep.lane_table(len(problems), args.runs)
     n_local = len(inst)
-    lane_base = rank * n_local                                # weak scaling: every rank gets its own 24 x runs lanes
+    lane_base = rank * n_local                                # weak scaling: every rank gets its own n_fns x runs lanes
     seed = 20261017
+    init_fes = n_local * NP                                   # evaluations charged by init_population (not by step launches)
 
     def barrier():
         if world > 1:
@@ -173,8 +226,8 @@ def main():
         rows = msweep.gather_results(res, world)               # the single collective of the sweep
         return res, rows
 
-    # ---- value: inputs resident in HBM -------------------------------------------------------------------
-    sw = msweep.RLEPSO_Sweep(pack, inst, actor, MAXFES, 50, seed=seed, lane_base=lane_base, time_kernels=True)
+    # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
+    sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, graph=not args.no_graph)
     for _ in range(args.warmup):
         one_sweep(sw)
     clocks = ClockSampler(local_rank)
@@ -183,13 +236,10 @@ def main():
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    fes_total, launches, k_ms, k_n, k_fes = 0, 0, 0.0, 0, 0
+    fes_total, launches = 0, 0
     for _ in range(args.steps):
         res, rows = one_sweep(sw)
-        ms, n = sw.kernel_ms()                                 # syncs; events were recorded inside the sweep
-        k_ms += ms; k_n += n
-        f = int(res['fes'].sum().item())
-        fes_total += f; k_fes += f - n_local * NP              # evaluations charged inside the step kernels
+        fes_total += int(res['fes'].sum().item())
         launches += sw.launches
     t1.record()
     barrier()
@@ -203,7 +253,7 @@ def main():
         fes_all = float(fes_total)
     value = fes_all / (ms_total / 1000.0)
 
-    # ---- e2e: host buffers in, host rows out, through the public sweep API ---------------------------------
+    # ---- e2e: host buffers in (packed instance table + lane table from pinned memory), host rows out -------------
     h_hdr = torch.from_numpy(np.frombuffer(pack.h_headers.tobytes(), dtype=np.uint8).copy()).pin_memory()
     h_cst = torch.from_numpy(pack.h_consts).pin_memory()
     h_lane = torch.from_numpy(inst).pin_memory()
@@ -213,12 +263,12 @@ def main():
     d2h = h_rows.numel() * 4
 
     def e2e_step():
-        pk = mp.InstancePack.from_pinned(problems, h_hdr, h_cst, dev)
-        lanes = h_lane.to(dev, non_blocking=True)
-        s2 = msweep.RLEPSO_Sweep(pk, lanes, actor, MAXFES, 50, seed=seed, lane_base=lane_base)
-        res = s2.run()
+        pack.headers.copy_(h_hdr, non_blocking=True)           # H2D of this step's inputs
+        pack.consts.copy_(h_cst, non_blocking=True)
+        sw.engine.lane_inst.copy_(h_lane, non_blocking=True)
+        res = sw.run()
         rows = msweep.gather_results(res, world)
-        h_rows.copy_(rows, non_blocking=True)
+        h_rows.copy_(rows, non_blocking=True)                  # D2H of the step's result
         torch.cuda.synchronize()
         return float(h_rows[:, 51].sum())
 
@@ -237,24 +287,39 @@ def main():
     e2e_value = e_fes / (e_ms / 1000.0)        # h_rows holds all ranks' lanes
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- roofline of the dominant kernel: one instrumented sweep of the same workload, CUDA events around every step
+    #      launch on the launching stream (a graph replay cannot be timed per kernel) ---------------------------------
+    k_ms = k_n = k_fes = 0
+    if rank == 0:
+        swi = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, time_kernels=True)
+        res = swi.run()
+        k_ms, k_n = swi.kernel_ms()
+        k_fes = int(res['fes'].sum().item()) - init_fes
+        del swi
+    barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        achieved = (k_fes * BYTES_PER_EVAL) / (k_ms / 1000.0) / 1e9 if k_ms > 0 else None
+        achieved = (k_fes * W['bytes_per_eval']) / (k_ms / 1000.0) / 1e9 if k_ms > 0 else None
+        state_mb = {'rlepso': n_local * (3 * NP * DIM + 3 * NP) * 4, 'lde': n_local * (NP * DIM + NP) * 4,
+                    'deddqn': n_local * ((NP * DIM + NP) * 4 + 8800)}[args.workload] / 1e6
         out = {
-            'metric': 'candidate evals/sec on BBOB dim=30 pop=100', 'value': value, 'unit': 'evals/s', 'n_gpus': world,
+            'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'RLEPSO rollouts, BBOB 24 fns x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
+            'config': {'workload': f'{W["desc"]} x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
                                    'one step = one complete sweep (init + all generations + all-gather)',
                        'lanes_per_gpu': n_local, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
-                       'l2': f'per-GPU state {n_local * (3 * NP * DIM + 3 * NP) * 4 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)',
+                       'launch': 'eager' if args.no_graph else 'policy forward + fused step replayed from one CUDA graph per step',
+                       'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
                        'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': None,
-                         'kernel': 'rlepso_step_kernel<30,BBOB>', 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,
-                         'kernel_share_of_step': k_ms / ms_total if ms_total else None, 'peak_source': peak_src,
-                         'note': 'algorithmic bytes = 744 B/eval x evals charged in the launch; the kernel is FP64-ALU bound '
-                                 '(FDR argmin: 3000 cross-multiplied comparisons per candidate), see DESIGN.md section 5'},
+                         'kernel': W['kernel'], 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,
+                         'kernel_share_of_step': (k_ms / (ms_total / args.steps)) if ms_total else None, 'peak_source': peak_src,
+                         'timed': 'separate instrumented (eager) sweep of the same workload right after the timed region',
+                         'note': f'algorithmic bytes = {W["bytes_per_eval"]} B/eval x evals charged by the step launches; see DESIGN.md section 4 '
+                                 'for what actually bounds the kernel (FP64 ALU / latency, not HBM)'},
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches), 'clocks': clk,
         }
@@ -262,7 +327,8 @@ def main():
             # the oracle port, timed in a fresh process (no CUDA context, so its fork pool is safe)
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
-                                    '--warmup', '1', '--cpu-gens', str(args.cpu_gens)], capture_output=True, text=True,
+                                    '--warmup', '1', '--cpu-gens', str(args.cpu_gens), '--workload', args.workload],
+                                   capture_output=True, text=True,
                                    timeout=600, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1', 'CUDA_VISIBLE_DEVICES': ''})
                 out['cpu_baseline'] = json.loads(r.stdout.strip().splitlines()[-1])['cpu_baseline']
             except Exception as ex:                              # never lose the GPU line over the baseline

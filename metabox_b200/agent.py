@@ -149,3 +149,21 @@ class LDE_PolicyNet(nn.Module):
         mu, sigma, h_, c_ = self.forward(x, h, c)
         eps = torch.randn_like(mu) if noise is None else noise
         return torch.clip(mu + sigma * eps, 0, 1)[0], h_, c_
+
+    def lstm_cell(self, x, h, c):
+        """One LSTM step written out (gate order i, f, g, o like torch.nn.LSTM) so that the rollout loop is plain
+        matmuls on the current stream (CUDA-graph capturable, no cuDNN RNN descriptor).  x [B,NP+10], h/c [B,cell]
+        -> mu [B,2NP], sigma [B,2NP], h', c'."""
+        L = self.lstm
+        gates = torch.addmm(L.bias_ih_l0 + L.bias_hh_l0, x, L.weight_ih_l0.t()) + h @ L.weight_hh_l0.t()
+        i, f, g, o = gates.chunk(4, dim=-1)
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h2 = torch.sigmoid(o) * torch.tanh(c2)
+        return self.mu(h2), torch.sigmoid(self.sigma(h2)), h2, c2
+
+    @torch.no_grad()
+    def step(self, x, h, c, noise=None):
+        """Batched `sampler` for B lanes: action [B,2NP] = clip(Normal(mu, sigma).sample(), 0, 1), new (h, c)."""
+        mu, sigma, h2, c2 = self.lstm_cell(x, h, c)
+        eps = torch.randn_like(mu) if noise is None else noise
+        return torch.clip(mu + sigma * eps, 0, 1), h2, c2

@@ -1,11 +1,13 @@
-"""Batched rollout driver: the B200 counterpart of the nested `for problem / for run / while not done`
-loops of `Tester.test` / `rollout` (`src/tester.py:190-219, 314-346`).
+"""Batched rollout drivers: the B200 counterpart of the nested `for problem / for run / while not done`
+loops of `Tester.test` / `rollout` (`src/tester.py:190-219, 314-346`) and of the agents' `rollout_episode`
+(`src/agent/rlepso_agent.py:294-303`, `lde_agent.py:147-163`, `de_ddqn_agent.py:108-117`).
 
 A *lane* is one (instance, run) rollout.  Lanes are independent (fresh seed, `problem.reset()`,
 `init_population` per run in the reference), so a sweep is: build the lane table -> shard it over ranks
--> every rank advances its lanes in lockstep, one fused step kernel + one policy forward per generation,
-no host synchronisation inside the loop except a done-poll every `poll` generations -> ONE all-gather of
-the result rows {curve[51], fes, return} at the end (NCCL over NVLink/NVSwitch).
+-> every rank advances its lanes in lockstep -- per step ONE fused optimizer kernel plus the policy forward
+as torch calls on the same stream, the pair captured once in a CUDA graph and replayed -- with no host
+synchronisation inside the loop except a done-poll every `poll` steps -> ONE all-gather of the result rows
+{curve[51], fes, return} at the end (NCCL over NVLink/NVSwitch).
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .optimizer import RLEPSO_Engine
+from .optimizer import DE_DDQN_Engine, LDE_Engine, RLEPSO_Engine
 
 
 def lane_table(n_instances, n_runs):
@@ -32,52 +34,94 @@ def shard_range(n_lanes, rank, world):
     return lo, lo + q + (1 if rank < r else 0)
 
 
-class RLEPSO_Sweep:
-    """All lanes of one rank through complete RLEPSO rollouts with the policy on the same stream."""
+class _Sweep:
+    """Common rollout loop.  Subclasses provide `_policy(feat) -> action` (torch, on the engine's device) and may
+    keep recurrent state.  `graph=True` captures `steps_per_graph` x (policy forward + fused step + return
+    accumulation) in one CUDA graph; the first call of `run()` captures, later calls only replay."""
 
-    def __init__(self, pack, lane_inst, actor, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False):
-        self.engine = RLEPSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
-        self.actor = actor
-        self.poll = poll
-        self.max_gens = int(math.ceil(maxFEs / self.engine.NP)) + 1
+    def __init__(self, engine, max_steps, poll=64, graph=True, steps_per_graph=1, time_kernels=False):
+        self.engine = engine
+        self.max_steps = int(max_steps)
+        self.poll = int(poll)
+        self.use_graph = bool(graph) and not time_kernels
+        self.steps_per_graph = int(steps_per_graph)
         self.time_kernels = time_kernels
         self.kernel_events = []
         self.launches = 0
-        self.ret = torch.zeros(self.engine.B, dtype=torch.float32, device=self.engine.device)
+        self.ret = torch.zeros(engine.B, dtype=torch.float32, device=engine.device)
+        self._graph = None
+
+    # -- to be provided -------------------------------------------------------------------------------------
+    def _policy(self, feat):
+        raise NotImplementedError
+
+    def _reset_policy(self):
+        pass
+
+    # -- one env step, all on the current stream, no sync -----------------------------------------------------
+    def _step(self):
+        eng = self.engine
+        alive = (eng.done == 0).to(torch.float32)
+        action = self._policy(eng.feature)
+        if self.time_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, reward, _ = eng.update(action)
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        else:
+            _, reward, _ = eng.update(action)
+        self.ret += torch.nan_to_num(reward, nan=0.0, posinf=0.0, neginf=0.0) * alive
+
+    def _capture(self):
+        # warm-up on a side stream (lazy cuBLAS / cudaFuncSetAttribute initialisation must not happen under capture)
+        s = torch.cuda.Stream(device=self.engine.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(self.steps_per_graph):
+                self._step()
+        self._graph = g
 
     @torch.no_grad()
     def run(self):
-        """-> dict(curve [B,51] f32, curve_len, fes i32, ret f32) device tensors (no host copy)."""
+        """-> dict(curve [B,51] f32 (padded like tester.py:204-205), curve_len, fes i32, ret f32) device tensors."""
         eng = self.engine
-        self.ret.zero_()
-        self.kernel_events = []
-        feat = eng.init_population()
-        self.launches = 1
-        gens = 0
-        while gens < self.max_gens:
-            for _ in range(self.poll):
-                alive = (eng.done == 0).to(torch.float32)
-                action = self.actor(feat)
-                if self.time_kernels:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    feat, reward, done = eng.update(action)
-                    e1.record()
-                    self.kernel_events.append((e0, e1))
-                else:
-                    feat, reward, done = eng.update(action)
-                self.ret += reward * alive
-                self.launches += 1
-                gens += 1
-                if gens >= self.max_gens:
+        if eng.B == 0:
+            z = torch.zeros(0, device=eng.device)
+            return dict(curve=torch.zeros(0, _lib.CURVE_LEN, device=eng.device), curve_len=z.int(), fes=z.int(), ret=z, steps=0)
+        with torch.cuda.device(eng.device):
+            if self.use_graph and self._graph is None:
+                eng.init_population()
+                self._reset_policy()
+                self._capture()
+            self.kernel_events = []
+            eng.init_population()
+            self._reset_policy()
+            self.ret.zero_()
+            self.launches = 1
+            steps = 0
+            per = self.steps_per_graph if self.use_graph else 1
+            while steps < self.max_steps:
+                for _ in range(max(1, self.poll // per)):
+                    if self.use_graph:
+                        self._graph.replay()
+                    else:
+                        self._step()
+                    self.launches += per
+                    steps += per
+                    if steps >= self.max_steps:
+                        break
+                if bool(torch.all(eng.done != 0)):          # the only host sync inside the sweep
                     break
-            if bool(torch.all(eng.done != 0)):          # the only host sync inside the sweep
-                break
-        # cost curves padded to 51 like tester.py:204-205
         idx = torch.arange(_lib.CURVE_LEN, device=eng.device)[None, :]
         last = torch.gather(eng.curve, 1, (eng.curve_len.long() - 1).clamp(min=0)[:, None])
         curve = torch.where(idx < eng.curve_len[:, None], eng.curve, last)
-        return dict(curve=curve, curve_len=eng.curve_len, fes=eng.fes, ret=self.ret, gens=gens)
+        return dict(curve=curve, curve_len=eng.curve_len, fes=eng.fes, ret=self.ret, steps=steps)
 
     def kernel_ms(self):
         """Sum / count of the step-kernel durations recorded by the last run (needs time_kernels=True)."""
@@ -85,6 +129,54 @@ class RLEPSO_Sweep:
             return 0.0, 0
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in self.kernel_events), len(self.kernel_events)
+
+
+class RLEPSO_Sweep(_Sweep):
+    """RLEPSO_Agent.rollout_episode (rlepso_agent.py:294-303) for all lanes of one rank."""
+
+    def __init__(self, pack, lane_inst, actor, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False,
+                 graph=True):
+        eng = RLEPSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        # every generation charges >= NP evaluations, so ceil(maxFEs/NP) generations always suffice
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        self.actor = actor
+
+    def _policy(self, feat):
+        return self.actor(feat)
+
+
+class LDE_Sweep(_Sweep):
+    """LDE_Agent.rollout_episode (lde_agent.py:147-163): LSTM state (h, c) per lane, zero at reset."""
+
+    def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, NP=None, poll=64,
+                 time_kernels=False, graph=True):
+        eng = LDE_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base, NP=NP or net.NP)
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        self.net = net
+        self.h = torch.zeros(eng.B, net.cell, device=eng.device)
+        self.c = torch.zeros(eng.B, net.cell, device=eng.device)
+
+    def _reset_policy(self):
+        self.h.zero_(); self.c.zero_()
+
+    def _policy(self, feat):
+        action, h, c = self.net.step(feat, self.h, self.c)
+        self.h.copy_(h); self.c.copy_(c)
+        return action
+
+
+class DE_DDQN_Sweep(_Sweep):
+    """DE_DDQN_Agent.rollout_episode (de_ddqn_agent.py:108-117): greedy argmax of the Q-network, one FE per step."""
+
+    def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=500, time_kernels=False,
+                 graph=True, steps_per_graph=10):
+        eng = DE_DDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
+        self.net = net
+
+    def _policy(self, feat):
+        q = self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0))
+        return torch.argmax(q, dim=-1).to(torch.int32)
 
 
 def gather_results(res, world):

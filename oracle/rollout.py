@@ -31,20 +31,70 @@ def rlepso_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoi
     return dict(cost=[float(c) for c in S.curve], fes=S.fes, ret=R, gens=gens, seconds=time.perf_counter() - t0)
 
 
+def lde_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50, NP=50):
+    """One LDE rollout (lde_agent.py:147-163).  `weights` None -> randomly initialised policy of the right width
+    (the shipped policy only fits NP = 50)."""
+    from . import lde as ol
+    np.random.seed(run_seed)
+    torch.manual_seed(run_seed)
+    cfg = ol.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint, NP=NP)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    if weights is None:
+        lstm = torch.nn.LSTM(NP + 10, 50, 1); mu_l = torch.nn.Linear(50, 2 * NP); sg_l = torch.nn.Linear(50, 2 * NP)
+        weights = {'_PolicyNet__lstm.' + k: v.detach() for k, v in lstm.state_dict().items()}
+        weights.update({'_PolicyNet__mu.weight': mu_l.weight.detach(), '_PolicyNet__mu.bias': mu_l.bias.detach(),
+                        '_PolicyNet__sigma.weight': sg_l.weight.detach(), '_PolicyNet__sigma.bias': sg_l.bias.detach()})
+    t0 = time.perf_counter()
+    S, feat = ol.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, ol.NumpyTape(NP, dim, nc))
+    h = torch.zeros(1, 1, 50); c = torch.zeros(1, 1, 50)
+    R, gens, done = 0., 0, False
+    while not done and (max_gens is None or gens < max_gens):
+        mu, sigma, h, c = oag.lde_forward(weights, torch.as_tensor(feat[None, None, :], dtype=torch.float32), h, c)
+        action = torch.clip(torch.normal(mu, sigma), 0, 1).reshape(-1).numpy()
+        S, feat, reward, done = ol.update(cfg, S, action, ev, inst.optimum, inst.lb, inst.ub, ol.NumpyTape(NP, dim, nc))
+        R += float(reward)
+        gens += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=gens, seconds=time.perf_counter() - t0)
+
+
+def deddqn_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One DE-DDQN rollout (de_ddqn_agent.py:108-117), greedy actions; `max_gens` bounds the number of STEPS."""
+    from . import deddqn as od
+    np.random.seed(run_seed)
+    cfg = od.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    t0 = time.perf_counter()
+    S, feat = od.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, od.NumpyTape(cfg.NP, dim, nc))
+    fes0 = 0                               # the initial NP evaluations are not part of the per-step rate
+    R, steps, done = 0., 0, False
+    while not done and (max_gens is None or steps < max_gens):
+        q = oag.deddqn_q(weights, np.nan_to_num(feat).astype(np.float32))
+        S, feat, reward, done = od.update(cfg, S, int(torch.argmax(q)), ev, inst.optimum, inst.lb, inst.ub,
+                                          od.NumpyTape(cfg.NP, dim, nc))
+        R += float(reward)
+        steps += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes - fes0, ret=R, gens=steps, seconds=time.perf_counter() - t0)
+
+
+ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout}
+
+
 def _worker(args):
     torch.set_num_threads(1)
-    fid, dim, maxFEs, weights, seed, max_gens, suit = args
+    fid, dim, maxFEs, weights, seed, max_gens, suit, algo, kw = args
     tr, te = ob.make_suite(suit, dim, 5.0)
     inst = [i for i in tr + te if i.fid == fid][0]
-    r = rlepso_rollout(inst, dim, maxFEs, weights, seed, max_gens)
+    r = ROLLOUTS[algo](inst, dim, maxFEs, weights, seed, max_gens, **kw)
     return r['fes'], r['seconds']
 
 
-def timed_sample(dim, maxFEs, weights, fids, max_gens, n_procs, suit='bbob', seed0=0):
-    """Run one bounded sample: each function id in `fids` gets one run truncated at `max_gens` generations,
-    spread over a pool of `n_procs` single-threaded workers.  -> (total fes, wall seconds)."""
+def timed_sample(dim, maxFEs, weights, fids, max_gens, n_procs, suit='bbob', seed0=0, algo='rlepso', **kw):
+    """Run one bounded sample: each function id in `fids` gets one run truncated at `max_gens` generations (steps for
+    DE-DDQN), spread over a pool of `n_procs` single-threaded workers.  -> (total fes, wall seconds)."""
     import multiprocessing as mp
-    jobs = [(f, dim, maxFEs, weights, seed0 + k, max_gens, suit) for k, f in enumerate(fids)]
+    jobs = [(f, dim, maxFEs, weights, seed0 + k, max_gens, suit, algo, kw) for k, f in enumerate(fids)]
     t0 = time.perf_counter()
     if n_procs <= 1:
         res = [_worker(j) for j in jobs]

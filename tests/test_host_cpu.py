@@ -96,3 +96,92 @@ def test_no_cpu_fallback_for_eval():
     tr, _ = mp.BBOB_Dataset.get_datasets('bbob', 10, 5)
     with pytest.raises(_lib.MbxError):
         tr.data[0].eval(np.zeros(10))
+
+
+# ----------------------------------------------------------------------------------------- agents (rollout forward)
+def test_policy_forward_matches_reference_kats():
+    """Weights + known-answer forwards extracted from the reference's shipped pickles (tests/golden/agents.npz)."""
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    sub = lambda pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    actor = ma.load_reference_weights(ma.RLEPSO_Actor(), sub('rlepso/'))
+    mu, sg = actor.distribution(torch.as_tensor(G['rlepso_kat/x']))
+    np.testing.assert_allclose(mu.detach().numpy(), G['rlepso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sg.detach().numpy(), G['rlepso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    a = actor(torch.as_tensor(G['rlepso_kat/x']), noise=torch.zeros(5, 35))
+    assert a.shape == (5, 35) and float(a.min()) >= 0 and float(a.max()) <= 1
+    net = ma.load_reference_weights(ma.DE_DDQN_Net(), sub('deddqn/'))
+    q = net(torch.as_tensor(G['deddqn_kat/x']))
+    np.testing.assert_allclose(q.detach().numpy(), G['deddqn_kat/q'], rtol=1e-4, atol=1e-5)
+    assert net.packed_weights().numel() == 99 * 100 + 100 + 3 * (100 * 100 + 100) + 100 * 4 + 4
+    lde = ma.load_reference_weights(ma.LDE_PolicyNet(), sub('lde/'))
+    x, h, c = (torch.as_tensor(G[f'lde_kat/{k}']) for k in ('x', 'h', 'c'))
+    mu, sigma, h2, c2 = lde.forward(x, h, c)                                 # nn.LSTM path (reference layout [1,B,*])
+    for got, key in ((mu, 'mu'), (sigma, 'sigma'), (h2, 'h_out'), (c2, 'c_out')):
+        np.testing.assert_allclose(got.detach().numpy(), G[f'lde_kat/{key}'], rtol=1e-5, atol=1e-6)
+    mu, sigma, h2, c2 = lde.lstm_cell(x[0], h[0], c[0])                           # written-out cell used by the sweep
+    for got, key in ((mu, 'mu'), (sigma, 'sigma'), (h2, 'h_out'), (c2, 'c_out')):
+        np.testing.assert_allclose(got.detach().numpy(), G[f'lde_kat/{key}'][0], rtol=1e-5, atol=1e-6)
+    act, _, _ = lde.step(x[0], h[0], c[0], noise=torch.zeros(3, 100))
+    np.testing.assert_allclose(act.numpy(), np.clip(G['lde_kat/mu'][0], 0, 1), rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------- sharding / gather (gloo, world 2)
+def test_shard_ranges_cover_the_lane_table():
+    from metabox_b200 import sweep
+    inst, run = sweep.lane_table(7, 5)
+    assert list(inst[:6]) == [0, 0, 0, 0, 0, 1] and list(run[:6]) == [0, 1, 2, 3, 4, 0]
+    for n, world in ((35, 1), (35, 2), (35, 4), (35, 8), (3, 8), (0, 2)):
+        spans = [sweep.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, n_lanes, q):
+    import torch
+    import torch.distributed as dist
+    from metabox_b200 import sweep
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        lo, hi = sweep.shard_range(n_lanes, rank, world)
+        lanes = torch.arange(lo, hi, dtype=torch.float32)
+        # a fake per-rank sweep result whose content encodes the global lane id
+        res = dict(curve=lanes[:, None] + torch.arange(51, dtype=torch.float32)[None, :] / 100.,
+                   fes=(1000 + lanes).to(torch.int32), ret=-lanes)
+        rows = sweep.gather_results(res, world)
+        q.put((rank, rows.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_lanes', [10, 7])
+def test_gather_results_world2_gloo(n_lanes):
+    """world_size-2 gloo run of the sweep's single collective: uneven shards, rows come back in global lane order on
+    every rank and convert to the reference's result-dict layout."""
+    import socket
+    import torch.multiprocessing as tmp
+    from metabox_b200 import sweep
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = tmp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_lanes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lanes = np.arange(n_lanes, dtype=np.float32)
+    for r in range(2):
+        rows = got[r]
+        assert rows.shape == (n_lanes, 53)
+        np.testing.assert_allclose(rows[:, 0], lanes); np.testing.assert_allclose(rows[:, 51], 1000 + lanes)
+        np.testing.assert_allclose(rows[:, 52], -lanes); np.testing.assert_allclose(rows[:, 50], lanes + 0.5)
+    if n_lanes == 10:
+        d = sweep.results_to_reference_dict(got[0], ['A', 'B'], 5, 'RLEPSO_Agent')
+        assert d['fes']['B']['RLEPSO_Agent'] == [1005, 1006, 1007, 1008, 1009]
+        assert len(d['cost']['A']['RLEPSO_Agent']) == 5 and len(d['cost']['A']['RLEPSO_Agent'][0]) == 51
