@@ -46,7 +46,7 @@ extern "C" {
  * problem/bbob.py:31-45 + the per-class constructors (bbob.py:149-890) or
  * problem/protein_docking.py:163-181 produce; `off` is the instance's offset (in doubles) into the
  * constants buffer.  BBOB constants layout at `off`:
- *     shift[D] | R[D*D] | M2[D*D] | cv0[D] | cv1[D] | cv2[D] | (Gallagher) y[P*D] | C[P*D] | w[P]
+ *     shift[D] | R[D*D] | M2[D*D] | cv0[D] | cv1[D] | cv2[D] | (Gallagher) y[P*D] | C[P*D] | w[P] | Ry[P*D] (= R y_p)
  * protein layout at `off`:
  *     coor_init[300] | basis[12*300] | inv_sqrt_eig[12] | q[100] | e4[100] (= e_i^(1/4)) | r[100]   */
 typedef struct MbxInstance {

@@ -4,8 +4,8 @@
 //
 // Calling convention: the CTA has staged the instance constants in shared memory (`C`, layout
 // shift|R|M2|cv0|cv1|cv2, see MbxInstance) and the candidate is reachable through an accessor
-// X(d) -> double.  `zs` is a per-thread scratch column in shared memory: element k at zs[k*NT]
-// (bank-conflict free).  Loops containing libm calls are kept rolled (code size); D*D mat-vecs are
+// X(d) -> double.  `zs` is a per-thread scratch column in shared memory: element k at zs[k*zst]
+// (bank-conflict free; `zst` = the column stride = number of evaluating threads).  Loops containing libm calls are kept rolled (code size); D*D mat-vecs are
 // fully unrolled over d with the operand vector in registers and R rows broadcast from smem.
 #pragma once
 #include "mbx_common.cuh"
@@ -31,7 +31,8 @@ __device__ __forceinline__ double t_osz(double x) {       // bbob.py:51-67
     double ax = fabs(x);
     double t = log(ax) / 0.1;
     double c1 = x > 0. ? 1.0 : 0.55, c2 = x > 0. ? 0.79 : 0.31;
-    double r = pow(exp(t + 0.49 * (sin(c1 * t) + sin(c2 * t))), 0.1);
+    // reference: (exp(t + 0.49(sin c1 t + sin c2 t)))^0.1 ; exp(0.1 u) == exp(u)^0.1 up to a few ulp and saves the pow
+    double r = exp((t + 0.49 * (sin(c1 * t) + sin(c2 * t))) * 0.1);
     return x > 0. ? r : (x < 0. ? -r : x);
 }
 __device__ __forceinline__ double t_asy(double x, double beta, double frac) {   // bbob.py:70-82
@@ -48,8 +49,8 @@ __device__ __forceinline__ double pen_x(const XA& X, double ub) {               
     return p;
 }
 // zs[k] = sum_d M[k][d] * y[d]   (M row-major in smem, y in registers)
-template <int D, int NT>
-__device__ __forceinline__ void matvec(const double* __restrict__ M, const double (&y)[D], double* zs) {
+template <int D>
+__device__ __forceinline__ void matvec(const double* __restrict__ M, const double (&y)[D], double* zs, const int zst) {
 #pragma unroll 2
     for (int k = 0; k < D; ++k) {
         const double* row = M + k * D;
@@ -60,31 +61,31 @@ __device__ __forceinline__ void matvec(const double* __restrict__ M, const doubl
             a1 = fma(row[d + 1], y[d + 1], a1);
         }
         if (D & 1) a0 = fma(row[D - 1], y[D - 1], a0);
-        zs[k * NT] = a0 + a1;
+        zs[k * zst] = a0 + a1;
     }
 }
-template <int D, int NT>
-__device__ __forceinline__ void load_col(double (&y)[D], const double* zs) {
+template <int D>
+__device__ __forceinline__ void load_col(double (&y)[D], const double* zs, const int zst) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) y[d] = zs[d * NT];
+    for (int d = 0; d < D; ++d) y[d] = zs[d * zst];
 }
-template <int D, int NT>
-__device__ __forceinline__ double rastrigin_sum(const double* zs) {
+template <int D>
+__device__ __forceinline__ double rastrigin_sum(const double* zs, const int zst) {
     double sc = 0., sq = 0.;
 #pragma unroll 1
     for (int k = 0; k < D; ++k) {
-        double z = zs[k * NT];
+        double z = zs[k * zst];
         sc += cos(6.283185307179586 * z);
         sq += z * z;
     }
     return 10. * ((double)D - sc) + sq;
 }
-template <int D, int NT>
-__device__ __forceinline__ double rosen_sum(const double* zs) {
+template <int D>
+__device__ __forceinline__ double rosen_sum(const double* zs, const int zst) {
     double f = 0.;
 #pragma unroll 1
     for (int k = 0; k + 1 < D; ++k) {
-        double a = zs[k * NT], b = zs[(k + 1) * NT];
+        double a = zs[k * zst], b = zs[(k + 1) * zst];
         double u = a * a - b, w = a - 1.;
         f += 100. * (u * u) + w * w;
     }
@@ -92,9 +93,9 @@ __device__ __forceinline__ double rosen_sum(const double* zs) {
 }
 
 // Noise-free f(x) incl. bias and boundary handling  (== BBOB_Basic_Problem.func)
-template <int D, int NT, class XA>
+template <int D, class XA>
 __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, const double* __restrict__ G,
-                            const XA& X, double* zs) {
+                            const XA& X, double* zs, const int zst) {
     ConstView<D> c(C);
     const double bias = h.bias, ub = h.ub;
     double y[D];
@@ -108,50 +109,50 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
     if (base == 9 || base == 19) {                       // z = M2 x + 0.5   (bbob.py:434, :703)
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = X(d);
-        matvec<D, NT>(c.M2, y, zs);
+        matvec<D>(c.M2, y, zs, zst);
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * NT] += 0.5;
+        for (int k = 0; k < D; ++k) zs[k * zst] += 0.5;
     } else if (base == 5 || base == 20) {
         // no rotation
     } else if (base == 24) {                             // z = R (2 sign(s) x - mu0)   (bbob.py:885-886)
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = c.cv2[d] * X(d) - h.sc[0];
-        matvec<D, NT>(c.R, y, zs);
+        matvec<D>(c.R, y, zs, zst);
     } else if (base == 8) {                              // R = I (bbob.py:362)
 #pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * NT] = X(d) - c.s[d];
+        for (int d = 0; d < D; ++d) zs[d * zst] = X(d) - c.s[d];
     } else if (base != 21 && base != 22) {               // z = R (x - s)   (bbob.py:6-8)
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = X(d) - c.s[d];
-        matvec<D, NT>(c.R, y, zs);
+        matvec<D>(c.R, y, zs, zst);
     }
     // ---------------------------------------------------------------- per-shape tails
     switch (base) {
     case 1: {                                            // Sphere bbob.py:156-159
         double f = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = zs[k * NT]; f += z * z; }
+        for (int k = 0; k < D; ++k) { double z = zs[k * zst]; f += z * z; }
         return f + bias + bh;
     }
     case 2: case 10: {                                   // Ellipsoidal bbob.py:220-226, 447-453
         double f = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = t_osz(zs[k * NT]); f += c.cv0[k] * (z * z); }
+        for (int k = 0; k < D; ++k) { double z = t_osz(zs[k * zst]); f += c.cv0[k] * (z * z); }
         return f + bias + bh;
     }
     case 3: {                                            // Rastrigin bbob.py:240-243
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * NT] = c.cv0[k] * t_asy(t_osz(zs[k * NT]), 0.2, c.cv1[k]);
-        return rastrigin_sum<D, NT>(zs) + bias;
+        for (int k = 0; k < D; ++k) zs[k * zst] = c.cv0[k] * t_asy(t_osz(zs[k * zst]), 0.2, c.cv1[k]);
+        return rastrigin_sum<D>(zs, zst) + bias;
     }
     case 4: {                                            // Buche-Rastrigin bbob.py:258-265
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            double z = t_osz(zs[k * NT]);
+            double z = t_osz(zs[k * zst]);
             if (!(k & 1) && z > 0.) z *= 10.;
-            zs[k * NT] = z * c.cv0[k];
+            zs[k * zst] = z * c.cv0[k];
         }
-        double r = rastrigin_sum<D, NT>(zs);
+        double r = rastrigin_sum<D>(zs, zst);
         return r + 100. * pen_x<D>(X, ub) + bias;
     }
     case 5: {                                            // Linear slope bbob.py:281-287
@@ -169,7 +170,7 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double f = 0.;
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            double z = zs[k * NT];
+            double z = zs[k * zst];
             if (z * c.s[k] > 0.) z *= 100.;
             f += z * z;
         }
@@ -179,72 +180,74 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double zh0 = fabs(zs[0]);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            double zh = zs[d * NT];
+            double zh = zs[d * zst];
             y[d] = fabs(zh) > 0.5 ? floor(0.5 + zh) : floor(0.5 + 10. * zh) / 10.;
         }
-        matvec<D, NT>(c.M2, y, zs);
+        matvec<D>(c.M2, y, zs, zst);
         double f = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = zs[k * NT]; f += c.cv0[k] * (z * z); }
+        for (int k = 0; k < D; ++k) { double z = zs[k * zst]; f += c.cv0[k] * (z * z); }
         return 0.1 * fmax(zh0 / 1e4, f) + bh + bias;
     }
     case 8: {                                            // Rosenbrock bbob.py:365-368
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * NT] = h.sc[0] * zs[k * NT] + 1.;
-        return rosen_sum<D, NT>(zs) + bias + bh;
+        for (int k = 0; k < D; ++k) zs[k * zst] = h.sc[0] * zs[k * zst] + 1.;
+        return rosen_sum<D>(zs, zst) + bias + bh;
     }
     case 9:                                              // Rosenbrock rotated bbob.py:432-435
-        return rosen_sum<D, NT>(zs) + bias;
+        return rosen_sum<D>(zs, zst) + bias;
     case 11: {                                           // Discus bbob.py:498-502
         double z0 = t_osz(zs[0]);
         double f = 0.;
 #pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = t_osz(zs[k * NT]); f += z * z; }
+        for (int k = 1; k < D; ++k) { double z = t_osz(zs[k * zst]); f += z * z; }
         return 1e6 * (z0 * z0) + f + bias;
     }
     case 12: {                                           // Bent cigar bbob.py:517-522
 #pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * NT], 0.5, c.cv1[d]);
-        matvec<D, NT>(c.R, y, zs);
+        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * zst], 0.5, c.cv1[d]);
+        matvec<D>(c.R, y, zs, zst);
         double f = 0.;
 #pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = zs[k * NT]; f += 1e6 * (z * z); }
+        for (int k = 1; k < D; ++k) { double z = zs[k * zst]; f += 1e6 * (z * z); }
         double z0 = zs[0];
         return z0 * z0 + f + bias;
     }
     case 13: {                                           // Sharp ridge bbob.py:537-540
         double f = 0.;
 #pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = zs[k * NT]; f += z * z; }
+        for (int k = 1; k < D; ++k) { double z = zs[k * zst]; f += z * z; }
         double z0 = zs[0];
         return z0 * z0 + 100. * sqrt(f) + bias;
     }
     case 14: {                                           // Different powers bbob.py:550-554
         double f = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) f += pow(fabs(zs[k * NT]), c.cv0[k]);
+        for (int k = 0; k < D; ++k) f += pow(fabs(zs[k * zst]), c.cv0[k]);
         return pow(f, 0.5) + bias + bh;
     }
     case 15: {                                           // Rastrigin F15 bbob.py:597-602
 #pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * NT] = t_asy(t_osz(zs[d * NT]), 0.2, c.cv1[d]);
-        load_col<D, NT>(y, zs);
-        matvec<D, NT>(c.M2, y, zs);
-        return rastrigin_sum<D, NT>(zs) + bias;
+        for (int d = 0; d < D; ++d) zs[d * zst] = t_asy(t_osz(zs[d * zst]), 0.2, c.cv1[d]);
+        load_col<D>(y, zs, zst);
+        matvec<D>(c.M2, y, zs, zst);
+        return rastrigin_sum<D>(zs, zst) + bias;
     }
     case 16: {                                           // Weierstrass bbob.py:620-625
 #pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * NT] = t_osz(zs[d * NT]);
-        load_col<D, NT>(y, zs);
-        matvec<D, NT>(c.M2, y, zs);
+        for (int d = 0; d < D; ++d) zs[d * zst] = t_osz(zs[d * zst]);
+        load_col<D>(y, zs, zst);
+        matvec<D>(c.M2, y, zs, zst);
         double tot = 0.;
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            double base2pi = 6.283185307179586 * (zs[k * NT] + 0.5);
+            // cos(2 pi 3^j (z + 0.5)) through cospi: exact range reduction for arguments up to ~5e6 (libm cos would take
+            // its Payne-Hanek slow path there); agrees with the reference's cos(fl(2 pi (z+0.5)) 3^j) to ~1e-9 * 0.5^j
+            double zz = 2. * (zs[k * zst] + 0.5);
             double inner = 0., a = 1., b = 1.;
 #pragma unroll 1
             for (int j = 0; j < 12; ++j) {
-                inner += a * cos(base2pi * b);
+                inner += a * cospi(zz * b);
                 a *= 0.5; b *= 3.;
             }
             tot += inner;
@@ -254,12 +257,12 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
     }
     case 17: case 18: {                                  // Schaffers bbob.py:639-645
 #pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * NT], 0.5, c.cv1[d]);
-        matvec<D, NT>(c.M2, y, zs);
+        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * zst], 0.5, c.cv1[d]);
+        matvec<D>(c.M2, y, zs, zst);
         double f = 0.;
 #pragma unroll 1
         for (int k = 0; k + 1 < D; ++k) {
-            double a = zs[k * NT], b = zs[(k + 1) * NT];
+            double a = zs[k * zst], b = zs[(k + 1) * zst];
             double s = sqrt(a * a + b * b);
             double sn = sin(50. * pow(s, 0.2));
             f += sqrt(s) * (sn * sn + 1.);
@@ -271,7 +274,7 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double f = 0.;
 #pragma unroll 1
         for (int k = 0; k + 1 < D; ++k) {
-            double a = zs[k * NT], b = zs[(k + 1) * NT];
+            double a = zs[k * zst], b = zs[(k + 1) * zst];
             double u = a * a - b, w = 1. - a;
             double s = 100. * (u * u) + w * w;
             f += s / 4000. - cos(s);
@@ -295,28 +298,23 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         return 4.189828872724339 - 0.01 * (f / (double)D) + 100. * pen + bias;
     }
     case 21: case 22: {                                  // Gallagher bbob.py:795-799
+        // z_p = R (x - y_p) = R x - R y_p : one mat-vec per candidate, R y_p packed by the host (problem.py const_block)
         const int P = h.n_peaks;
-        const double* gy = G + ConstView<D>::kDoubles;
-        const double* gC = gy + P * D;
+        const double* gC = G + ConstView<D>::kDoubles + P * D;
         const double* gw = gC + P * D;
+        const double* gRy = gw + P;
         const double coef = -0.5 / (double)D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = X(d);
+        matvec<D>(c.R, y, zs, zst);
+        load_col<D>(y, zs, zst);
         double g = -1e300;
 #pragma unroll 1
         for (int p = 0; p < P; ++p) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) y[d] = X(d) - __ldg(gy + p * D + d);
             double acc = 0.;
-#pragma unroll 2
-            for (int k = 0; k < D; ++k) {
-                const double* row = c.R + k * D;
-                double a0 = 0., a1 = 0.;
 #pragma unroll
-                for (int d = 0; d + 1 < D; d += 2) {
-                    a0 = fma(row[d], y[d], a0);
-                    a1 = fma(row[d + 1], y[d + 1], a1);
-                }
-                if (D & 1) a0 = fma(row[D - 1], y[D - 1], a0);
-                double z = a0 + a1;
+            for (int k = 0; k < D; ++k) {
+                const double z = y[k] - __ldg(gRy + p * D + k);
                 acc += __ldg(gC + p * D + k) * (z * z);
             }
             g = fmax(g, __ldg(gw + p) * exp(coef * acc));
@@ -328,12 +326,12 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double prod = 1.;
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            double z = zs[k * NT], acc = 0., p2 = 2.;
+            double z = zs[k * zst], acc = 0., p2 = 2., ip2 = 0.5;
 #pragma unroll 4
             for (int j = 0; j < 32; ++j) {
                 double t = p2 * z;
-                acc += fabs(t - floor(t + 0.5)) / p2;
-                p2 *= 2.;
+                acc += fabs(t - floor(t + 0.5)) * ip2;      // == / 2^j exactly
+                p2 *= 2.; ip2 *= 0.5;
             }
             prod *= pow(1. + (double)(k + 1) * acc, h.sc[0]);
         }
@@ -349,7 +347,7 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         }
         double sc = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) sc += cos(6.283185307179586 * zs[k * NT]);
+        for (int k = 0; k < D; ++k) sc += cos(6.283185307179586 * zs[k * zst]);
         return fmin(s1, (double)D + h.sc[1] * s2) + 10. * ((double)D - sc) + 1e4 * pen_x<D>(X, ub) + bias;
     }
     }

@@ -75,7 +75,7 @@ __device__ __forceinline__ double dd_eval_one(const MbxInstance& h, const double
         f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31);
     } else if ((threadIdx.x & 31) == 0) {
         XF32 X{x};
-        f = bbob_true<D, 1>(h, sC, gC, X, scratch);
+        f = bbob_true<D>(h, sC, gC, X, scratch, 1);
         if (h.noise != MBX_NOISE_NONE) {
             double d0, d1, d2;
             if (noise_tape) { d0 = noise_tape[0]; d1 = noise_tape[tape_stride]; d2 = noise_tape[2 * tape_stride]; }

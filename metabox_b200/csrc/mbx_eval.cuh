@@ -32,7 +32,7 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
                                               const TX* tile, int n, int row0, double* scratch, TO* out,
                                               bool subtract_opt, const Philox& ph, uint32_t gen, uint32_t lane,
                                               uint32_t tag, const double* noise_tape, int tape_stride,
-                                              const unsigned char* only_mask = nullptr) {
+                                              const unsigned char* only_mask = nullptr, const int zst = MBX_NT) {
     if (KIND == MBX_KIND_PROTEIN) {
         const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
         double* ws = scratch + w * MBX_PROT_WARP_SCRATCH;
@@ -47,8 +47,8 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
         const int i = threadIdx.x;
         if (i < n && !(only_mask && !only_mask[i])) {
             double f;
-            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; f = bbob_true<D, MBX_NT>(h, sC, gC, X, scratch + i); }
-            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; f = bbob_true<D, MBX_NT>(h, sC, gC, X, scratch + i); }
+            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; f = bbob_true<D>(h, sC, gC, X, scratch + i, zst); }
+            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; f = bbob_true<D>(h, sC, gC, X, scratch + i, zst); }
             if (h.noise != MBX_NOISE_NONE) {
                 double d0, d1, d2;
                 if (noise_tape) {

@@ -206,7 +206,8 @@ class BBOB_Problem(Basic_Problem):
         M2 = self.M2 if self.M2 is not None else np.zeros((D, D))
         parts = [self.shift, self.rotate.reshape(-1), np.asarray(M2).reshape(-1), *self.cv]
         if self.peaks is not None:
-            parts += [self.peaks[0].reshape(-1), self.peaks[1].reshape(-1), self.peaks[2]]
+            parts += [self.peaks[0].reshape(-1), self.peaks[1].reshape(-1), self.peaks[2],
+                      np.matmul(self.peaks[0], self.rotate.T).reshape(-1)]      # R y_p (Gallagher: z_p = R x - R y_p)
         return np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1) for p in parts])
 
     def header(self, off):
