@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libmbx.so')
+# MBX_LIB selects a measurement build (libmbx_prof.so); the default is the product library
+LIB_PATH = os.environ.get('MBX_LIB') or os.path.join(_HERE, 'csrc', 'libmbx.so')
 
 MAX_DIM, MAX_NP, CURVE_LEN = 64, 128, 51
 KIND_BBOB, KIND_PROTEIN = 0, 1
@@ -91,7 +92,7 @@ SIGNATURES = {
                                   _P, _P, _P, C.c_int, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
-OPTIONAL_SIGNATURES = {}
+OPTIONAL_SIGNATURES = {'mbx_prof_read': (C.c_int, [_P, C.c_int])}     # only in libmbx_prof.so
 
 
 def lib():

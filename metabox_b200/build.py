@@ -34,9 +34,9 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def _compile(src, verbose):
-    obj = os.path.join(BUILD, src.replace('.cu', '.o'))
-    cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+def _compile(src, verbose, extra=(), bdir=BUILD):
+    obj = os.path.join(bdir, src.replace('.cu', '.o'))
+    cmd = [NVCC] + FLAGS + list(extra) + ['-c', os.path.join(CSRC, src), '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + '.log', 'w') as f:
@@ -48,19 +48,24 @@ def _compile(src, verbose):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, profile=False):
+    """profile=True builds the phase-instrumented variant libmbx_prof.so (-DMBX_PROFILE; measurement only, selected with
+    the MBX_LIB environment variable -- the product library is never instrumented)."""
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if not force and not needs_build():
+    lib = LIB.replace('libmbx.so', 'libmbx_prof.so') if profile else LIB
+    bdir = BUILD + '_prof' if profile else BUILD
+    if not profile and not force and not needs_build():
         return LIB
-    os.makedirs(BUILD, exist_ok=True)
+    os.makedirs(bdir, exist_ok=True)
+    extra = ['-DMBX_PROFILE=1'] if profile else []
     with cf.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart']
+        objs = list(ex.map(lambda s: _compile(s, verbose, extra, bdir), srcs))
+    cmd = [NVCC, '-shared', '-o', lib] + objs + ['-lcudart']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, profile='--profile' in sys.argv))

@@ -29,14 +29,14 @@ struct ConstView {          // shared-memory views of one BBOB instance
 
 __device__ __forceinline__ double t_osz(double x) {       // bbob.py:51-67
     double ax = fabs(x);
-    double t = log(ax) / 0.1;
+    double t = log(ax) * 10.;                              // reference: / 0.1 (<= 1 ulp apart)
     double c1 = x > 0. ? 1.0 : 0.55, c2 = x > 0. ? 0.79 : 0.31;
     // reference: (exp(t + 0.49(sin c1 t + sin c2 t)))^0.1 ; exp(0.1 u) == exp(u)^0.1 up to a few ulp and saves the pow
     double r = exp((t + 0.49 * (sin(c1 * t) + sin(c2 * t))) * 0.1);
     return x > 0. ? r : (x < 0. ? -r : x);
 }
 __device__ __forceinline__ double t_asy(double x, double beta, double frac) {   // bbob.py:70-82
-    return x > 0. ? pow(x, 1. + beta * frac * sqrt(x)) : x;
+    return x > 0. ? exp((1. + beta * frac * sqrt(x)) * log(x)) : x;      // x^e as exp(e ln x): a few ulp, far inside 1e-6
 }
 template <int D, class XA>
 __device__ __forceinline__ double pen_x(const XA& X, double ub) {               // bbob.py:85-93
@@ -75,7 +75,7 @@ __device__ __forceinline__ double rastrigin_sum(const double* zs, const int zst)
 #pragma unroll 1
     for (int k = 0; k < D; ++k) {
         double z = zs[k * zst];
-        sc += cos(6.283185307179586 * z);
+        sc += cospi(2. * z);                               // cos(2 pi z) without the libm range reduction
         sq += z * z;
     }
     return 10. * ((double)D - sc) + sq;
@@ -90,6 +90,71 @@ __device__ __forceinline__ double rosen_sum(const double* zs, const int zst) {
         f += 100. * (u * u) + w * w;
     }
     return f;
+}
+
+// Gallagher: max_p w_p exp(-(1/2D) sum_k C_pk (y_k - (R y_p)_k)^2), y = R x in zs (bbob.py:795-799).
+// exp is monotone, so the maximum is attained at argmax_p s_p, s_p = ln w_p - acc_p / 2D.  The P x D scan runs in float32
+// (packed f32x2, constants pre-rounded by the host).  Error budget of the float32 acc_p: each z_k = y_k - c_k is off by at
+// most E = 1.3e-7 (max|y| + 5 sqrt(D) + 1) (input roundings + the subtraction; |c| <= |y_p|_2 <= 5 sqrt(D)), which moves
+// sum C z^2 by <= 2 E sqrt(sum C) sqrt(acc) + E^2 sum C (Cauchy-Schwarz; C_pk <= sqrt(1000) so sum C <= 31.7 D); products and
+// the non-negative summation add <= (D + 4) 2^-24 acc.  delta_p = |coef| (K1 sqrt(acc) + 4e-6 acc) + 3e-6 bounds the error
+// of s_p with margin (ln w, coef and the final fma roundings are ~1e-7 |s|).  The scan keeps the best
+// s_p and the highest upper bound among the others; when the best lower bound clears that upper bound, the float64 value
+// is computed for that peak alone with the reference's operation order -- bit-identical to evaluating all P peaks in
+// float64.  Otherwise (near-tie) the candidate falls back to the full float64 loop.
+template <int D>
+__device__ __forceinline__ double gallagher_peak64(const double* __restrict__ gC, const double* __restrict__ gRy, const double* __restrict__ gw,
+                                                   const int p, const double* zs, const int zst, const double coef) {
+    double acc = 0.;
+#pragma unroll 2
+    for (int k = 0; k < D; ++k) {
+        const double z = zs[k * zst] - __ldg(gRy + p * D + k);
+        acc += __ldg(gC + p * D + k) * (z * z);
+    }
+    return __ldg(gw + p) * exp(coef * acc);
+}
+template <int D>
+__device__ __forceinline__ double gallagher_max(const double* __restrict__ G, const int P, const double* zs, const int zst) {
+    static_assert(D % 2 == 0, "packed float32 screening pairs adjacent dimensions");
+    const double* gC = G + ConstView<D>::kDoubles + P * D;
+    const double* gw = gC + P * D;
+    const double* gRy = gw + P;
+    const int o32 = (ConstView<D>::kDoubles + 3 * P * D + P + 1) & ~1;
+    const float4* g32 = reinterpret_cast<const float4*>(G + o32);
+    const float* lnw = reinterpret_cast<const float*>(G + o32 + P * D);
+    const double coef = -0.5 / (double)D;
+    const float coef32 = (float)coef;
+    float2 yf[D / 2];
+#pragma unroll
+    for (int k = 0; k < D / 2; ++k) yf[k] = make_float2((float)zs[(2 * k) * zst], (float)zs[(2 * k + 1) * zst]);
+    float ymax = 0.f;
+#pragma unroll
+    for (int k = 0; k < D / 2; ++k) ymax = fmaxf(ymax, fmaxf(fabsf(yf[k].x), fabsf(yf[k].y)));
+    const float K1 = -coef32 * 2.f * 1.3e-7f * (ymax + 5.f * sqrtf((float)D) + 1.f) * sqrtf(31.7f * (float)D);
+    float s1 = -INFINITY, lo1 = -INFINITY, hi2 = -INFINITY;
+    int p1 = 0;
+#pragma unroll 1
+    for (int p = 0; p < P; ++p) {
+        float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < D / 2; ++k) {
+            const float4 c4 = __ldg(g32 + p * (D / 2) + k);
+            const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
+            const float2 wz = __fmul2_rn(make_float2(c4.x, c4.y), z);
+            acc2 = __ffma2_rn(wz, z, acc2);
+        }
+        const float acc = acc2.x + acc2.y;
+        const float s = fmaf(coef32, acc, __ldg(lnw + p));
+        const float dl = fmaf(K1, sqrtf(acc), fmaf(-4e-6f * coef32, acc, 3e-6f));
+        const float hi = s + dl, lo = s - dl;
+        if (s > s1) { hi2 = fmaxf(hi2, s1 + (s1 - lo1)); s1 = s; lo1 = lo; p1 = p; }
+        else hi2 = fmaxf(hi2, hi);
+    }
+    if (lo1 > hi2) return gallagher_peak64<D>(gC, gRy, gw, p1, zs, zst, coef);
+    double g = -1e300;                                     // near-tie (or non-finite input): all peaks in float64
+#pragma unroll 1
+    for (int p = 0; p < P; ++p) g = fmax(g, gallagher_peak64<D>(gC, gRy, gw, p, zs, zst, coef));
+    return g;
 }
 
 // Noise-free f(x) incl. bias and boundary handling  (== BBOB_Basic_Problem.func)
@@ -223,8 +288,8 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
     case 14: {                                           // Different powers bbob.py:550-554
         double f = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) f += pow(fabs(zs[k * zst]), c.cv0[k]);
-        return pow(f, 0.5) + bias + bh;
+        for (int k = 0; k < D; ++k) f += exp(c.cv0[k] * log(fabs(zs[k * zst])));     // |z|^e ; z = 0 -> exp(-inf) = 0
+        return sqrt(f) + bias + bh;
     }
     case 15: {                                           // Rastrigin F15 bbob.py:597-602
 #pragma unroll 1
@@ -241,14 +306,20 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double tot = 0.;
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            // cos(2 pi 3^j (z + 0.5)) through cospi: exact range reduction for arguments up to ~5e6 (libm cos would take
-            // its Payne-Hanek slow path there); agrees with the reference's cos(fl(2 pi (z+0.5)) 3^j) to ~1e-9 * 0.5^j
-            double zz = 2. * (zs[k * zst] + 0.5);
-            double inner = 0., a = 1., b = 1.;
-#pragma unroll 1
-            for (int j = 0; j < 12; ++j) {
-                inner += a * cospi(zz * b);
-                a *= 0.5; b *= 3.;
+            // sum_j 0.5^j cos(2 pi 3^j (z + 0.5)): (cos, sin) of the base angle once (sincospi: exact range reduction), then
+            // the triple-angle map (c, s) -> (c (1 - 4 s^2), s (4 c^2 - 1)) eleven times.  The pair form has no 1/sin
+            // blow-up: an angle error triples per step, so term j carries <= 3^j ulp * 0.5^j weight (~1e-14 in total),
+            // below the reference's own cos(fl(2 pi (z + 0.5)) 3^j) argument rounding.
+            double sn, cs;
+            sincospi(2. * (zs[k * zst] + 0.5), &sn, &cs);
+            double inner = cs, a = 0.5;
+#pragma unroll
+            for (int j = 1; j < 12; ++j) {
+                const double c2 = cs * cs, s2 = sn * sn;
+                cs = cs * (1. - 4. * s2);
+                sn = sn * (4. * c2 - 1.);
+                inner = fma(a, cs, inner);
+                a *= 0.5;
             }
             tot += inner;
         }
@@ -264,7 +335,7 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         for (int k = 0; k + 1 < D; ++k) {
             double a = zs[k * zst], b = zs[(k + 1) * zst];
             double s = sqrt(a * a + b * b);
-            double sn = sin(50. * pow(s, 0.2));
+            double sn = sin(50. * exp(0.2 * log(s)));          // s^0.2 ; s = 0 -> 0
             f += sqrt(s) * (sn * sn + 1.);
         }
         double m = (1. / (double)(D - 1)) * f;
@@ -299,26 +370,10 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
     }
     case 21: case 22: {                                  // Gallagher bbob.py:795-799
         // z_p = R (x - y_p) = R x - R y_p : one mat-vec per candidate, R y_p packed by the host (problem.py const_block)
-        const int P = h.n_peaks;
-        const double* gC = G + ConstView<D>::kDoubles + P * D;
-        const double* gw = gC + P * D;
-        const double* gRy = gw + P;
-        const double coef = -0.5 / (double)D;
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = X(d);
         matvec<D>(c.R, y, zs, zst);
-        load_col<D>(y, zs, zst);
-        double g = -1e300;
-#pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-            double acc = 0.;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const double z = y[k] - __ldg(gRy + p * D + k);
-                acc += __ldg(gC + p * D + k) * (z * z);
-            }
-            g = fmax(g, __ldg(gw + p) * exp(coef * acc));
-        }
+        double g = gallagher_max<D>(G, h.n_peaks, zs, zst);
         double t = t_osz(10. - g);
         return t * t + bias + bh;
     }
@@ -326,14 +381,18 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         double prod = 1.;
 #pragma unroll 1
         for (int k = 0; k < D; ++k) {
-            double z = zs[k * zst], acc = 0., p2 = 2., ip2 = 0.5;
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
-                double t = p2 * z;
-                acc += fabs(t - floor(t + 0.5)) * ip2;      // == / 2^j exactly
-                p2 *= 2.; ip2 *= 0.5;
+            // sum_{j=1..32} |2^j z - round(2^j z)| / 2^j : every term is exact in binary64 (power-of-two scalings, |2^j z| <
+            // 2^51); round() through the 1.5*2^52 magic constant (ties give the same |.| = 0.5 as the reference's floor(t+.5))
+            const double z = zs[k * zst];
+            double acc = 0.;
+#pragma unroll
+            for (int j = 1; j <= 32; ++j) {
+                const double p2 = (double)(1ull << j), ip2 = 1. / (double)(1ull << j);
+                const double t = p2 * z;
+                const double r = (t + 6755399441055744.) - 6755399441055744.;
+                acc = fma(fabs(t - r), ip2, acc);
             }
-            prod *= pow(1. + (double)(k + 1) * acc, h.sc[0]);
+            prod *= exp(h.sc[0] * log(1. + (double)(k + 1) * acc));
         }
         return prod * h.sc[1] - h.sc[1] + pen_x<D>(X, ub) + bias;
     }
@@ -347,7 +406,7 @@ __device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, 
         }
         double sc = 0.;
 #pragma unroll 1
-        for (int k = 0; k < D; ++k) sc += cos(6.283185307179586 * zs[k * zst]);
+        for (int k = 0; k < D; ++k) sc += cospi(2. * zs[k * zst]);
         return fmin(s1, (double)D + h.sc[1] * s2) + 10. * ((double)D - sc) + 1e4 * pen_x<D>(X, ub) + bias;
     }
     }

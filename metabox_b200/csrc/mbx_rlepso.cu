@@ -6,7 +6,34 @@
 #include "mbx_eval.cuh"
 #include "mbx_launch.h"
 
-#define FDR_IB 2      // ranks per block in the sorted FDR scan
+
+// Phase profiling build (python -m metabox_b200.build --profile -> libmbx_prof.so, never the product library): thread 0 of
+// every CTA accumulates clock64() deltas per phase into g_prof; read back with mbx_prof_read().
+#ifdef MBX_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_INIT long long tp_ = clock64();
+#define PROF_MARK(k)                                                                   \
+    do {                                                                               \
+        if (threadIdx.x == 0) {                                                        \
+            long long t_ = clock64();                                                  \
+            atomicAdd(&g_prof[k], (unsigned long long)(t_ - tp_));                     \
+            tp_ = t_;                                                                  \
+        }                                                                              \
+    } while (0)
+extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
+    if (cudaMemcpyFromSymbol(h16, g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return MBX_ECUDA;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return MBX_ECUDA;
+    }
+    return MBX_OK;
+}
+#define PROF_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)(v)); } while (0)
+#else
+#define PROF_INIT
+#define PROF_MARK(k)
+#define PROF_ADD(k, v)
+#endif
 
 // Shared-memory plan, sized by the run-time population size (NP = 100 -> 62 KB at D = 30: 3 CTAs per SM).
 struct RlLayout {
@@ -37,6 +64,8 @@ struct RlepsoViews {
     float *xs, *pf32, *nc, *cc, *tmpf;
     int *pni, *rank, *order;
     unsigned char *tgt, *mask, *better;
+    unsigned short* fbl;        // FDR items that need the exact float64 pass (aliases xs: written before P2 fills xs)
+    int* nfb;
     float* redv;
     int* redi;
     __device__ __forceinline__ RlepsoViews(unsigned char* s, const RlLayout& L) {
@@ -56,6 +85,8 @@ struct RlepsoViews {
         tgt = s + L.oTgt; mask = tgt + N * D; better = mask + N;
         redv = reinterpret_cast<float*>(s + L.oRed);
         redi = reinterpret_cast<int*>(s + L.oRed + 32);
+        nfb = reinterpret_cast<int*>(s + L.oRed + 56);
+        fbl = reinterpret_cast<unsigned short*>(xs);
     }
 };
 
@@ -73,6 +104,66 @@ __device__ __forceinline__ bool log_and_done(const MbxRunConfig& cfg, bool has_o
         else { curve[clen] = gbest; clen += 1; }
     }
     return done;
+}
+
+// FDR pass 1: float32 screening (see the comment at the call site).  Work item = (pair of 2-rank blocks {m, nb-1-m},
+// pair of dimensions): every item scans ~NP candidates.  Sign convention: a = pf[s]-pf[r] <= 0; the carried best is
+// (nab, bb) = (-a_best, q_best); candidate wins iff  a*bb + nab*q < 0.
+#define FDR_TAU 1e-6f
+#define FDR_TINY 1e-35f
+struct FdrChain {          // two ranks x two dims
+    float2 nab, bb;
+    int jx, jy;
+    bool amb;
+};
+__device__ __forceinline__ void fdr_visit(FdrChain& c, const float2 s2, const float2 x2, const float2 npf, const float2 npx, const int s) {
+    const float2 a = __fadd2_rn(s2, npf);
+    const float2 dq = __fadd2_rn(x2, npx);
+    const float2 q = make_float2(fabsf(dq.x) + 1e-5f, fabsf(dq.y) + 1e-5f);
+    const float2 nr = __fmul2_rn(c.nab, q);
+    const float2 m = __ffma2_rn(a, c.bb, nr);
+    const float2 t = __ffma2_rn(nr, make_float2(FDR_TAU, FDR_TAU), make_float2(FDR_TINY, FDR_TINY));
+    c.amb = c.amb || !(fabsf(m.x) > t.x) || !(fabsf(m.y) > t.y);
+    if (m.x < 0.f) { c.nab.x = -a.x; c.bb.x = q.x; c.jx = s; }
+    if (m.y < 0.f) { c.nab.y = -a.y; c.bb.y = q.y; c.jy = s; }
+}
+template <int D>
+__device__ __forceinline__ void fdr_screen(const int NP, const int tid, const float* __restrict__ spx, const float2* __restrict__ spf2,
+                                           const int* __restrict__ order, unsigned char* tgt, unsigned short* fbl, int* nfb) {
+    static_assert(D % 2 == 0, "the packed FDR scan pairs adjacent dimensions");
+    constexpr int DP = D / 2;
+    const int nb = (NP + 1) / 2, npair = (nb + 1) / 2;
+    for (int w = tid; w < npair * DP; w += MBX_NT) {
+        const int pq = w / DP, d = 2 * (w - pq * DP);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int m = half ? nb - 1 - pq : pq;
+            if (half && m == pq) break;
+            const int ra = 2 * m, rb = ra + 1;
+            const bool hasb = rb < NP;
+            const float2 pxa = *reinterpret_cast<const float2*>(spx + ra * D + d), pfa = spf2[ra];
+            const float2 pxb = hasb ? *reinterpret_cast<const float2*>(spx + rb * D + d) : pxa, pfb = hasb ? spf2[rb] : pfa;
+            const float2 npxa = make_float2(-pxa.x, -pxa.y), npfa = make_float2(-pfa.x, -pfa.y);
+            const float2 npxb = make_float2(-pxb.x, -pxb.y), npfb = make_float2(-pfb.x, -pfb.y);
+            FdrChain A{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), ra, ra, false};      // start from j = i (ratio 0)
+            FdrChain B{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), rb, rb, false};
+#pragma unroll 2
+            for (int s = 0; s < ra; ++s) {
+                const float2 x2 = *reinterpret_cast<const float2*>(spx + s * D + d), s2 = spf2[s];
+                fdr_visit(A, s2, x2, npfa, npxa, s);
+                fdr_visit(B, s2, x2, npfb, npxb, s);
+            }
+            if (hasb) fdr_visit(B, pfa, pxa, npfb, npxb, ra);                  // candidate s = ra for the block's second rank
+            const int oa = order[ra] * D + d;
+            if (A.amb) { const int k = atomicAdd(nfb, 2); fbl[k] = (unsigned short)(ra * D + d); fbl[k + 1] = (unsigned short)(ra * D + d + 1); }
+            else { tgt[oa] = (unsigned char)A.jx; tgt[oa + 1] = (unsigned char)A.jy; }
+            if (hasb) {
+                const int ob = order[rb] * D + d;
+                if (B.amb) { const int k = atomicAdd(nfb, 2); fbl[k] = (unsigned short)(rb * D + d); fbl[k + 1] = (unsigned short)(rb * D + d + 1); }
+                else { tgt[ob] = (unsigned char)B.jx; tgt[ob + 1] = (unsigned char)B.jy; }
+            }
+        }
+    }
 }
 
 // =====================================================================================================
@@ -128,6 +219,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     const int b = blockIdx.x;
     if (S.done[b]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    PROF_INIT
     const int NP = cfg.NP, tid = threadIdx.x;
     const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN);
     RlepsoViews<D, KIND> V(smem_raw, L);
@@ -136,7 +228,6 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b];
     Philox ph(cfg.seed);
-    double* spx = V.A;                                   // pbest_x as f64, rows in ascending-pbest order
     // ---- P0: per-particle scalars, draws, coefficients (:112-132) -------------------------------------------
     for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
     if (tid < NP) {
@@ -162,57 +253,51 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         gc[3] = (double)(scale * a5); gc[4] = (double)(scale * a6);
     }
     __syncthreads();
-    // ---- P0b: stable rank of the pbest costs; sorted f64 copies of pbest / pbest_x ----------------------------------
+    PROF_MARK(0);
+    // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
+    float* spx = reinterpret_cast<float*>(V.A);          // pbest_x rows in ascending-pbest order [NP*D]
+    float2* spf2 = reinterpret_cast<float2*>(V.spf);     // sorted pbest, duplicated (f, f) for the packed FDR scan
     if (tid < NP) {
         const float fi = V.pf32[tid];
         int r = 0;
         for (int j = 0; j < NP; ++j) { const float fj = V.pf32[j]; r += (fj < fi || (fj == fi && j < tid)) ? 1 : 0; }
-        V.rank[tid] = r; V.order[r] = tid; V.spf[r] = (double)fi;
+        V.rank[tid] = r; V.order[r] = tid; spf2[r] = make_float2(fi, fi);
     }
+    if (tid == 0) *V.nfb = 0;
     __syncthreads();
-    for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; spx[V.rank[i] * D + (e - i * D)] = (double)S.pbest_x[base + e]; }
+    for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; spx[V.rank[i] * D + (e - i * D)] = S.pbest_x[base + e]; }
     __syncthreads();
+    PROF_MARK(1);
     const MbxInstance& h = *V.h;
     const double lb = h.lb, ub = h.ub, vmax = 0.1 * (ub - lb);
-    // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5)   (:97-103) ------------------
+    // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5), first minimum   (:97-103) ----
     // The minimum is <= 0 (j = i gives 0), so only particles with a strictly better pbest -- the ones BEFORE i in the
-    // sorted order -- and exact ties can win: particle of rank r scans s < r only (half the pairs on average).
-    // a/b < a'/b'  <=>  a*b' < a'*b  (b,b' > 0): cross-multiplication in f64; exact ties -> lowest original index (np.argmin).
-    // Work item = (pair of rank blocks {m, nb-1-m}, d): every item scans ~NP candidates.
+    // sorted order -- can win (equal costs tie with j = i at ratio 0 and are resolved by the index rule).
+    // Pass 1 (all items): float32 screening by cross-multiplication  a/q < a'/q'  <=>  a q' < a' q  (q, q' > 0) on the
+    // float32 inputs, packed f32x2 over two adjacent dimensions, two ranks per thread (4 independent chains).  Every
+    // comparison whose margin is below TAU (>= 3x the worst-case float32 rounding of both sides), or is NaN, marks the
+    // (rank, d) item ambiguous.  Pass 2 (ambiguous items only, compacted): the reference's own float64 divisions and
+    // first-index argmin.  An unambiguous float32 winner beats every other candidate by > 1e-6 relative, so the float64
+    // quotients are ordered the same way and the result equals np.argmin exactly.
+    fdr_screen<D>(NP, tid, spx, spf2, V.order, V.tgt, V.fbl, V.nfb);
+    __syncthreads();
     {
-        const int nb = (NP + FDR_IB - 1) / FDR_IB, npair = (nb + 1) / 2;
-        for (int w = tid; w < npair * D; w += MBX_NT) {
-            const int pq = w / D, d = w - pq * D;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int m = half ? nb - 1 - pq : pq;
-                if (half && m == pq) break;
-                const int ra = m * FDR_IB, rb = ra + 1;
-                const bool hasb = rb < NP;
-                const double pxa = spx[ra * D + d], pfa = V.spf[ra];
-                const double pxb = hasb ? spx[rb * D + d] : pxa, pfb = hasb ? V.spf[rb] : pfa;
-                double abA = 0., bbA = 1e-5, abB = 0., bbB = 1e-5;       // start from j = i (ratio 0)
-                int jsA = ra, jsB = rb;
-#pragma unroll 2
-                for (int s = 0; s < ra; ++s) {
-                    const double pxs = spx[s * D + d], pfs = V.spf[s];
-                    const double a1 = pfs - pfa, q1 = fabs(pxs - pxa) + 1e-5;
-                    const double a2 = pfs - pfb, q2 = fabs(pxs - pxb) + 1e-5;
-                    const double l1 = a1 * bbA, r1 = abA * q1, l2 = a2 * bbB, r2 = abB * q2;
-                    if (l1 < r1 || (l1 == r1 && V.order[s] < V.order[jsA])) { abA = a1; bbA = q1; jsA = s; }
-                    if (l2 < r2 || (l2 == r2 && V.order[s] < V.order[jsB])) { abB = a2; bbB = q2; jsB = s; }
-                }
-                if (hasb) {                                              // candidate s = ra for the second rank of the block
-                    const double a2 = pfa - pfb, q2 = fabs(pxa - pxb) + 1e-5;
-                    const double l2 = a2 * bbB, r2 = abB * q2;
-                    if (l2 < r2 || (l2 == r2 && V.order[ra] < V.order[jsB])) { abB = a2; bbB = q2; jsB = ra; }
-                    V.tgt[V.order[rb] * D + d] = (unsigned char)jsB;
-                }
-                V.tgt[V.order[ra] * D + d] = (unsigned char)jsA;
+        const int nfb = *V.nfb;
+        PROF_ADD(6, nfb); PROF_ADD(7, NP * D);
+        for (int k = tid; k < nfb; k += MBX_NT) {
+            const int item = V.fbl[k], r = item / D, d = item - r * D;
+            const double pxr = (double)spx[r * D + d], pfr = (double)spf2[r].x;
+            double best = 0.; int bs = r, bo = V.order[r];
+            for (int s = 0; s < r; ++s) {
+                const double q = ((double)spf2[s].x - pfr) / (fabs((double)spx[s * D + d] - pxr) + 1e-5);
+                const int o = V.order[s];
+                if (q < best || (q == best && o < bo)) { best = q; bs = s; bo = o; }
             }
+            V.tgt[V.order[r] * D + d] = (unsigned char)bs;
         }
     }
     __syncthreads();
+    PROF_MARK(2);
     // ---- P2: velocity + position, element-wise over (i,d)   (:76-95, :105-109, :179-195) ---------------
     for (int e = tid; e < NP * D; e += MBX_NT) {
         const int i = e / D, d = e - i * D;
@@ -224,13 +309,13 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             uint4 w = ph((uint32_t)e, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_PD);
             ru = u01(w.x); t0 = bounded(w.y, NP); t1 = bounded(w.z, NP); fu = u01(w.w);
         }
-        const double x = (double)S.x[base + e], v = (double)S.v[base + e], pxi = spx[V.rank[i] * D + d];
+        const double x = (double)S.x[base + e], v = (double)S.v[base + e], pxi = (double)spx[V.rank[i] * D + d];
         const int tsel = (V.pf32[t1] < V.pf32[t0]) ? t1 : t0;          // argmin of the 2 picks, tie -> first
-        const double own = (ru > pci[i]) ? pxi : spx[V.rank[tsel] * D + d];
+        const double own = (ru > pci[i]) ? pxi : (double)spx[V.rank[tsel] * D + d];
         const double v_clpso = ru * (own - x);
         const int tg = V.tgt[e];                                       // sorted position of the FDR target
         if (dbg) dbg[base + e] = V.order[tg];
-        const double v_fdr = fu * (spx[tg * D + d] - pxi);
+        const double v_fdr = fu * ((double)spx[tg * D + d] - pxi);
         const double v_pbest = V.r1[i] * (pxi - x);
         const double v_gbest = V.r2[i] * (V.gx[d] - x);
         const int per = NP / 5;
@@ -244,10 +329,12 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         S.x[base + e] = nx32; S.v[base + e] = (float)nv;
     }
     __syncthreads();
+    PROF_MARK(3);
     // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                          MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP, nullptr, L.NPp);
     __syncthreads();
+    PROF_MARK(4);
     // ---- P4: pbest / gbest / patience / re-init mask (:200-238) ------------------------------------------
     int fes = S.fes[b] + NP;
     float gbest = S.gbest_val[b];
@@ -327,6 +414,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         }
     }
     if (tid < NP) S.pni[pb + tid] = V.pni[tid];
+    PROF_MARK(5);
     // ---- P6: bookkeeping (:225-228, :241-261) ----------------------------------------------------------------
     if (tid == 0) {
         if (gidx >= 0) { S.gbest_val[b] = gbest; S.gbest_idx[b] = gidx; }

@@ -206,8 +206,17 @@ class BBOB_Problem(Basic_Problem):
         M2 = self.M2 if self.M2 is not None else np.zeros((D, D))
         parts = [self.shift, self.rotate.reshape(-1), np.asarray(M2).reshape(-1), *self.cv]
         if self.peaks is not None:
-            parts += [self.peaks[0].reshape(-1), self.peaks[1].reshape(-1), self.peaks[2],
-                      np.matmul(self.peaks[0], self.rotate.T).reshape(-1)]      # R y_p (Gallagher: z_p = R x - R y_p)
+            y, Cm, w = self.peaks
+            Ry = np.matmul(y, self.rotate.T)                                    # R y_p (Gallagher: z_p = R x - R y_p)
+            parts += [y.reshape(-1), Cm.reshape(-1), w, Ry.reshape(-1)]
+            # float32 screening copies (mbx_bbob.cuh gallagher_max): per peak D/2 groups (C_k, C_k+1, Ry_k, Ry_k+1), then
+            # ln(w_p); the group array starts on a 16-byte boundary (every instance block starts on one, see pack_host)
+            P = y.shape[0]
+            if (4 * D + 2 * D * D + 3 * P * D + P) % 2:
+                parts.append(np.zeros(1))
+            g = np.concatenate([Cm.reshape(P, D // 2, 2), Ry.reshape(P, D // 2, 2)], axis=2).astype(np.float32).reshape(-1)
+            lnw = np.zeros(P + (P % 2), dtype=np.float32); lnw[:P] = np.log(w)
+            parts += [g.view(np.float64), lnw.view(np.float64)]
         return np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1) for p in parts])
 
     def header(self, off):
@@ -353,6 +362,8 @@ def pack_host(problems):
     blocks, headers, off = [], [], 0
     for p in problems:
         blk = p.const_block()
+        if blk.size % 2:                                        # keep every block 16-byte aligned
+            blk = np.concatenate([blk, np.zeros(1)])
         headers.append(p.header(off))
         blocks.append(blk)
         off += blk.size

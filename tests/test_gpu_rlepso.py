@@ -236,3 +236,40 @@ def test_done_lanes_are_frozen_and_empty_batch():
     assert torch.equal(snap[0], eng.x) and torch.equal(snap[1], eng.fes) and torch.equal(snap[2], eng.curve)
     e0 = mo.RLEPSO_Engine(pack, [], 300, 50, log_interval=6)
     e0.init_population(); e0.update(torch.zeros(0, 35).to(eng.device))
+
+
+@pytest.mark.parametrize('dim', [10, 30])
+def test_fdr_targets_exact_incl_ties_duplicates_and_converged_swarms(dim):
+    """FDR target indices (rlepso_optimizer.py:97-103) must equal np.argmin of the float64 quotients exactly.  The kernel
+    screens in float32 and re-does ambiguous items with the reference's float64 divisions: crafted swarms hit both
+    paths -- random, duplicated rows, all-equal costs, equal-cost groups, collapsed swarms (coordinates equal up to a few
+    float32 ulps), huge / tiny cost scales."""
+    import torch
+    from metabox_b200 import optimizer as mo, problem as mp
+    from oracle import rlepso as orl
+    NP = 100
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', dim, 5)
+    pack = mp.InstancePack(te.data[:1])
+    g = np.random.RandomState(5)
+    cases = []
+    px = g.uniform(-5, 5, (NP, dim)); pf = g.uniform(0, 100, NP); cases.append(('random', px, pf))
+    px2 = px.copy(); px2[10:40] = px2[0:30]; cases.append(('duplicated rows', px2, pf))
+    cases.append(('all costs equal', px, np.full(NP, 3.25)))
+    pf3 = np.repeat(g.uniform(0, 10, 10), 10); g.shuffle(pf3); cases.append(('equal-cost groups', px, pf3))
+    c = g.uniform(-4, 4, dim).astype(np.float32).astype(np.float64)
+    px4 = c[None, :] * (1 + g.randint(-3, 4, (NP, dim)) * 2.0 ** -23); cases.append(('collapsed swarm', px4, g.uniform(1e-8, 2e-8, NP)))
+    px5 = c[None, :] + np.zeros((NP, dim)); cases.append(('identical positions', px5, g.uniform(0, 1, NP)))
+    cases.append(('huge costs', px, g.uniform(0, 1, NP) * 1e30))
+    cases.append(('tiny costs', px, g.uniform(0, 1, NP) * 1e-30))
+    pf8 = pf.copy(); pf8[0:99:3] = pf8[1:100:3]; px8 = np.round(px * 4) / 4; cases.append(('grid positions + cost ties', px8, pf8))
+    B = len(cases)
+    eng = mo.RLEPSO_Engine(pack, [0] * B, 2000 * dim, 50, seed=1)
+    eng.init_population()
+    PX = np.stack([c_[1] for c_ in cases]).astype(np.float32); PF = np.stack([c_[2] for c_ in cases]).astype(np.float32)
+    eng.pbest_x.copy_(torch.as_tensor(PX)); eng.pbest.copy_(torch.as_tensor(PF))
+    dbg = torch.full((B, NP, dim), -1, dtype=torch.int32, device=eng.device)
+    eng.update(torch.rand(B, 35).to(eng.device), dbg=dbg)
+    got = dbg.cpu().numpy()
+    for b, (name, _, _) in enumerate(cases):
+        want = orl.fdr_targets(PX[b].astype(np.float64), PF[b].astype(np.float64))
+        np.testing.assert_array_equal(got[b], want, err_msg=f'FDR targets: {name} (dim {dim})')
