@@ -113,9 +113,26 @@ __device__ __forceinline__ double gallagher_peak64(const double* __restrict__ gC
     }
     return __ldg(gw + p) * exp(coef * acc);
 }
+struct GalScan {            // running (best s, its lower bound, its peak) and the highest upper bound among the others
+    float s1 = -INFINITY, lo1 = -INFINITY, hi2 = -INFINITY;
+    int p1 = 0;
+    __device__ __forceinline__ void visit(const float acc, const float lnw, const float coef32, const float K1, const int p) {
+        const float s = fmaf(coef32, acc, lnw);
+        const float dl = fmaf(K1, sqrtf(acc), fmaf(-4e-6f * coef32, acc, 3e-6f));
+        const float hi = s + dl, lo = s - dl;
+        if (s > s1) { hi2 = fmaxf(hi2, s1 + (s1 - lo1)); s1 = s; lo1 = lo; p1 = p; }
+        else hi2 = fmaxf(hi2, hi);
+    }
+};
+// `tile` (optional): shared-memory staging buffer of `tile_bytes` bytes, 16-byte aligned.  With a tile, ALL threads of the
+// CTA must call (it contains __syncthreads; `act` = this thread has a candidate): the float32 peak table is streamed
+// through shared memory once per CTA (register double-buffered) and broadcast to the threads, instead of every warp
+// pulling it through L1/L2 again.  Without a tile (tile == nullptr) only active threads call and peaks come from __ldg.
 template <int D>
-__device__ __forceinline__ double gallagher_max(const double* __restrict__ G, const int P, const double* zs, const int zst) {
+__device__ __forceinline__ double gallagher_max(const double* __restrict__ G, const int P, const double* zs, const int zst,
+                                                const bool act = true, float4* tile = nullptr, const int tile_bytes = 0) {
     static_assert(D % 2 == 0, "packed float32 screening pairs adjacent dimensions");
+    constexpr int HD = D / 2;
     const double* gC = G + ConstView<D>::kDoubles + P * D;
     const double* gw = gC + P * D;
     const double* gRy = gw + P;
@@ -124,37 +141,97 @@ __device__ __forceinline__ double gallagher_max(const double* __restrict__ G, co
     const float* lnw = reinterpret_cast<const float*>(G + o32 + P * D);
     const double coef = -0.5 / (double)D;
     const float coef32 = (float)coef;
-    float2 yf[D / 2];
-#pragma unroll
-    for (int k = 0; k < D / 2; ++k) yf[k] = make_float2((float)zs[(2 * k) * zst], (float)zs[(2 * k + 1) * zst]);
+    float2 yf[HD];
     float ymax = 0.f;
+    if (act) {
 #pragma unroll
-    for (int k = 0; k < D / 2; ++k) ymax = fmaxf(ymax, fmaxf(fabsf(yf[k].x), fabsf(yf[k].y)));
-    const float K1 = -coef32 * 2.f * 1.3e-7f * (ymax + 5.f * sqrtf((float)D) + 1.f) * sqrtf(31.7f * (float)D);
-    float s1 = -INFINITY, lo1 = -INFINITY, hi2 = -INFINITY;
-    int p1 = 0;
-#pragma unroll 1
-    for (int p = 0; p < P; ++p) {
-        float2 acc2 = make_float2(0.f, 0.f);
+        for (int k = 0; k < HD; ++k) yf[k] = make_float2((float)zs[(2 * k) * zst], (float)zs[(2 * k + 1) * zst]);
 #pragma unroll
-        for (int k = 0; k < D / 2; ++k) {
-            const float4 c4 = __ldg(g32 + p * (D / 2) + k);
-            const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
-            const float2 wz = __fmul2_rn(make_float2(c4.x, c4.y), z);
-            acc2 = __ffma2_rn(wz, z, acc2);
-        }
-        const float acc = acc2.x + acc2.y;
-        const float s = fmaf(coef32, acc, __ldg(lnw + p));
-        const float dl = fmaf(K1, sqrtf(acc), fmaf(-4e-6f * coef32, acc, 3e-6f));
-        const float hi = s + dl, lo = s - dl;
-        if (s > s1) { hi2 = fmaxf(hi2, s1 + (s1 - lo1)); s1 = s; lo1 = lo; p1 = p; }
-        else hi2 = fmaxf(hi2, hi);
+        for (int k = 0; k < HD; ++k) ymax = fmaxf(ymax, fmaxf(fabsf(yf[k].x), fabsf(yf[k].y)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < HD; ++k) yf[k] = make_float2(0.f, 0.f);
     }
-    if (lo1 > hi2) return gallagher_peak64<D>(gC, gRy, gw, p1, zs, zst, coef);
+    const float K1 = -coef32 * 2.f * 1.3e-7f * (ymax + 5.f * sqrtf((float)D) + 1.f) * sqrtf(31.7f * (float)D);
+    GalScan sc;
+    if (tile == nullptr) {
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < HD; ++k) {
+                const float4 c4 = __ldg(g32 + p * HD + k);
+                const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
+                acc2 = __ffma2_rn(__fmul2_rn(make_float2(c4.x, c4.y), z), z, acc2);
+            }
+            sc.visit(acc2.x + acc2.y, __ldg(lnw + p), coef32, K1, p);
+        }
+    } else {
+        const int tid = threadIdx.x, NT = blockDim.x;
+        int TP = tile_bytes / (16 * HD + 4);
+        if (TP * HD > 2 * NT) TP = 2 * NT / HD;                  // two prefetch registers per thread
+        float* tl = reinterpret_cast<float*>(tile + TP * HD);
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        float rl = 0.f;
+        auto fetch = [&](const int p0) {
+            const int n = min(TP, P - p0);
+            if (tid < n * HD) r0 = __ldg(g32 + p0 * HD + tid);
+            if (tid + NT < n * HD) r1 = __ldg(g32 + p0 * HD + tid + NT);
+            if (tid < n) rl = __ldg(lnw + p0 + tid);
+        };
+        fetch(0);
+#pragma unroll 1
+        for (int p0 = 0; p0 < P; p0 += TP) {
+            const int n = min(TP, P - p0);
+            __syncthreads();                                     // previous tile fully consumed
+            if (tid < n * HD) tile[tid] = r0;
+            if (tid + NT < n * HD) tile[tid + NT] = r1;
+            if (tid < n) tl[tid] = rl;
+            __syncthreads();
+            if (p0 + TP < P) fetch(p0 + TP);                     // in flight while this tile is consumed
+            if (act) {
+#pragma unroll 1
+                for (int p = 0; p < n; ++p) {
+                    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < HD; ++k) {
+                        const float4 c4 = tile[p * HD + k];
+                        const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
+                        acc2 = __ffma2_rn(__fmul2_rn(make_float2(c4.x, c4.y), z), z, acc2);
+                    }
+                    sc.visit(acc2.x + acc2.y, tl[p], coef32, K1, p0 + p);
+                }
+            }
+        }
+        __syncthreads();                                         // the tile may be reused by the caller
+    }
+    if (!act) return 0.;
+    if (sc.lo1 > sc.hi2) return gallagher_peak64<D>(gC, gRy, gw, sc.p1, zs, zst, coef);
     double g = -1e300;                                     // near-tie (or non-finite input): all peaks in float64
 #pragma unroll 1
     for (int p = 0; p < P; ++p) g = fmax(g, gallagher_peak64<D>(gC, gRy, gw, p, zs, zst, coef));
     return g;
+}
+// Gallagher f(x) with the staged peak table: every thread of the CTA calls (act = has a candidate).
+template <int D, class XA>
+__device__ __forceinline__ double bbob_gallagher_cta(const MbxInstance& h, const double* __restrict__ C, const double* __restrict__ G,
+                                                     const XA& X, double* zs, const int zst, const bool act, float4* tile, const int tile_bytes) {
+    ConstView<D> c(C);
+    double bh = 0.;
+    if (act) {
+        if (h.bh_coef != 0.) {
+            const double p = pen_x<D>(X, h.ub);
+            bh = (h.bh_coef == 1.) ? p : h.bh_coef * p;
+        }
+        double y[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = X(d);
+        matvec<D>(c.R, y, zs, zst);
+    }
+    const double g = gallagher_max<D>(G, h.n_peaks, zs, zst, act, tile, tile_bytes);
+    if (!act) return 0.;
+    const double t = t_osz(10. - g);
+    return t * t + h.bias + bh;
 }
 
 // Noise-free f(x) incl. bias and boundary handling  (== BBOB_Basic_Problem.func)

@@ -32,7 +32,8 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
                                               const TX* tile, int n, int row0, double* scratch, TO* out,
                                               bool subtract_opt, const Philox& ph, uint32_t gen, uint32_t lane,
                                               uint32_t tag, const double* noise_tape, int tape_stride,
-                                              const unsigned char* only_mask = nullptr, const int zst = MBX_NT) {
+                                              const unsigned char* only_mask = nullptr, const int zst = MBX_NT,
+                                              void* gtile = nullptr, const int gtile_bytes = 0) {
     if (KIND == MBX_KIND_PROTEIN) {
         const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
         double* ws = scratch + w * MBX_PROT_WARP_SCRATCH;
@@ -45,21 +46,34 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
         }
     } else {
         const int i = threadIdx.x;
-        if (i < n && !(only_mask && !only_mask[i])) {
+        const bool act = i < n && !(only_mask && !only_mask[i]);
+        // Gallagher with a staging tile is CTA-cooperative (barriers inside): every thread takes the branch (h is CTA-uniform)
+        const bool gal_cta = gtile != nullptr && (h.base == 21 || h.base == 22);
+        if (act || gal_cta) {
+            const int ii = act ? i : 0;
             double f;
-            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; f = bbob_true<D>(h, sC, gC, X, scratch + i, zst); }
-            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; f = bbob_true<D>(h, sC, gC, X, scratch + i, zst); }
-            if (h.noise != MBX_NOISE_NONE) {
-                double d0, d1, d2;
-                if (noise_tape) {
-                    d0 = noise_tape[row0 + i]; d1 = noise_tape[tape_stride + row0 + i]; d2 = noise_tape[2 * tape_stride + row0 + i];
-                } else {
-                    noise_draws(ph, h.noise, (uint32_t)(row0 + i), gen, lane, tag, d0, d1, d2);
-                }
-                f = bbob_noise(h, f, d0, d1, d2);
+            if (sizeof(TX) == 4) {
+                XF32 X{reinterpret_cast<const float*>(tile) + ii * D};
+                f = gal_cta ? bbob_gallagher_cta<D>(h, sC, gC, X, scratch + ii, zst, act, reinterpret_cast<float4*>(gtile), gtile_bytes)
+                            : bbob_true<D>(h, sC, gC, X, scratch + ii, zst);
+            } else {
+                XF64 X{reinterpret_cast<const double*>(tile) + ii * D};
+                f = gal_cta ? bbob_gallagher_cta<D>(h, sC, gC, X, scratch + ii, zst, act, reinterpret_cast<float4*>(gtile), gtile_bytes)
+                            : bbob_true<D>(h, sC, gC, X, scratch + ii, zst);
             }
-            if (subtract_opt && h.has_optimum) f = f - h.optimum;
-            out[i] = (TO)f;
+            if (act) {
+                if (h.noise != MBX_NOISE_NONE) {
+                    double d0, d1, d2;
+                    if (noise_tape) {
+                        d0 = noise_tape[row0 + i]; d1 = noise_tape[tape_stride + row0 + i]; d2 = noise_tape[2 * tape_stride + row0 + i];
+                    } else {
+                        noise_draws(ph, h.noise, (uint32_t)(row0 + i), gen, lane, tag, d0, d1, d2);
+                    }
+                    f = bbob_noise(h, f, d0, d1, d2);
+                }
+                if (subtract_opt && h.has_optimum) f = f - h.optimum;
+                out[i] = (TO)f;
+            }
         }
     }
 }
