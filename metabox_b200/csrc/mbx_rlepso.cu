@@ -35,35 +35,47 @@ extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
 #define PROF_ADD(k, v)
 #endif
 
-// Shared-memory plan, sized by the run-time population size (NP = 100 -> 62 KB at D = 30: 3 CTAs per SM).
+// Shared-memory plan, sized by the run-time population size (NP = 100, D = 30 -> 55.2 KB: 4 CTAs per SM).
+// Lifetimes: region A holds the sorted pbest_x (f32) and the FDR targets during P0-P2 and the evaluation scratch in P3;
+// the block [spf2 .. order] is dead during P3 and doubles as the Gallagher peak-table staging tile.
 struct RlLayout {
     int NP, NPp;
-    size_t oConst, oA, oPer, oGco, oGx, oXs, oF, oI, oTgt, oRed, bytes;
+    size_t oConst, oA, oSpf, oR1, oR2, oGco, oRank, oOrder, oTileEnd, oGx, oTmpf, oUr, oXs, oF, oPni, oMask, oRed, bytes;
     __host__ __device__ RlLayout(int np, int D, int kConst, bool protein) {
         NP = np; NPp = (np + 3) & ~3;
         const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)D * NPp;
         const size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
-        oA = oConst + sizeof(double) * kConst;               // sorted pbest_x as f64 [NP*D]  /  eval scratch
-        oPer = oA + sizeof(double) * regionA;                // 5 per-particle double arrays
-        oGco = oPer + sizeof(double) * 5 * NPp;              // 5 groups x (w, c1..c4)
-        oGx = oGco + sizeof(double) * 32;                    // gbest_x as double [D]
-        oXs = oGx + sizeof(double) * MBX_MAX_DIM;            // new positions f32 [NP*D]
-        oF = oXs + sizeof(float) * NPp * D;                  // 4 per-particle float arrays
-        oI = oF + sizeof(float) * 4 * NPp;                   // 3 per-particle int arrays
-        oTgt = oI + sizeof(int) * 3 * NPp;                   // FDR targets u8 [NP*D] + 2 masks u8 [NP]
-        oRed = (oTgt + (size_t)NPp * D + 2 * NPp + 15) & ~(size_t)15;
-        bytes = oRed + 64;
+        oA = oConst + sizeof(double) * kConst;               // spx f32 [NP*D] | tgt u8 [NP*D]   /   eval scratch f64
+        oSpf = oA + sizeof(double) * regionA;                // sorted pbest duplicated (f, f) float2 [NP]
+        oR1 = oSpf + sizeof(float2) * NPp;                   // rand1 as Philox word u32 [NP]
+        oR2 = oR1 + 4 * NPp;                                 // rand2
+        oGco = oR2 + 4 * NPp;                                // 5 groups x (w, c1..c4) f64
+        oRank = oGco + sizeof(double) * 26;                  // rank / order u8 [NP]
+        oOrder = oRank + NPp;
+        oTileEnd = oOrder + NPp;                             // --- end of the block that is dead during P3 ---
+        oGx = (oTileEnd + 7) & ~(size_t)7;                   // gbest_x as double [D]
+        oTmpf = oGx + sizeof(double) * D;                    // re-initialisation costs f32 [NP]
+        oUr = oTmpf + 4 * NPp;                               // re-init uniform as Philox word u32 [NP]
+        oXs = (oUr + 4 * NPp + 15) & ~(size_t)15;            // new positions f32 [NP*D]  (P1: list of ambiguous FDR items)
+        oF = oXs + sizeof(float) * NPp * D;                  // pf32, nc, cc f32 [NP]
+        oPni = oF + sizeof(float) * 3 * NPp;                 // per_no_improve i32 [NP]
+        oMask = oPni + 4 * NPp;                              // re-init mask, better flags u8 [NP]
+        oRed = (oMask + 2 * NPp + 15) & ~(size_t)15;         // reduction scratch + a0 coefficients + list counter
+        bytes = oRed + 96;
     }
 };
 
 template <int D, int KIND>
 struct RlepsoViews {
     MbxInstance* h;
-    double *sC, *A, *spf, *cm, *r1, *r2, *ur, *gco, *gx;
-    float *xs, *pf32, *nc, *cc, *tmpf;
-    int *pni, *rank, *order;
-    unsigned char *tgt, *mask, *better;
+    double *sC, *A, *gco, *gx;
+    float2* spf2;
+    uint32_t *r1u, *r2u, *uru;
+    float *spx, *xs, *pf32, *nc, *cc, *tmpf, *a0c;
+    int* pni;
+    unsigned char *rank, *order, *tgt, *mask, *better, *tile;
+    int tile_bytes;
     unsigned short* fbl;        // FDR items that need the exact float64 pass (aliases xs: written before P2 fills xs)
     int* nfb;
     float* redv;
@@ -73,19 +85,26 @@ struct RlepsoViews {
         h = reinterpret_cast<MbxInstance*>(s);
         sC = reinterpret_cast<double*>(s + L.oConst);
         A = reinterpret_cast<double*>(s + L.oA);
-        double* per = reinterpret_cast<double*>(s + L.oPer);
-        spf = per; cm = per + N; r1 = per + 2 * N; r2 = per + 3 * N; ur = per + 4 * N;
+        spx = reinterpret_cast<float*>(s + L.oA);
+        tgt = s + L.oA + sizeof(float) * N * D;
+        spf2 = reinterpret_cast<float2*>(s + L.oSpf);
+        r1u = reinterpret_cast<uint32_t*>(s + L.oR1);
+        r2u = reinterpret_cast<uint32_t*>(s + L.oR2);
+        uru = reinterpret_cast<uint32_t*>(s + L.oUr);
         gco = reinterpret_cast<double*>(s + L.oGco);
         gx = reinterpret_cast<double*>(s + L.oGx);
+        rank = s + L.oRank; order = s + L.oOrder;
+        tmpf = reinterpret_cast<float*>(s + L.oTmpf);
+        tile = s + L.oSpf; tile_bytes = (int)(L.oTileEnd - L.oSpf);
         xs = reinterpret_cast<float*>(s + L.oXs);
         float* f = reinterpret_cast<float*>(s + L.oF);
-        pf32 = f; nc = f + N; cc = f + 2 * N; tmpf = f + 3 * N;
-        int* ii = reinterpret_cast<int*>(s + L.oI);
-        pni = ii; rank = ii + N; order = ii + 2 * N;
-        tgt = s + L.oTgt; mask = tgt + N * D; better = mask + N;
+        pf32 = f; nc = f + N; cc = f + 2 * N;
+        pni = reinterpret_cast<int*>(s + L.oPni);
+        mask = s + L.oMask; better = mask + N;
         redv = reinterpret_cast<float*>(s + L.oRed);
         redi = reinterpret_cast<int*>(s + L.oRed + 32);
         nfb = reinterpret_cast<int*>(s + L.oRed + 56);
+        a0c = reinterpret_cast<float*>(s + L.oRed + 64);
         fbl = reinterpret_cast<unsigned short*>(xs);
     }
 };
@@ -130,7 +149,7 @@ __device__ __forceinline__ void fdr_visit(FdrChain& c, const float2 s2, const fl
 }
 template <int D>
 __device__ __forceinline__ void fdr_screen(const int NP, const int tid, const float* __restrict__ spx, const float2* __restrict__ spf2,
-                                           const int* __restrict__ order, unsigned char* tgt, unsigned short* fbl, int* nfb) {
+                                           const unsigned char* __restrict__ order, unsigned char* tgt, unsigned short* fbl, int* nfb) {
     static_assert(D % 2 == 0, "the packed FDR scan pairs adjacent dimensions");
     constexpr int DP = D / 2;
     const int nb = (NP + 1) / 2, npair = (nb + 1) / 2;
@@ -200,7 +219,7 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     __syncthreads();
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, MBX_GEN_INIT, (uint32_t)(cfg.lane_base + b),
                                          MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP, nullptr, L.NPp,
-                                         V.tgt, L.NPp * D);       // FDR targets are dead here: Gallagher peak-table staging tile
+                                         V.tile, V.tile_bytes);   // P0-P2 per-particle scratch is dead here: Gallagher peak-table staging tile
     __syncthreads();
     float v = INFINITY; int ix = tid;
     if (tid < NP) {
@@ -218,7 +237,7 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, 3)
+__global__ void __launch_bounds__(MBX_NT, 4)
 rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                    MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, const double* __restrict__ pci,
                    const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
@@ -242,12 +261,10 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         V.pf32[i] = S.pbest[pb + i]; V.cc[i] = S.c_cost[pb + i];
         const int pni = S.pni[pb + i];
         V.pni[i] = pni;
-        const int per = NP / 5;
-        int g = i / per; if (g > 4) g = 4;
-        const float a0 = action[(size_t)b * 35 + g * 5];             // stride 5, width 7 (overlapping windows)
-        V.cm[i] = (double)(a0 * 0.01f) * (double)pni;
-        if (cfg.use_tape) { V.r1[i] = T.rand1[pb + i]; V.r2[i] = T.rand2[pb + i]; V.ur[i] = T.reinit_u[pb + i]; }
-        else { uint4 w4 = ph((uint32_t)i, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_P); V.r1[i] = u01(w4.x); V.r2[i] = u01(w4.y); V.ur[i] = u01(w4.z); }
+        if (!cfg.use_tape) {                                          // tape mode reads its float64 draws from the tape directly
+            uint4 w4 = ph((uint32_t)i, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_P);
+            V.r1u[i] = w4.x; V.r2u[i] = w4.y; V.uru[i] = w4.z;
+        }
     }
     if (tid < 5) {                                                   // float32 coefficient math (numpy-2 promotion)
         const float* a = action + (size_t)b * 35 + tid * 5;
@@ -256,19 +273,20 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         float ssum = a3 + a4; ssum = ssum + a5; ssum = ssum + a6; ssum = ssum + 1e-5f;
         float scale = 1.f / ssum; scale = scale * a2; scale = scale * 8.f;
         double* gc = V.gco + tid * 5;
+        V.a0c[tid] = a[0] * 0.01f;                                   // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
         gc[0] = (double)w; gc[1] = (double)(scale * a3); gc[2] = (double)(scale * a4);
         gc[3] = (double)(scale * a5); gc[4] = (double)(scale * a6);
     }
     __syncthreads();
     PROF_MARK(0);
     // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
-    float* spx = reinterpret_cast<float*>(V.A);          // pbest_x rows in ascending-pbest order [NP*D]
-    float2* spf2 = reinterpret_cast<float2*>(V.spf);     // sorted pbest, duplicated (f, f) for the packed FDR scan
+    float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
+    float2* spf2 = V.spf2;                               // sorted pbest, duplicated (f, f) for the packed FDR scan
     if (tid < NP) {
         const float fi = V.pf32[tid];
         int r = 0;
         for (int j = 0; j < NP; ++j) { const float fj = V.pf32[j]; r += (fj < fi || (fj == fi && j < tid)) ? 1 : 0; }
-        V.rank[tid] = r; V.order[r] = tid; spf2[r] = make_float2(fi, fi);
+        V.rank[tid] = (unsigned char)r; V.order[r] = (unsigned char)tid; spf2[r] = make_float2(fi, fi);
     }
     if (tid == 0) *V.nfb = 0;
     __syncthreads();
@@ -357,8 +375,9 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         const int tg = V.tgt[e];                                       // sorted position of the FDR target
         if (dbg) dbg[base + e] = V.order[tg];
         const double v_fdr = fu * ((double)spx[tg * D + d] - pxi);
-        const double v_pbest = V.r1[i] * (pxi - x);
-        const double v_gbest = V.r2[i] * (V.gx[d] - x);
+        const double r1 = cfg.use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = cfg.use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
+        const double v_pbest = r1 * (pxi - x);
+        const double v_gbest = r2 * (V.gx[d] - x);
         const int per = NP / 5;
         int g = i / per; if (g > 4) g = 4;
         const double* gc = V.gco + g * 5;
@@ -375,7 +394,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                          MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP, nullptr, L.NPp,
-                                         V.tgt, L.NPp * D);       // FDR targets are dead here: Gallagher peak-table staging tile
+                                         V.tile, V.tile_bytes);   // P0-P2 per-particle scratch is dead here: Gallagher peak-table staging tile
     __syncthreads();
     PROF_MARK(4);
     // ---- P4: pbest / gbest / patience / re-init mask (:200-238) ------------------------------------------
@@ -392,10 +411,15 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         V.better[i] = bt;
         if (bt) { V.pf32[i] = ncv; S.pbest[pb + i] = ncv; }
         S.c_cost[pb + i] = ncv;
-        int pni = (ncv < V.cc[i]) ? 0 : V.pni[i] + 1;
+        const int pni0 = V.pni[i];
+        int pni = (ncv < V.cc[i]) ? 0 : pni0 + 1;
         V.pni[i] = pni;
         V.cc[i] = ncv;
-        mymask = V.ur[i] < V.cm[i] * 0.01 * (double)pni;
+        const int per = NP / 5;
+        int g = i / per; if (g > 4) g = 4;
+        const double cm = (double)V.a0c[g] * (double)pni0;            // float32 coefficient x per_no_improve of the old state
+        const double ur = cfg.use_tape ? T.reinit_u[pb + i] : u01(V.uru[i]);
+        mymask = ur < cm * 0.01 * (double)pni;
         V.mask[i] = mymask;
     }
     const int any_mask = __syncthreads_or(mymask ? 1 : 0);
@@ -431,7 +455,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, c2, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                              MBX_TAG_NOISE2,
                                              cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP + 3 * NP : nullptr, NP,
-                                             noisy ? nullptr : V.mask, L.NPp, V.tgt, L.NPp * D);
+                                             noisy ? nullptr : V.mask, L.NPp, V.tile, V.tile_bytes);
         __syncthreads();
         int nmask = 0;
         float v2 = INFINITY; int ix2 = tid;
@@ -495,6 +519,7 @@ static int launch_step_t(const MbxInstance* inst, const double* consts, const in
     static bool attr_done = false;
     if (!attr_done) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     MbxRlepsoTape t{};
