@@ -22,6 +22,29 @@
 #define MBX_TAG_DDQN_D 11u
 #define MBX_GEN_INIT 0xFFFFFFFFu
 
+// Phase profiling build (python -m metabox_b200.build --profile -> libmbx_prof.so, never the product library): thread 0 of
+// every CTA accumulates clock64() deltas per phase into g_prof (one copy per translation unit; mbx_prof_read() in
+// mbx_rlepso.cu reads that unit's copy).
+#ifdef MBX_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_INIT long long tp_ = clock64();
+#define PROF_MARK(k)                                                                   \
+    do {                                                                               \
+        if (threadIdx.x == 0) {                                                        \
+            long long t_ = clock64();                                                  \
+            atomicAdd(&g_prof[k], (unsigned long long)(t_ - tp_));                     \
+            tp_ = t_;                                                                  \
+        }                                                                              \
+    } while (0)
+#define PROF_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)(v)); } while (0)
+#define PROF_ADD_ANY(k, v) atomicAdd(&g_prof[k], (unsigned long long)(v))
+#else
+#define PROF_INIT
+#define PROF_MARK(k)
+#define PROF_ADD(k, v)
+#define PROF_ADD_ANY(k, v)
+#endif
+
 struct Philox {
     uint32_t k0, k1;
     __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}

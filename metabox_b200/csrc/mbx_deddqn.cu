@@ -2,8 +2,8 @@
 // mutation by the chosen operator (rand/1, rand/2, rand-to-best/2, cur-to-rand/1; F = 0.5, Cr = 1) ->
 // clip -> fitness of the single trial -> reward -> operator-credit history (N_tot / N_succ / OM per
 // generation slot, window OM_W) -> greedy `<=` replacement, gbest / gworst / stagnation -> cost-curve
-// log -> the 99 state features of the next individual.  One CTA per lane; warp 0 evaluates the trial
-// while warps 1-3 rank the population costs for the median.
+// log -> the 99 state features of the next individual.  One CTA per lane; the single trial is evaluated by the
+// whole CTA (one dimension per thread, mbx_bbob_cta.cuh).
 // Reference: optimizer/de_ddqn_optimizer.py:46-74 (init_population), :76-129 (__get_state), :131-220
 // (update); operators/mutate.py:36-39,53-56,124-127,178-181; crossover.py:6-18; boundary_control.py:5-9.
 // numpy twin: oracle/deddqn.py (documents the reference quirks that are reproduced here).
@@ -28,7 +28,7 @@ template <int D, int KIND>
 struct DdqnSmem {
     static constexpr int N = MBX_MAX_NP;
     static constexpr int kConst = EvalTraits<D, KIND>::kConstDoubles;
-    static constexpr int kScratch = (KIND == MBX_KIND_PROTEIN) ? MBX_PROT_WARP_SCRATCH : D;      // one candidate
+    static constexpr int kScratch = (KIND == MBX_KIND_PROTEIN) ? MBX_PROT_WARP_SCRATCH : D + 1;  // one candidate
     static constexpr size_t oHdr = 0;
     static constexpr size_t oConst = sizeof(MbxInstance);
     static constexpr size_t oScr = oConst + sizeof(double) * kConst;
@@ -64,25 +64,30 @@ __device__ __forceinline__ int dd_rank(const float* c, int i, int NP) {
     return r;
 }
 
-// fitness of ONE candidate (float32 tile `x`), noise applied; warp 0 only.  Returns in lane 0.
+// fitness of ONE candidate (float32 tile `x`), noise applied.  ALL threads of the CTA call: the BBOB path is the
+// CTA-cooperative evaluator (the D dimensions of the single trial are spread over D threads, mbx_bbob_cta.cuh), the
+// protein path uses warp 0.  The result is valid in thread 0.
 template <int D, int KIND>
 __device__ __forceinline__ double dd_eval_one(const MbxInstance& h, const double* sC, const double* gC, const float* x,
                                               double* scratch, const Philox& ph, uint32_t idx, uint32_t gen, uint32_t lane,
                                               const double* noise_tape, int tape_stride) {
     double f = 0.;
     if (KIND == MBX_KIND_PROTEIN) {
-        XF32 X{x};
-        f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31);
-    } else if ((threadIdx.x & 31) == 0) {
-        XF32 X{x};
-        f = bbob_true<D>(h, sC, gC, X, scratch, 1);
-        if (h.noise != MBX_NOISE_NONE) {
-            double d0, d1, d2;
-            if (noise_tape) { d0 = noise_tape[0]; d1 = noise_tape[tape_stride]; d2 = noise_tape[2 * tape_stride]; }
-            else noise_draws(ph, h.noise, idx, gen, lane, MBX_TAG_NOISE, d0, d1, d2);
-            f = bbob_noise(h, f, d0, d1, d2);
+        if (threadIdx.x < 32) {
+            XF32 X{x};
+            f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31);
         }
-        if (h.has_optimum) f = f - h.optimum;
+    } else {
+        f = bbob_eval_cta<D, float>(h, sC, gC, x, 1, scratch, nullptr, nullptr, 0);
+        if (threadIdx.x == 0) {
+            if (h.noise != MBX_NOISE_NONE) {
+                double d0, d1, d2;
+                if (noise_tape) { d0 = noise_tape[0]; d1 = noise_tape[tape_stride]; d2 = noise_tape[2 * tape_stride]; }
+                else noise_draws(ph, h.noise, idx, gen, lane, MBX_TAG_NOISE, d0, d1, d2);
+                f = bbob_noise(h, f, d0, d1, d2);
+            }
+            if (h.has_optimum) f = f - h.optimum;
+        }
     }
     return f;
 }
@@ -310,17 +315,16 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         if (dbg) dbg[(size_t)b * (D + 1) + d] = t32;
     }
     __syncthreads();
-    // ---- warp 0: fitness of the trial (:159-163); warps 1..3: median of the (pre-selection) costs (:172) ---------------
-    if (tid < 32) {
+    // ---- median of the (pre-selection) costs (:172), then the fitness of the trial with the whole CTA (:159-163) ----------
+    for (int i = tid; i < NP; i += MBX_NT) {
+        const int rk = dd_rank(sc, i, NP);
+        if (rk == (NP - 1) / 2) mf[1] = sc[i];
+        if (rk == NP / 2) mf[2] = sc[i];
+    }
+    {
         const double f = dd_eval_one<D, KIND>(h, sC, consts + gi->off, trial, scratch, ph, 0u, (uint32_t)fes0, lane,
                                               cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 : nullptr, 1);
         if (tid == 0) mf[0] = (float)f;
-    } else {
-        for (int i = tid - 32; i < NP; i += MBX_NT - 32) {
-            const int rk = dd_rank(sc, i, NP);
-            if (rk == (NP - 1) / 2) mf[1] = sc[i];
-            if (rk == NP / 2) mf[2] = sc[i];
-        }
     }
     __syncthreads();
     const float tc = mf[0];

@@ -1,14 +1,18 @@
 // mbx_eval.cuh -- CTA-cooperative evaluation of a tile of candidates + constant staging.
 // Shared by the stand-alone eval kernel and the fused optimizer kernels.
 #pragma once
-#include "mbx_bbob.cuh"
+#include "mbx_bbob_cta.cuh"
 
 template <int D, int KIND>
 struct EvalTraits {
     static constexpr int kConstDoubles = (KIND == MBX_KIND_PROTEIN) ? MBX_PROT_DOUBLES : ConstView<D>::kDoubles;
     // scratch doubles a CTA of MBX_NT threads needs while evaluating
     static constexpr int kScratchDoubles =
-        (KIND == MBX_KIND_PROTEIN) ? (MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : D * MBX_NT;
+        (KIND == MBX_KIND_PROTEIN) ? (MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (D + 1) * MBX_NT;
+    // scratch doubles needed to evaluate n candidates (BBOB: the [n][D+1] tile of bbob_eval_cta)
+    static __host__ __device__ constexpr int scratch_for(int n) {
+        return (KIND == MBX_KIND_PROTEIN) ? (MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (D + 1) * n;
+    }
 };
 
 // cooperative copy of the instance header + constants into shared memory
@@ -25,7 +29,8 @@ __device__ __forceinline__ void stage_instance(const MbxInstance* __restrict__ i
 
 // Evaluate candidates [0,n) of a shared-memory tile (row-major [n][D], element type TX) and write
 // cost = f(x) (- optimum) with noise into out (float32 if OUT32 else float64).  All threads of the
-// CTA must call this (it contains barriers for the protein path only through __syncwarp).
+// CTA must call this (the BBOB path is CTA-cooperative and contains barriers; `scratch` needs
+// EvalTraits::scratch_for(n) doubles; `zst` is unused).
 //   noise_tape : per-candidate draws [3][stride] (d0,d1,d2) or nullptr -> Philox(seed, lane, gen, tag)
 template <int D, int KIND, class TX, class TO>
 __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double* sC, const double* gC,
@@ -45,35 +50,22 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
             if (l == 0) out[i] = (TO)e;
         }
     } else {
+        // CTA-cooperative BBOB evaluation (mbx_bbob_cta.cuh): every thread participates, thread i receives f(x_i)
         const int i = threadIdx.x;
         const bool act = i < n && !(only_mask && !only_mask[i]);
-        // Gallagher with a staging tile is CTA-cooperative (barriers inside): every thread takes the branch (h is CTA-uniform)
-        const bool gal_cta = gtile != nullptr && (h.base == 21 || h.base == 22);
-        if (act || gal_cta) {
-            const int ii = act ? i : 0;
-            double f;
-            if (sizeof(TX) == 4) {
-                XF32 X{reinterpret_cast<const float*>(tile) + ii * D};
-                f = gal_cta ? bbob_gallagher_cta<D>(h, sC, gC, X, scratch + ii, zst, act, reinterpret_cast<float4*>(gtile), gtile_bytes)
-                            : bbob_true<D>(h, sC, gC, X, scratch + ii, zst);
-            } else {
-                XF64 X{reinterpret_cast<const double*>(tile) + ii * D};
-                f = gal_cta ? bbob_gallagher_cta<D>(h, sC, gC, X, scratch + ii, zst, act, reinterpret_cast<float4*>(gtile), gtile_bytes)
-                            : bbob_true<D>(h, sC, gC, X, scratch + ii, zst);
-            }
-            if (act) {
-                if (h.noise != MBX_NOISE_NONE) {
-                    double d0, d1, d2;
-                    if (noise_tape) {
-                        d0 = noise_tape[row0 + i]; d1 = noise_tape[tape_stride + row0 + i]; d2 = noise_tape[2 * tape_stride + row0 + i];
-                    } else {
-                        noise_draws(ph, h.noise, (uint32_t)(row0 + i), gen, lane, tag, d0, d1, d2);
-                    }
-                    f = bbob_noise(h, f, d0, d1, d2);
+        double f = bbob_eval_cta<D, TX>(h, sC, gC, tile, n, scratch, only_mask, reinterpret_cast<float4*>(gtile), gtile_bytes);
+        if (act) {
+            if (h.noise != MBX_NOISE_NONE) {
+                double d0, d1, d2;
+                if (noise_tape) {
+                    d0 = noise_tape[row0 + i]; d1 = noise_tape[tape_stride + row0 + i]; d2 = noise_tape[2 * tape_stride + row0 + i];
+                } else {
+                    noise_draws(ph, h.noise, (uint32_t)(row0 + i), gen, lane, tag, d0, d1, d2);
                 }
-                if (subtract_opt && h.has_optimum) f = f - h.optimum;
-                out[i] = (TO)f;
+                f = bbob_noise(h, f, d0, d1, d2);
             }
+            if (subtract_opt && h.has_optimum) f = f - h.optimum;
+            out[i] = (TO)f;
         }
     }
 }

@@ -7,19 +7,7 @@
 #include "mbx_launch.h"
 
 
-// Phase profiling build (python -m metabox_b200.build --profile -> libmbx_prof.so, never the product library): thread 0 of
-// every CTA accumulates clock64() deltas per phase into g_prof; read back with mbx_prof_read().
 #ifdef MBX_PROFILE
-__device__ unsigned long long g_prof[16];
-#define PROF_INIT long long tp_ = clock64();
-#define PROF_MARK(k)                                                                   \
-    do {                                                                               \
-        if (threadIdx.x == 0) {                                                        \
-            long long t_ = clock64();                                                  \
-            atomicAdd(&g_prof[k], (unsigned long long)(t_ - tp_));                     \
-            tp_ = t_;                                                                  \
-        }                                                                              \
-    } while (0)
 extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
     if (cudaMemcpyFromSymbol(h16, g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return MBX_ECUDA;
     if (reset) {
@@ -28,14 +16,9 @@ extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
     }
     return MBX_OK;
 }
-#define PROF_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)(v)); } while (0)
-#else
-#define PROF_INIT
-#define PROF_MARK(k)
-#define PROF_ADD(k, v)
 #endif
 
-// Shared-memory plan, sized by the run-time population size (NP = 100, D = 30 -> 55.2 KB: 4 CTAs per SM).
+// Shared-memory plan, sized by the run-time population size (NP = 100, D = 30 -> 56.0 KB: 4 CTAs per SM).
 // Lifetimes: region A holds the sorted pbest_x (f32) and the FDR targets during P0-P2 and the evaluation scratch in P3;
 // the block [spf2 .. order] is dead during P3 and doubles as the Gallagher peak-table staging tile.
 struct RlLayout {
@@ -43,7 +26,7 @@ struct RlLayout {
     size_t oConst, oA, oSpf, oR1, oR2, oGco, oRank, oOrder, oTileEnd, oGx, oTmpf, oUr, oXs, oF, oPni, oMask, oRed, bytes;
     __host__ __device__ RlLayout(int np, int D, int kConst, bool protein) {
         NP = np; NPp = (np + 3) & ~3;
-        const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)D * NPp;
+        const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)(D + 1) * NPp;   // bbob_eval_cta tile [NP][D+1]
         const size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
         oA = oConst + sizeof(double) * kConst;               // spx f32 [NP*D] | tgt u8 [NP*D]   /   eval scratch f64

@@ -50,4 +50,5 @@ for sel in a.fids.split(','):
     fb = buf[6] / max(1, buf[7])
     ms = e0.elapsed_time(e1) / a.steps
     print(f'fid={sel:>4} lanes={len(lanes):5d} {ms:8.4f} ms/launch  {len(lanes) * 100 / ms / 1e3:8.1f} Mev/s | ' +
-          ' | '.join(f'{n.split()[0]} {100 * x / v.sum():5.1f}%' for n, x in zip(names, v)) + f' | FDR exact-pass items {100 * fb:.3f}%')
+          ' | '.join(f'{n.split()[0]} {100 * x / v.sum():5.1f}%' for n, x in zip(names, v)) + f' | FDR exact-pass items {100 * fb:.3f}%' +
+          (f' | Gallagher scan {100 * buf[8] / v.sum():.1f}% exact {100 * buf[9] / v.sum():.1f}% f64-fallbacks/launch {buf[10] / a.steps:.1f}' if buf[8] else ''))
