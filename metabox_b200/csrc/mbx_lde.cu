@@ -10,48 +10,66 @@
 
 #define LDE_BINS 5
 
-template <int D, int KIND>
-struct LdeSmem {
-    static constexpr int N = MBX_MAX_NP;
-    static constexpr int kConst = EvalTraits<D, KIND>::kConstDoubles;
-    static constexpr int kScratch = EvalTraits<D, KIND>::kScratchDoubles;
-    static constexpr size_t oHdr = 0;
-    static constexpr size_t oConst = sizeof(MbxInstance);
-    static constexpr size_t oScr = oConst + sizeof(double) * kConst;
-    static constexpr size_t oPs = oScr + sizeof(double) * kScratch;          // parent population f32 [N*D] (sorted)
-    static constexpr size_t oTs = oPs + sizeof(float) * N * D;               // trial population  f32 [N*D]
-    static constexpr size_t oF = oTs + sizeof(float) * N * D;                // fit, tfit, nfit, sf, cr : 5 x f32 [N]
-    static constexpr size_t oI = oF + sizeof(float) * 5 * N;                 // pidx, r1, r2, jr, rank : 5 x i32 [N]
-    static constexpr size_t oH = oI + sizeof(int) * 5 * N;                   // 2 histograms (int[8] each)
-    static constexpr size_t oRed = oH + sizeof(int) * 16;
-    static constexpr size_t kBytes = ((oRed + 64 + 15) / 16) * 16;
+// Shared-memory plan, sized by the run-time population size (NP = 100, D = 30 -> 55.2 KB: 4 CTAs per SM).
+// Lifetimes: the sorted parents `ps` (f32) share the evaluation scratch (they are re-read from HBM/L2 in P5); the block
+// [sf .. jr] is dead during P3 and doubles as the Gallagher peak-table staging tile.
+struct LdeLayout {
+    int NP, NPp;
+    size_t oConst, oScr, oTs, oF, oTile, oTileEnd, oRank, oSrc, oH, oRed, bytes;
+    __host__ __device__ LdeLayout(int np, int D, int kConst, int scratchDoubles) {
+        NP = np; NPp = (np + 3) & ~3;
+        size_t scr = (size_t)scratchDoubles;
+        const size_t psd = ((size_t)NPp * D * sizeof(float) + 7) / 8;
+        if (psd > scr) scr = psd;
+        oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
+        oScr = oConst + sizeof(double) * kConst;             // P0-P2: parents f32 [NP*D] (sorted)  /  P3: eval scratch f64
+        oTs = oScr + sizeof(double) * scr;                   // trial population f32 [NP*D]
+        oF = oTs + sizeof(float) * NPp * D;                  // fit, tfit, nfit f32 [NP]
+        oTile = (oF + 12 * NPp + 15) & ~(size_t)15;          // sf, cr f32 [NP] | pidx, r1, r2, jr i32 [NP]   (dead in P3)
+        oTileEnd = oTile + 24 * NPp;
+        oRank = oTileEnd;                                    // rank i32 [NP]
+        oSrc = oRank + 4 * NPp;                              // stored row of sorted parent i, u8 [NP]
+        oH = (oSrc + NPp + 15) & ~(size_t)15;                // 2 histograms (int[8] each)
+        oRed = oH + 64;
+        bytes = oRed + 64;
+    }
 };
 
 template <int D, int KIND>
 struct LdeViews {
-    using L = LdeSmem<D, KIND>;
     MbxInstance* h;
     double *sC, *scr;
     float *ps, *ts, *fit, *tfit, *nfit, *sf, *cr;
     int *pidx, *r1, *r2, *jr, *rank, *hist0, *hist1;
+    unsigned char *src, *tile;
+    int tile_bytes;
     float* redv;
     int* redi;
-    __device__ __forceinline__ LdeViews(unsigned char* s) {
-        const int N = L::N;
-        h = reinterpret_cast<MbxInstance*>(s + L::oHdr);
-        sC = reinterpret_cast<double*>(s + L::oConst);
-        scr = reinterpret_cast<double*>(s + L::oScr);
-        ps = reinterpret_cast<float*>(s + L::oPs);
-        ts = reinterpret_cast<float*>(s + L::oTs);
-        float* f = reinterpret_cast<float*>(s + L::oF);
-        fit = f; tfit = f + N; nfit = f + 2 * N; sf = f + 3 * N; cr = f + 4 * N;
-        int* ii = reinterpret_cast<int*>(s + L::oI);
-        pidx = ii; r1 = ii + N; r2 = ii + 2 * N; jr = ii + 3 * N; rank = ii + 4 * N;
-        hist0 = reinterpret_cast<int*>(s + L::oH); hist1 = hist0 + 8;
-        redv = reinterpret_cast<float*>(s + L::oRed);
-        redi = reinterpret_cast<int*>(s + L::oRed + 32);
+    __device__ __forceinline__ LdeViews(unsigned char* s, const LdeLayout& L) {
+        const int N = L.NPp;
+        h = reinterpret_cast<MbxInstance*>(s);
+        sC = reinterpret_cast<double*>(s + L.oConst);
+        scr = reinterpret_cast<double*>(s + L.oScr);
+        ps = reinterpret_cast<float*>(s + L.oScr);
+        ts = reinterpret_cast<float*>(s + L.oTs);
+        float* f = reinterpret_cast<float*>(s + L.oF);
+        fit = f; tfit = f + N; nfit = f + 2 * N;
+        float* g = reinterpret_cast<float*>(s + L.oTile);
+        sf = g; cr = g + N;
+        int* ii = reinterpret_cast<int*>(s + L.oTile + 8 * N);
+        pidx = ii; r1 = ii + N; r2 = ii + 2 * N; jr = ii + 3 * N;
+        tile = s + L.oTile; tile_bytes = (int)(L.oTileEnd - L.oTile);
+        rank = reinterpret_cast<int*>(s + L.oRank);
+        src = s + L.oSrc;
+        hist0 = reinterpret_cast<int*>(s + L.oH); hist1 = hist0 + 8;
+        redv = reinterpret_cast<float*>(s + L.oRed);
+        redi = reinterpret_cast<int*>(s + L.oRed + 32);
     }
 };
+template <int D, int KIND>
+__host__ __device__ inline LdeLayout lde_layout(int NP) {
+    return LdeLayout(NP, D, EvalTraits<D, KIND>::kConstDoubles, EvalTraits<D, KIND>::scratch_for((NP + 3) & ~3));
+}
 
 // cost-curve protocol (lde_optimizer.py:190-197) -- same tail as every optimizer
 __device__ __forceinline__ bool lde_log_and_done(const MbxRunConfig& cfg, bool done, int fes, float gbest, int& log_index,
@@ -133,8 +151,9 @@ __global__ void __launch_bounds__(MBX_NT)
 lde_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                 MbxRunConfig cfg, MbxLdeState S, MbxLdeTape T, float* __restrict__ feature) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    LdeViews<D, KIND> V(smem_raw);
     const int b = blockIdx.x, NP = cfg.NP, tid = threadIdx.x;
+    const LdeLayout L = lde_layout<D, KIND>(NP);
+    LdeViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
     stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     __syncthreads();
@@ -149,7 +168,8 @@ lde_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     __syncthreads();
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.ts, NP, 0, V.scr, V.nfit, true, ph, MBX_GEN_INIT,
                                          (uint32_t)(cfg.lane_base + b), MBX_TAG_NOISE,
-                                         cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP);
+                                         cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP, nullptr, 0,
+                                         V.tile, V.tile_bytes);
     __syncthreads();
     float fmin, fmax;
     lde_minmax(V.nfit, NP, V.redv, fmin, fmax);
@@ -172,15 +192,16 @@ lde_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT)
+__global__ void __launch_bounds__(MBX_NT, 4)
 lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                 MbxRunConfig cfg, MbxLdeState S, MbxLdeTape T, const float* __restrict__ action, float* __restrict__ feature,
                 float* __restrict__ reward, float* __restrict__ dbg) {
     const int b = blockIdx.x;
     if (S.done[b]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    LdeViews<D, KIND> V(smem_raw);
     const int NP = cfg.NP, tid = threadIdx.x;
+    const LdeLayout L = lde_layout<D, KIND>(NP);
+    LdeViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
     stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
@@ -192,7 +213,7 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     __syncthreads();
     lde_rank(V.nfit, V.rank, NP);
     __syncthreads();
-    if (tid < NP) V.fit[V.rank[tid]] = V.nfit[tid];
+    if (tid < NP) { V.fit[V.rank[tid]] = V.nfit[tid]; V.src[V.rank[tid]] = (unsigned char)tid; }
     for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; V.ps[V.rank[i] * D + (e - i * D)] = S.pop[base + e]; }
     // ---- P1: per-individual parameters and draws (:164-167, :88-123) ---------------------------------------------
     if (tid < NP) {
@@ -242,8 +263,10 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     }
     __syncthreads();
     // ---- P3: fitness of the trials (:54) -------------------------------------------------------------------------------
+    // (the evaluation scratch overwrites the parents' shared-memory copy; P5 re-reads the surviving parents from HBM/L2)
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.ts, NP, 0, V.scr, V.tfit, true, ph, gen, lane,
-                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP);
+                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP,
+                                         nullptr, 0, V.tile, V.tile_bytes);
     __syncthreads();
     // ---- P4: selection `<=` (:59-61), reward (:170-173) ------------------------------------------------------------------
     if (tid < NP) {
@@ -259,10 +282,26 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     // ---- P5: re-sort the survivors (__get_feature :146) and write the state back --------------------------------------------
     lde_rank(V.nfit, V.rank, NP);
     __syncthreads();
-    for (int e = tid; e < NP * D; e += MBX_NT) {
-        const int i = e / D;
-        const float xv = (V.tfit[i] <= V.fit[i]) ? V.ts[e] : V.ps[e];
-        S.pop[base + (size_t)V.rank[i] * D + (e - i * D)] = xv;
+    {
+        // survivors: trial if tfit <= fit else the parent, whose row is re-read from the stored (old) population; every
+        // read of the old population happens before the first write of the new one
+        constexpr int EPT = (MBX_MAX_NP * D + MBX_NT - 1) / MBX_NT;
+        float keep[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int e = tid + k * MBX_NT;
+            keep[k] = 0.f;
+            if (e < NP * D) {
+                const int i = e / D;
+                keep[k] = (V.tfit[i] <= V.fit[i]) ? V.ts[e] : S.pop[base + (size_t)V.src[i] * D + (e - i * D)];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int e = tid + k * MBX_NT;
+            if (e < NP * D) { const int i = e / D; S.pop[base + (size_t)V.rank[i] * D + (e - i * D)] = keep[k]; }
+        }
     }
     __syncthreads();
     if (tid < NP) V.tfit[V.rank[tid]] = V.nfit[tid];                       // tfit := survivors' costs, sorted
@@ -290,12 +329,12 @@ static int lde_launch_init_t(const MbxInstance* inst, const double* consts, cons
     auto kern = lde_init_kernel<D, KIND>;
     static bool attr_done = false;
     if (!attr_done) {
-        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LdeSmem<D, KIND>::kBytes));
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
     MbxLdeTape t{};
     if (tape) t = *tape;
-    kern<<<B, MBX_NT, LdeSmem<D, KIND>::kBytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, feature);
+    kern<<<B, MBX_NT, lde_layout<D, KIND>(cfg->NP).bytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, feature);
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
@@ -306,12 +345,13 @@ static int lde_launch_step_t(const MbxInstance* inst, const double* consts, cons
     auto kern = lde_step_kernel<D, KIND>;
     static bool attr_done = false;
     if (!attr_done) {
-        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LdeSmem<D, KIND>::kBytes));
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     MbxLdeTape t{};
     if (tape) t = *tape;
-    kern<<<B, MBX_NT, LdeSmem<D, KIND>::kBytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, action, feature, reward, dbg);
+    kern<<<B, MBX_NT, lde_layout<D, KIND>(cfg->NP).bytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, action, feature, reward, dbg);
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
