@@ -47,13 +47,14 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
                     help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3')
-    ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256; deddqn 64)')
+    ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stripes', type=int, default=3, help='independent lane stripes per GPU, each on its own CUDA stream + graph')
     ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
     if a.runs is None:
-        a.runs = 64 if a.workload == 'deddqn' else 256
+        a.runs = 256                                  # C3: 256 runs in lockstep
     if a.cpu_gens is None:
         a.cpu_gens = 1500 if a.workload == 'deddqn' else 40
     return a
@@ -176,13 +177,22 @@ def build_policy(workload, dev, NP):
     return net.to(dev).eval(), wsrc
 
 
-def make_sweep(workload, pack, lanes, net, seed, lane_base, NP, **kw):
+def make_sweep(workload, pack, lanes, net, seed, lane_base, NP, stripes=1, **kw):
     from metabox_b200 import sweep as msweep
+    if stripes > 1:
+        return msweep.StripedSweep(lambda ln, lb: make_sweep(workload, pack, ln, net, seed, lb, NP, **kw), lanes, lane_base, stripes)
     if workload == 'rlepso':
         return msweep.RLEPSO_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
     if workload == 'lde':
         return msweep.LDE_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, NP=NP, **kw)
     return msweep.DE_DDQN_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
+
+
+def sweep_engines(sw):
+    """(lo, hi, engine) of every stripe of a sweep."""
+    if hasattr(sw, 'children'):
+        return [(lo, hi, c.engine) for (lo, hi), c in zip(sw.bounds, sw.children)]
+    return [(0, sw.engine.B, sw.engine)]
 
 
 def main():
@@ -227,7 +237,7 @@ def main():
         return res, rows
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
-    sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, graph=not args.no_graph)
+    sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph)
     for _ in range(args.warmup):
         one_sweep(sw)
     clocks = ClockSampler(local_rank)
@@ -265,7 +275,8 @@ def main():
     def e2e_step():
         pack.headers.copy_(h_hdr, non_blocking=True)           # H2D of this step's inputs
         pack.consts.copy_(h_cst, non_blocking=True)
-        sw.engine.lane_inst.copy_(h_lane, non_blocking=True)
+        for lo, hi, eng in sweep_engines(sw):                   # lane table of every stripe
+            eng.lane_inst.copy_(h_lane[lo:hi], non_blocking=True)
         res = sw.run()
         rows = msweep.gather_results(res, world)
         h_rows.copy_(rows, non_blocking=True)                  # D2H of the step's result
@@ -310,7 +321,7 @@ def main():
             'config': {'workload': f'{W["desc"]} x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
                                    'one step = one complete sweep (init + all generations + all-gather)',
                        'lanes_per_gpu': n_local, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
-                       'launch': 'eager' if args.no_graph else 'policy forward + fused step replayed from one CUDA graph per step',
+                       'launch': 'eager' if args.no_graph else f'policy forward + fused step replayed from one CUDA graph per step; {args.stripes} lane stripe(s) on separate streams',
                        'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
                        'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

@@ -130,7 +130,7 @@ int mbx_rlepso_init(const MbxInstance* d_inst, const double* d_consts, const int
 
 /* d_action [B,35] f32 in [0,1] ; outputs d_feature [B,1] f32, d_reward [B] f32 (+1/-1), st->done.
  * d_pci [NP] f64 = the CLPSO learning-probability table (rlepso_optimizer.py:24-25).
- * Lanes whose done flag is already set are skipped (outputs untouched).
+ * Lanes whose done flag is already set are skipped: state and feature untouched, reward = 0.
  * d_dbg (optional, may be null): [B, NP, D] int32 FDR target indices for index-parity tests.       */
 int mbx_rlepso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
                     const MbxRunConfig* cfg, const MbxRlepsoState* st, const MbxRlepsoTape* tape,
@@ -170,7 +170,7 @@ int mbx_lde_init(const MbxInstance* d_inst, const double* d_consts, const int32_
                  void* stream);
 
 /* d_action [B, 2*NP] f32 (scale factors | crossover rates) ; outputs d_feature, d_reward [B] f32
- * ((bsf - bsf_next)/bsf), st->done.  Finished lanes are skipped.
+ * ((bsf - bsf_next)/bsf), st->done.  Finished lanes are skipped (reward = 0).
  * d_dbg (optional): [B, NP*(D+1)] f32 = trial vectors [NP,D] then trial costs [NP] (index-parity tests). */
 int mbx_lde_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
                  const MbxRunConfig* cfg, const MbxLdeState* st, const MbxLdeTape* tape, const float* d_action,

@@ -65,6 +65,7 @@ def load_reference_weights(module: nn.Module, weights: dict, prefix=''):
 class RLEPSO_Actor(nn.Module):
     """Two MLPs 1->64->32->35 (mu, sigma); action = clamp(Normal(mu, sigma).sample(), 0, 1)."""
     feature_dim, action_dim, max_sigma, min_sigma = 1, 35, 0.7, 0.01
+    takes_noise = True          # forward(x, noise=...) accepts externally drawn standard-normal noise
 
     def __init__(self):
         super().__init__()
@@ -131,6 +132,7 @@ class DE_DDQN_Net(MLP):
 # ------------------------------------------------------------------------------------------ LDE
 class LDE_PolicyNet(nn.Module):
     """LSTM(NP+10 -> 50) + Linear mu/sigma heads -> 2*NP (lde_agent.py:8-29)."""
+    takes_noise = True          # step(x, h, c, noise=...) accepts externally drawn standard-normal noise
 
     def __init__(self, NP=50, cell=50, bins=5):
         super().__init__()

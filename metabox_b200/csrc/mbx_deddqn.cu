@@ -235,7 +235,7 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
                    MbxRunConfig cfg, MbxDdqnState S, MbxDdqnTape T, const int32_t* __restrict__ action,
                    float* __restrict__ feature, float* __restrict__ reward, float* __restrict__ dbg) {
     const int b = blockIdx.x;
-    if (S.done[b]) return;
+    if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
     using L = DdqnSmem<D, KIND>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MbxInstance* sh = reinterpret_cast<MbxInstance*>(smem_raw + L::oHdr);

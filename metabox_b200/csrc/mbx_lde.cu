@@ -197,7 +197,7 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
                 MbxRunConfig cfg, MbxLdeState S, MbxLdeTape T, const float* __restrict__ action, float* __restrict__ feature,
                 float* __restrict__ reward, float* __restrict__ dbg) {
     const int b = blockIdx.x;
-    if (S.done[b]) return;
+    if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NP = cfg.NP, tid = threadIdx.x;
     const LdeLayout L = lde_layout<D, KIND>(NP);

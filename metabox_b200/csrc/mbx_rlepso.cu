@@ -226,7 +226,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
                    const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
                    int32_t* __restrict__ dbg) {
     const int b = blockIdx.x;
-    if (S.done[b]) return;
+    if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PROF_INIT
     const int NP = cfg.NP, tid = threadIdx.x;

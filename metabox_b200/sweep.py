@@ -48,8 +48,16 @@ class _Sweep:
         self.time_kernels = time_kernels
         self.kernel_events = []
         self.launches = 0
+        self.finite_reward = False          # RLEPSO: reward is +1 / -1, never NaN / inf
         self.ret = torch.zeros(engine.B, dtype=torch.float32, device=engine.device)
         self._graph = None
+        # own generator for the policy's action noise: sweeps replaying their graphs concurrently on different streams
+        # must not share the default generator's graph-side offset
+        self.gen = torch.Generator(device=engine.device)
+        self.gen.manual_seed((int(getattr(engine, 'seed', 0)) * 1000003 + int(getattr(engine, 'lane_base', 0))) & (2 ** 62 - 1))
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, generator=self.gen, device=self.engine.device, dtype=torch.float32)
 
     # -- to be provided -------------------------------------------------------------------------------------
     def _policy(self, feat):
@@ -61,7 +69,6 @@ class _Sweep:
     # -- one env step, all on the current stream, no sync -----------------------------------------------------
     def _step(self):
         eng = self.engine
-        alive = (eng.done == 0).to(torch.float32)
         action = self._policy(eng.feature)
         if self.time_kernels:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -71,7 +78,8 @@ class _Sweep:
             self.kernel_events.append((e0, e1))
         else:
             _, reward, _ = eng.update(action)
-        self.ret += torch.nan_to_num(reward, nan=0.0, posinf=0.0, neginf=0.0) * alive
+        # finished lanes report reward 0 (the step kernels write it), so no alive mask is needed
+        self.ret += reward if self.finite_reward else torch.nan_to_num(reward, nan=0.0, posinf=0.0, neginf=0.0)
 
     def _capture(self):
         # warm-up on a side stream (lazy cuBLAS / cudaFuncSetAttribute initialisation must not happen under capture)
@@ -82,10 +90,46 @@ class _Sweep:
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
         with torch.cuda.graph(g):
             for _ in range(self.steps_per_graph):
                 self._step()
         self._graph = g
+
+    # -- the sweep in three pieces (so that several sweeps can be interleaved on different streams) -----------------
+    def _begin(self):
+        """init_population (+ graph capture on first use); everything on the current stream."""
+        eng = self.engine
+        if self.use_graph and self._graph is None:
+            eng.init_population()
+            self._reset_policy()
+            self._capture()
+        self.kernel_events = []
+        eng.init_population()
+        self._reset_policy()
+        self.ret.zero_()
+        self.launches = 1
+        self.steps = 0
+
+    def _advance(self):
+        """up to `poll` more env steps on the current stream, no host sync."""
+        per = self.steps_per_graph if self.use_graph else 1
+        for _ in range(max(1, self.poll // per)):
+            if self.steps >= self.max_steps:
+                break
+            if self.use_graph:
+                self._graph.replay()
+            else:
+                self._step()
+            self.launches += per
+            self.steps += per
+
+    def _result(self):
+        eng = self.engine
+        idx = torch.arange(_lib.CURVE_LEN, device=eng.device)[None, :]
+        last = torch.gather(eng.curve, 1, (eng.curve_len.long() - 1).clamp(min=0)[:, None])
+        curve = torch.where(idx < eng.curve_len[:, None], eng.curve, last)
+        return dict(curve=curve, curve_len=eng.curve_len, fes=eng.fes, ret=self.ret, steps=self.steps)
 
     @torch.no_grad()
     def run(self):
@@ -95,33 +139,12 @@ class _Sweep:
             z = torch.zeros(0, device=eng.device)
             return dict(curve=torch.zeros(0, _lib.CURVE_LEN, device=eng.device), curve_len=z.int(), fes=z.int(), ret=z, steps=0)
         with torch.cuda.device(eng.device):
-            if self.use_graph and self._graph is None:
-                eng.init_population()
-                self._reset_policy()
-                self._capture()
-            self.kernel_events = []
-            eng.init_population()
-            self._reset_policy()
-            self.ret.zero_()
-            self.launches = 1
-            steps = 0
-            per = self.steps_per_graph if self.use_graph else 1
-            while steps < self.max_steps:
-                for _ in range(max(1, self.poll // per)):
-                    if self.use_graph:
-                        self._graph.replay()
-                    else:
-                        self._step()
-                    self.launches += per
-                    steps += per
-                    if steps >= self.max_steps:
-                        break
+            self._begin()
+            while self.steps < self.max_steps:
+                self._advance()
                 if bool(torch.all(eng.done != 0)):          # the only host sync inside the sweep
                     break
-        idx = torch.arange(_lib.CURVE_LEN, device=eng.device)[None, :]
-        last = torch.gather(eng.curve, 1, (eng.curve_len.long() - 1).clamp(min=0)[:, None])
-        curve = torch.where(idx < eng.curve_len[:, None], eng.curve, last)
-        return dict(curve=curve, curve_len=eng.curve_len, fes=eng.fes, ret=self.ret, steps=steps)
+            return self._result()
 
     def kernel_ms(self):
         """Sum / count of the step-kernel durations recorded by the last run (needs time_kernels=True)."""
@@ -140,8 +163,11 @@ class RLEPSO_Sweep(_Sweep):
         # every generation charges >= NP evaluations, so ceil(maxFEs/NP) generations always suffice
         super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
         self.actor = actor
+        self.finite_reward = True
 
     def _policy(self, feat):
+        if getattr(self.actor, 'takes_noise', False):
+            return self.actor(feat, noise=self._randn(feat.shape[0], self.actor.action_dim))
         return self.actor(feat)
 
 
@@ -160,7 +186,10 @@ class LDE_Sweep(_Sweep):
         self.h.zero_(); self.c.zero_()
 
     def _policy(self, feat):
-        action, h, c = self.net.step(feat, self.h, self.c)
+        if getattr(self.net, 'takes_noise', False):
+            action, h, c = self.net.step(feat, self.h, self.c, noise=self._randn(feat.shape[0], 2 * self.net.NP))
+        else:
+            action, h, c = self.net.step(feat, self.h, self.c)
         self.h.copy_(h); self.c.copy_(c)
         return action
 
@@ -177,6 +206,48 @@ class DE_DDQN_Sweep(_Sweep):
     def _policy(self, feat):
         q = self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0))
         return torch.argmax(q, dim=-1).to(torch.int32)
+
+
+class StripedSweep:
+    """`n_stripes` sweeps over contiguous slices of the lane table, each with its own engine, CUDA graph and CUDA stream,
+    advanced round-robin.  Lanes are independent, so the stripes never synchronise with each other: the tail wave of one
+    stripe's step kernel and its small policy kernels overlap with the other stripes' step kernels (the SMs stay full).
+    Philox streams are keyed by the global lane id, so the results are identical to the unstriped sweep.
+    `make(lane_inst_slice, lane_base) -> _Sweep`."""
+
+    def __init__(self, make, lane_inst, lane_base=0, n_stripes=2):
+        n = len(lane_inst)
+        k = max(1, min(int(n_stripes), n))
+        self.bounds = [shard_range(n, r, k) for r in range(k)]
+        self.children = [make(lane_inst[lo:hi], lane_base + lo) for lo, hi in self.bounds]
+        dev = self.children[0].engine.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.children]
+        self.engine = self.children[0].engine            # (bench.py e2e leg: lane table upload)
+        self.launches = 0
+
+    @torch.no_grad()
+    def run(self):
+        cur = torch.cuda.current_stream()
+        for c, st in zip(self.children, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                c._begin()
+        live = list(range(len(self.children)))
+        while live:
+            for j in live:
+                with torch.cuda.stream(self.streams[j]):
+                    self.children[j]._advance()
+            live = [j for j in live if self.children[j].steps < self.children[j].max_steps
+                    and not bool(torch.all(self.children[j].engine.done != 0))]
+        res = []
+        for c, st in zip(self.children, self.streams):
+            with torch.cuda.stream(st):
+                res.append(c._result())
+            cur.wait_stream(st)
+        self.launches = sum(c.launches for c in self.children)
+        out = {k: torch.cat([r[k] for r in res]) for k in ('curve', 'curve_len', 'fes', 'ret')}
+        out['steps'] = max(r['steps'] for r in res)
+        return out
 
 
 def gather_results(res, world):

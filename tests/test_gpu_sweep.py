@@ -66,6 +66,22 @@ def test_rlepso_sweep_graph_equals_eager():
     assert np.all(np.abs(ra[:, 52]) <= 31)             # return = sum of +-1 over <= 30 generations
 
 
+def test_striped_sweep_on_two_streams_equals_the_single_sweep():
+    """Lane stripes on separate CUDA streams / graphs: Philox streams are keyed by the global lane id, so the rows are
+    bit-identical to the unstriped sweep (deterministic policy)."""
+    from metabox_b200 import agent as ma, sweep
+    pack, probs = _pack()
+    actor = _MeanActor(ma.load_reference_weights(ma.RLEPSO_Actor(), _weights('rlepso')).cuda().eval())
+    inst, _ = sweep.lane_table(len(probs), 3)
+    one = sweep.RLEPSO_Sweep(pack, inst, actor, 3000, 50, seed=9, lane_base=7, graph=True, poll=8)
+    two = sweep.StripedSweep(lambda ln, lb: sweep.RLEPSO_Sweep(pack, ln, actor, 3000, 50, seed=9, lane_base=lb, graph=True, poll=8),
+                             inst, lane_base=7, n_stripes=3)
+    r1, r2, r2b = _rows(one), _rows(two), _rows(two)
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(r2, r2b)
+    assert two.launches >= 3 * 30
+
+
 class _MeanLDE:
     def __init__(self, net):
         self.net, self.NP, self.cell = net, net.NP, net.cell
