@@ -185,3 +185,18 @@ def test_gather_results_world2_gloo(n_lanes):
         d = sweep.results_to_reference_dict(got[0], ['A', 'B'], 5, 'RLEPSO_Agent')
         assert d['fes']['B']['RLEPSO_Agent'] == [1005, 1006, 1007, 1008, 1009]
         assert len(d['cost']['A']['RLEPSO_Agent']) == 5 and len(d['cost']['A']['RLEPSO_Agent'][0]) == 51
+
+
+def test_tester_rows_to_reference_dict_layout():
+    """Host-side assembly of test.pkl / rollout.pkl entries (tester.py:123-127, 282-300) from gathered result rows."""
+    from metabox_b200 import tester as mt
+    rows = np.zeros((6, 53))
+    rows[:, :51] = np.linspace(5, 1, 51)[None, :] + np.arange(6)[:, None]
+    rows[:, 51] = 2000 + np.arange(6)
+    rows[:, 52] = -3.0
+    out = mt.rows_to_results(rows, ['A', 'B'], 3, 'RLEPSO_Agent', {'cost': {}, 'fes': {}, 'return': {}})
+    assert list(out['cost']) == ['A', 'B'] and out['fes']['B']['RLEPSO_Agent'] == [2003, 2004, 2005]
+    assert len(out['cost']['A']['RLEPSO_Agent']) == 3 and len(out['cost']['A']['RLEPSO_Agent'][0]) == 51
+    assert out['return']['A']['RLEPSO_Agent'] == [-3.0] * 3 and isinstance(out['fes']['A']['RLEPSO_Agent'][0], int)
+    out2 = mt.rows_to_results(rows, ['A', 'B'], 3, 'X', {'cost': {}, 'fes': {}})
+    assert 'return' not in out2 and mt.cal_t0(4, 50) > 0
