@@ -244,3 +244,55 @@ def test_deddqn_steps_match_reference():
             n_total += 1; n_gen2 += int(S.gen >= 3); n_evict += int(S.win_len >= od.W_); n_done += int(done)
         np.testing.assert_allclose(np.array(S.curve, dtype=np.float64), G[f'{key}/curve'], rtol=1e-6, atol=1e-10)
     assert n_total >= 900 and n_gen2 >= 100 and n_evict >= 300 and n_done >= 1
+
+
+# ----------------------------------------------------------------------------------------- GLEET
+def _gleet_state_from(G, pre):
+    from oracle import gleet as og
+    return og.State(x=G[pre + 'x'], v=G[pre + 'v'], pbest_x=G[pre + 'pbest_x'], c_cost=G[pre + 'c_cost'], pbest=G[pre + 'pbest'],
+                    pni=G[pre + 'pni'].astype(np.int32), gbest_x=G[pre + 'gbest_x'], gbest_val=np.float32(G[pre + 'gbest_val']),
+                    gbest_idx=int(G[pre + 'gbest_idx']), no_improve=int(G[pre + 'no_improve']), w=float(G[pre + 'w']),
+                    max_cost=np.float32(G[pre + 'max_cost']), pbest_feature=G[pre + 'pbest_feature'],
+                    gbest_feature=G[pre + 'gbest_feature'], fes=int(G[pre + 'fes']), log_index=int(G[pre + 'log_index']),
+                    curve=[np.float32(c) for c in G[pre + 'curve']])
+
+
+def _gleet_cmp(S, state, G, pre, tag):
+    for k in ('x', 'v', 'pbest_x', 'gbest_x'):
+        np.testing.assert_array_equal(getattr(S, k), G[pre + k], err_msg=f'{tag} {k}')
+    for k in ('c_cost', 'pbest'):
+        np.testing.assert_allclose(getattr(S, k), G[pre + k], rtol=1e-6, atol=1e-10, err_msg=f'{tag} {k}')
+    np.testing.assert_array_equal(S.pni, G[pre + 'pni'], err_msg=f'{tag} pni')
+    assert S.gbest_idx == int(G[pre + 'gbest_idx']) and S.no_improve == int(G[pre + 'no_improve']), tag
+    assert S.fes == int(G[pre + 'fes']) and S.log_index == int(G[pre + 'log_index']), tag
+    assert S.w == float(G[pre + 'w']), tag                                   # the same float64 subtraction chain
+    # the reference computes its features from the float64 positions BEFORE they are rounded to the float32 store, the
+    # engine from the stored float32 values: cost / counter / distance features agree to float32 rounding, the cosine
+    # feature (col 8: a dot product with cancellation, range [-1, 1]) to 5e-6 absolute
+    atol = np.where(np.arange(27) % 9 == 8, 5e-6, 1e-9)
+    close = lambda a, b, at: np.all(np.abs(np.asarray(a, dtype=np.float64) - b) <= at + 2e-6 * np.abs(b))
+    assert close(S.pbest_feature, G[pre + 'pbest_feature'], atol[None, :9]), f'{tag} pbest_feature'
+    assert close(S.gbest_feature, G[pre + 'gbest_feature'], atol[:9]), f'{tag} gbest_feature'
+    assert np.all(np.abs(state - G[pre + 'state']) <= atol[None, :] + 2e-6 * np.abs(G[pre + 'state'])), f'{tag} state [NP,27]'
+    np.testing.assert_allclose(np.array(S.curve, dtype=np.float64), G[pre + 'curve'], rtol=1e-6, atol=1e-10)
+
+
+def test_gleet_steps_match_reference():
+    """The real GLEET_Optimizer (teacher-forced on float32-representable state, seeded np.random) vs the oracle replaying
+    the same draws: positions / velocities / pbest bit-exact, the 27 features per particle within float32 rounding."""
+    from oracle import gleet as og
+    G = load('gleet.npz')
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = og.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, state = og.init_population(cfg, ev, optimum, lb, ub, og.NumpyTape(cfg.NP, dim, nc))
+        _gleet_cmp(S, state, G, f'{key}/s0/', f'{key} init')
+        for t in range(1, int(G[f'{key}/n_steps']) + 1):
+            S = _gleet_state_from(G, f'{key}/s{t - 1}/')
+            np.random.seed(int(G[f'{key}/s{t}/seed']))
+            N, state, reward, done = og.update(cfg, S, G[f'{key}/s{t}/action'], ev, optimum, lb, ub, og.NumpyTape(cfg.NP, dim, nc))
+            _gleet_cmp(N, state, G, f'{key}/s{t}/', f'{key} step {t}')
+            np.testing.assert_allclose(reward, float(G[f'{key}/s{t}/reward']), rtol=1e-6, atol=1e-9)
+            assert done == bool(G[f'{key}/s{t}/done'])
