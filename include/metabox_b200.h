@@ -218,6 +218,43 @@ int mbx_deddqn_step(const MbxInstance* d_inst, const double* d_consts, const int
                     float* d_feature, float* d_reward, float* d_dbg, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * GLEET backbone (PSO family, whole swarm per step, per-particle action) -- replaces GLEET_Optimizer.init_population /
+ * update / observe (optimizer/gleet_optimizer.py:76-112, 193-314, 128-158) for B lanes at once; the reference's fixed
+ * configuration: ps = 100, c = 4.1, w = 0.9 decaying by 0.5 / (maxFEs / ps) per step, clipping border, 'direct' reward
+ * x 100 (:10-32).  State (all device, updated in place):
+ *   x, v, pbest_x [B,NP,D] f32 ; c_cost, pbest [B,NP] f32 ; pni [B,NP] i32 (per_no_improve) ; gbest_x [B,D] f32 ;
+ *   gbest_val [B] f32 ; gbest_idx, no_improve, fes, log_index, curve_len, gen [B] i32 ; w [B] f64 (inertia) ;
+ *   max_cost [B] f32 (= min of the initial costs, :49) ; pbest_feature [B,NP,9] f32 ; gbest_feature [B,9] f32 ;
+ *   curve [B, MBX_CURVE_LEN] f32 ; done [B] u8                                                                 */
+typedef struct MbxGleetState {
+    float *x, *v, *pbest_x, *c_cost, *pbest;
+    int32_t* pni;
+    float *gbest_x, *gbest_val;
+    int32_t *gbest_idx, *no_improve, *fes, *log_index, *curve_len, *gen;
+    double* w;
+    float *max_cost, *pbest_feature, *gbest_feature;
+    float* curve;
+    uint8_t* done;
+} MbxGleetState;
+
+/* Recorded draws for parity tests (device, float64; null when use_tape=0):
+ *   init_pos_u, init_vel_u [B,NP,D] ; rand1, rand2 [B,NP] ; noise [B,3,NP]                                   */
+typedef struct MbxGleetTape {
+    const double *init_pos_u, *init_vel_u, *rand1, *rand2, *noise;
+} MbxGleetTape;
+
+/* d_state [B,NP,27] f32 = observe (9) | pbest_feature (9) | gbest_feature (9) per particle (:110-112, :297-300) */
+int mbx_gleet_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                   const MbxRunConfig* cfg, const MbxGleetState* st, const MbxGleetTape* tape, float* d_state, int B,
+                   void* stream);
+
+/* d_action [B,NP] f32 in [0,1] (share of the pbest attraction per particle) ; outputs d_state [B,NP,27] f32,
+ * d_reward [B] f32 (100 (gbest_before - gbest_after) / max_cost), st->done.  Finished lanes are skipped (reward = 0). */
+int mbx_gleet_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                   const MbxRunConfig* cfg, const MbxGleetState* st, const MbxGleetTape* tape, const float* d_action,
+                   float* d_state, float* d_reward, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

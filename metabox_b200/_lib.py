@@ -68,6 +68,16 @@ class MbxDdqnTape(C.Structure):
     _fields_ = [(n, _P) for n in ('init_u', 'r5', 'noise')]
 
 
+class MbxGleetState(C.Structure):
+    _fields_ = [(n, _P) for n in ('x', 'v', 'pbest_x', 'c_cost', 'pbest', 'pni', 'gbest_x', 'gbest_val', 'gbest_idx',
+                                  'no_improve', 'fes', 'log_index', 'curve_len', 'gen', 'w', 'max_cost', 'pbest_feature',
+                                  'gbest_feature', 'curve', 'done')]
+
+
+class MbxGleetTape(C.Structure):
+    _fields_ = [(n, _P) for n in ('init_pos_u', 'init_vel_u', 'rand1', 'rand2', 'noise')]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/metabox_b200.h declares
@@ -90,6 +100,10 @@ SIGNATURES = {
                                   C.c_int, _P]),
     'mbx_deddqn_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxDdqnState), C.POINTER(MbxDdqnTape), _P,
                                   _P, _P, _P, C.c_int, _P]),
+    'mbx_gleet_init': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxGleetState), C.POINTER(MbxGleetTape), _P,
+                                 C.c_int, _P]),
+    'mbx_gleet_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxGleetState), C.POINTER(MbxGleetTape), _P,
+                                 _P, _P, C.c_int, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
 OPTIONAL_SIGNATURES = {'mbx_prof_read': (C.c_int, [_P, C.c_int])}     # only in libmbx_prof.so

@@ -135,4 +135,27 @@ int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const i
                          (cudaStream_t)stream);
 }
 
+
+int mbx_gleet_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxGleetState* st, const MbxGleetTape* tape, float* d_state, int B, void* stream) {
+    int rc = check_cfg("mbx_gleet_init", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_state, "mbx_gleet_init: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_pos_u && tape->init_vel_u), "mbx_gleet_init: use_tape without tape");
+    return mbx_launch_gleet_init(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_state, B, (cudaStream_t)stream);
+}
+
+int mbx_gleet_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxGleetState* st, const MbxGleetTape* tape, const float* d_action, float* d_state, float* d_reward,
+                   int B, void* stream) {
+    int rc = check_cfg("mbx_gleet_step", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_action && d_state && d_reward, "mbx_gleet_step: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->rand1 && tape->rand2), "mbx_gleet_step: use_tape without tape");
+    return mbx_launch_gleet_step(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_action, d_state, d_reward, B,
+                                 (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -38,3 +38,9 @@ int mbx_launch_deddqn_init(int kind, const MbxInstance* inst, const double* cons
 int mbx_launch_deddqn_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                            const MbxRunConfig* cfg, const MbxDdqnState* s, const MbxDdqnTape* tape, const int32_t* action,
                            float* feature, float* reward, float* dbg, int B, cudaStream_t st);
+int mbx_launch_gleet_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                          const MbxRunConfig* cfg, const MbxGleetState* s, const MbxGleetTape* tape, float* state, int B,
+                          cudaStream_t st);
+int mbx_launch_gleet_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                          const MbxRunConfig* cfg, const MbxGleetState* s, const MbxGleetTape* tape, const float* action,
+                          float* state, float* reward, int B, cudaStream_t st);

@@ -496,3 +496,123 @@ class DE_DDQN_Optimizer(Learnable_Optimizer):
         feat, reward, done = self._engine.update(a)
         self._sync()
         return feat[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())
+
+
+# ======================================================================================== GLEET
+class GLEET_Engine:
+    """B lanes of the GLEET backbone (gleet_optimizer.py:34-314) on one GPU.  `feature` is the [B, NP, 27] state
+    (observe | pbest_feature | gbest_feature per particle); the action is [B, NP] float32 in [0, 1]."""
+    NP = 100
+    N_FEAT = 27
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None,
+                 lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)
+        self.NP = int(NP or GLEET_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.x, self.v, self.pbest_x = z(B, NPn, D), z(B, NPn, D), z(B, NPn, D)
+        self.c_cost, self.pbest = z(B, NPn), z(B, NPn)
+        self.pni = z(B, NPn, dt=i32)
+        self.gbest_x, self.gbest_val = z(B, D), z(B)
+        self.gbest_idx, self.no_improve, self.fes, self.log_index, self.curve_len, self.gen = (z(B, dt=i32) for _ in range(6))
+        self.w = z(B, dt=torch.float64)
+        self.max_cost = z(B)
+        self.pbest_feature, self.gbest_feature = z(B, NPn, 9), z(B, 9)
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, NPn, self.N_FEAT), z(B)
+        self._state = _lib.MbxGleetState(*[t.data_ptr() for t in (
+            self.x, self.v, self.pbest_x, self.c_cost, self.pbest, self.pni, self.gbest_x, self.gbest_val, self.gbest_idx,
+            self.no_improve, self.fes, self.log_index, self.curve_len, self.gen, self.w, self.max_cost, self.pbest_feature,
+            self.gbest_feature, self.curve, self.done)])
+
+    def _cfg(self, use_tape):
+        return _run_config(self.pack.kind, self.NP, self.dim, self.maxFEs, self.n_logpoint, self.log_interval, use_tape,
+                           self.seed, self.lane_base)
+
+    def init_population(self, tape=None):
+        """-> state [B, NP, 27] float32."""
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxGleetTape, tape, self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_gleet_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                           C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                           _lib.stream_ptr())
+        _lib.check(rc, 'mbx_gleet_init')
+        return self.feature
+
+    def update(self, action, tape=None):
+        """action [B, NP] float32 device tensor -> (state [B,NP,27], reward [B], done [B] uint8), all on device."""
+        import torch
+        if tuple(action.shape) != (self.B, self.NP):
+            raise ValueError(f'GLEET action must be [B, NP] = {(self.B, self.NP)}, got {tuple(action.shape)}')
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxGleetTape, tape, self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_gleet_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                           C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(action),
+                                           _lib.ptr(self.feature), _lib.ptr(self.reward), self.B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_gleet_step')
+        return self.feature, self.reward, self.done
+
+    cost_curves = RLEPSO_Engine.cost_curves
+    load_state = RLEPSO_Engine.load_state
+
+    def read_state(self, b):
+        keys = ('x', 'v', 'pbest_x', 'c_cost', 'pbest', 'pni', 'gbest_x', 'gbest_val', 'gbest_idx', 'no_improve', 'w',
+                'max_cost', 'pbest_feature', 'gbest_feature', 'fes', 'log_index', 'curve_len', 'curve', 'done', 'gen')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class GLEET_Optimizer(Learnable_Optimizer):
+    """Drop-in for `GLEET_Optimizer` (gleet_optimizer.py:6-314): one problem, numpy in / numpy out."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.__config = config
+        self.dim = config.dim
+        self.ps = 100
+        self.max_fes = config.maxFEs
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self._engine = None
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = GLEET_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, self.ps)
+        state = self._engine.init_population()
+        self._sync()
+        return state[0].cpu().numpy().astype(np.float64)
+
+    def _sync(self):
+        e = self._engine
+        self.fes = int(e.fes[0].item())
+        self.log_index = int(e.log_index[0].item())
+        self.cost = e.cost_curves(pad=False)[0]
+
+    def update(self, action, problem):
+        import torch
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1))
+        state, reward, done = self._engine.update(a.to(self._engine.device))
+        self._sync()
+        return state[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .optimizer import DE_DDQN_Engine, LDE_Engine, RLEPSO_Engine
+from .optimizer import DE_DDQN_Engine, GLEET_Engine, LDE_Engine, RLEPSO_Engine
 
 
 def lane_table(n_instances, n_runs):
@@ -206,6 +206,20 @@ class DE_DDQN_Sweep(_Sweep):
     def _policy(self, feat):
         q = self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0))
         return torch.argmax(q, dim=-1).to(torch.int32)
+
+
+class GLEET_Sweep(_Sweep):
+    """GLEET_Agent.rollout_episode (gleet_agent.py:293-303): `policy(state [B,NP,27]) -> action [B,NP]` in [0,1] (the
+    reference's attention actor, or any torch callable, runs on the same stream between the fused steps)."""
+
+    def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False,
+                 graph=True):
+        eng = GLEET_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        self.policy = policy
+
+    def _policy(self, feat):
+        return self.policy(feat)
 
 
 class StripedSweep:

@@ -58,6 +58,11 @@ for k, p in enumerate(probs):
             act = torch.rand(B, 35, generator=g).to(dev)
             fn = lambda eng=eng, act=act: eng.update(act)
             n = B * NP
+        elif algo == 'gleet':
+            eng = mo.GLEET_Engine(pack, lane, 10 ** 9, 50, log_interval=10 ** 7, seed=1); eng.init_population()
+            act = torch.rand(B, NP, generator=g).to(dev)
+            fn = lambda eng=eng, act=act: eng.update(act)
+            n = B * NP
         elif algo == 'lde':
             eng = mo.LDE_Engine(pack, lane, 10 ** 9, 50, log_interval=10 ** 7, seed=1, NP=NP); eng.init_population()
             act = torch.rand(B, 2 * NP, generator=g).to(dev)
