@@ -301,10 +301,15 @@ def main():
     # ---- roofline of the dominant kernel: one instrumented sweep of the same workload, CUDA events around every step
     #      launch on the launching stream (a graph replay cannot be timed per kernel) ---------------------------------
     k_ms = k_n = k_fes = 0
+    k_sweep_ms = 0.0
     if rank == 0:
         swi = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, time_kernels=True)
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
         res = swi.run()
+        i1.record()
         k_ms, k_n = swi.kernel_ms()
+        k_sweep_ms = i0.elapsed_time(i1)
         k_fes = int(res['fes'].sum().item()) - init_fes
         del swi
     barrier()
@@ -312,6 +317,16 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = (k_fes * W['bytes_per_eval']) / (k_ms / 1000.0) / 1e9 if k_ms > 0 else None
+        traffic, traffic_note = None, 'no ncu --set full capture recorded for this kernel'
+        try:                                                    # DRAM bytes per launch from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(W['kernel'])
+            if tr:
+                traffic = tr['dram_bytes_per_launch'] * n_local / tr['lanes_per_launch']
+                traffic_note = (f"bytes per launch of {n_local} lanes, scaled from {tr['dram_bytes_per_launch']:.4g} B at "
+                                f"{tr['lanes_per_launch']} lanes ({tr['launch']}); {tr['source']}; algorithmic bytes of a full launch = "
+                                f"{n_local * NP * W['bytes_per_eval']:.4g}")
+        except Exception:
+            pass
         state_mb = {'rlepso': n_local * (3 * NP * DIM + 3 * NP) * 4, 'lde': n_local * (NP * DIM + NP) * 4,
                     'deddqn': n_local * ((NP * DIM + NP) * 4 + 8800)}[args.workload] / 1e6
         out = {
@@ -325,10 +340,11 @@ def main():
                        'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
                        'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_note': traffic_note,
                          'kernel': W['kernel'], 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,
-                         'kernel_share_of_step': (k_ms / (ms_total / args.steps)) if ms_total else None, 'peak_source': peak_src,
-                         'timed': 'separate instrumented (eager) sweep of the same workload right after the timed region',
+                         'kernel_share_of_step': (k_ms / k_sweep_ms) if k_sweep_ms else None, 'peak_source': peak_src,
+                         'timed': 'separate instrumented (eager, unstriped) sweep of the same workload right after the timed region; '
+                                  'kernel_share_of_step = step-kernel time / duration of that sweep',
                          'note': f'algorithmic bytes = {W["bytes_per_eval"]} B/eval x evals charged by the step launches; see DESIGN.md section 4 '
                                  'for what actually bounds the kernel (FP64 ALU / latency, not HBM)'},
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

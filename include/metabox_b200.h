@@ -255,6 +255,15 @@ int mbx_gleet_step(const MbxInstance* d_inst, const double* d_consts, const int3
                    float* d_state, float* d_reward, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Landscape features of sampled walks -- replaces cal_fdc / cal_rie / cal_acf / cal_nop
+ * (optimizer/dedqn_optimizer.py:8-76) and the DFDC / DRIE statistics of RL_HPSDE
+ * (optimizer/rl_hpsde_optimizer.py:169-216) for B walks at once.
+ *   d_sample [B,S,D] f64, d_cost [B,S] f64, d_ref [B,D] f64 or null (null: the best sample of each walk is the reference)
+ *   d_out [B,6] f64 = fdc, rie, acf, nop, dfdc_r, drie_r   (the reference thresholds the last two at 0.15 / 0.5)   */
+int mbx_landscape_features(const double* d_sample, const double* d_cost, const double* d_ref, int B, int S, int D,
+                           double* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

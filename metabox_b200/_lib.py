@@ -104,6 +104,7 @@ SIGNATURES = {
                                  C.c_int, _P]),
     'mbx_gleet_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxGleetState), C.POINTER(MbxGleetTape), _P,
                                  _P, _P, C.c_int, _P]),
+    'mbx_landscape_features': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
 OPTIONAL_SIGNATURES = {'mbx_prof_read': (C.c_int, [_P, C.c_int])}     # only in libmbx_prof.so

@@ -158,4 +158,13 @@ int mbx_gleet_step(const MbxInstance* d_inst, const double* d_consts, const int3
                                  (cudaStream_t)stream);
 }
 
+
+int mbx_landscape_features(const double* d_sample, const double* d_cost, const double* d_ref, int B, int S, int D,
+                           double* d_out, void* stream) {
+    MBX_REQUIRE(B >= 0 && S >= 3 && S <= 512 && D > 0, "mbx_landscape_features: bad shape B=%d S=%d D=%d (3 <= S <= 512)", B, S, D);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_sample && d_cost && d_out, "mbx_landscape_features: null pointer");
+    return mbx_launch_landscape(d_sample, d_cost, d_ref, B, S, D, d_out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -296,3 +296,22 @@ def test_gleet_steps_match_reference():
             _gleet_cmp(N, state, G, f'{key}/s{t}/', f'{key} step {t}')
             np.testing.assert_allclose(reward, float(G[f'{key}/s{t}/reward']), rtol=1e-6, atol=1e-9)
             assert done == bool(G[f'{key}/s{t}/done'])
+
+
+# ----------------------------------------------------------------------------------------- landscape features
+def test_landscape_features_match_reference():
+    """cal_fdc / cal_rie / cal_acf / cal_nop of the reference's dedqn_optimizer.py and the DFDC / DRIE classifications of
+    rl_hpsde_optimizer.py on seeded walks (incl. stepped and plateau costs) vs the oracle."""
+    from oracle import landscape as ol
+    G = load('landscape.npz')
+    n_bool = 0
+    for key in G['cases']:
+        x, c, ref = G[f'{key}/x'], G[f'{key}/c'], G[f'{key}/ref']
+        f = ol.features(x, c, ref)
+        np.testing.assert_allclose(f[:4], G[f'{key}/dedqn'], rtol=1e-9, atol=1e-12, err_msg=key)
+        a, b = G[f'{key}/hpsde_bool']
+        if a >= 0 and abs(f[4] - 0.15) > 1e-9:
+            assert int(0.15 < f[4] <= 1) == a, key; n_bool += 1            # rl_hpsde_optimizer.py:175-180
+        if b >= 0 and abs(f[5] - 0.5) > 1e-9:
+            assert int(0.5 <= f[5] <= 1) == b, key; n_bool += 1             # :212-217
+    assert n_bool >= 40
