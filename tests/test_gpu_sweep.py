@@ -68,10 +68,14 @@ def test_rlepso_sweep_graph_equals_eager():
 
 def test_striped_sweep_on_two_streams_equals_the_single_sweep():
     """Lane stripes on separate CUDA streams / graphs: Philox streams are keyed by the global lane id, so the rows are
-    bit-identical to the unstriped sweep (deterministic policy)."""
+    bit-identical to the unstriped sweep (element-wise policy)."""
     from metabox_b200 import agent as ma, sweep
+    import torch
     pack, probs = _pack()
-    actor = _MeanActor(ma.load_reference_weights(ma.RLEPSO_Actor(), _weights('rlepso')).cuda().eval())
+
+    def actor(x):                    # element-wise => bit-identical whatever the batch size (an MLP's GEMM kernel choice is not)
+        k = torch.arange(1, 36, device=x.device, dtype=torch.float32)
+        return torch.clamp(0.5 + 0.45 * torch.sin(x * k * 7.0), 0, 1)
     inst, _ = sweep.lane_table(len(probs), 3)
     one = sweep.RLEPSO_Sweep(pack, inst, actor, 3000, 50, seed=9, lane_base=7, graph=True, poll=8)
     two = sweep.StripedSweep(lambda ln, lb: sweep.RLEPSO_Sweep(pack, ln, actor, 3000, 50, seed=9, lane_base=lb, graph=True, poll=8),
