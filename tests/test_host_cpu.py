@@ -200,3 +200,85 @@ def test_tester_rows_to_reference_dict_layout():
     assert out['return']['A']['RLEPSO_Agent'] == [-3.0] * 3 and isinstance(out['fes']['A']['RLEPSO_Agent'][0], int)
     out2 = mt.rows_to_results(rows, ['A', 'B'], 3, 'X', {'cost': {}, 'fes': {}})
     assert 'return' not in out2 and mt.cal_t0(4, 50) > 0
+
+
+# ----------------------------------------------------------------------------------------- LDE training maths (CPU)
+def _reference_lde_loss(net, inputs, actions, hs, cs, rewards, traj_num, gamma=0.99):
+    """`LDE_Agent.train_episode` (lde_agent.py:116-129) + `__discounted_norm_rewards` (:68-83) restated with the
+    reference's own data layout (trajectory-major flat batches, nn.LSTM forward) for ONE problem."""
+    import torch
+    T, L = rewards.shape                      # L = traj_num trajectories of equal length T
+    flat = lambda a: a.permute(1, 0, 2).reshape(L * T, -1)          # trajectory-major like the reference's append order
+    mu, sigma, _, _ = net.forward(flat(inputs)[None], flat(hs)[None], flat(cs)[None])
+    logp = torch.sum(torch.distributions.Normal(mu[0], sigma[0]).log_prob(flat(actions) + 1e-8), 1)
+    r = rewards.t().reshape(-1).numpy()
+    disc = np.zeros_like(r)
+    for ep in range(traj_num):
+        run = 0.
+        for t in reversed(range(T)):
+            run = run * gamma + r[ep * T + t]
+            disc[ep * T + t] = run
+    return -torch.mean(logp * torch.as_tensor(disc, dtype=torch.float32))
+
+
+def test_lde_reinforce_loss_and_discounting_match_the_reference_formulas():
+    import torch
+    from metabox_b200 import agent as ma, trainer as mt
+    torch.manual_seed(0)
+    NP, T, TR, P = 10, 7, 20, 3
+    net = ma.LDE_PolicyNet(NP=NP)
+    L = P * TR
+    inputs, actions = torch.rand(T, L, NP + 10), torch.rand(T, L, 2 * NP)
+    hs, cs = torch.randn(T, L, 50) * 0.3, torch.randn(T, L, 50) * 0.3
+    rewards, weight = torch.rand(T, L), torch.ones(T, L)
+    loss, n = mt.reinforce_loss(net, inputs, actions, hs, cs, rewards, weight, TR)
+    want = sum(_reference_lde_loss(net, inputs[:, p * TR:(p + 1) * TR], actions[:, p * TR:(p + 1) * TR], hs[:, p * TR:(p + 1) * TR],
+                                   cs[:, p * TR:(p + 1) * TR], rewards[:, p * TR:(p + 1) * TR], TR) for p in range(P))
+    assert n == P
+    np.testing.assert_allclose(float(loss.detach()), float(want.detach()), rtol=2e-5)
+    # gradients agree too (the hand-written LSTM cell == nn.LSTM)
+    g1 = torch.autograd.grad(loss, list(net.parameters()), retain_graph=True)
+    g2 = torch.autograd.grad(want, list(net.parameters()))
+    for a, b in zip(g1, g2):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-4, atol=2e-5)
+    # finished steps carry zero weight
+    w2 = weight.clone(); w2[4:, :5] = 0
+    l2, _ = mt.reinforce_loss(net, inputs, actions, hs, cs, rewards * w2, w2, TR)
+    assert np.isfinite(float(l2)) and abs(float(l2) - float(loss)) > 0
+
+
+def _grad_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from metabox_b200 import trainer as mt
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(3, 2)
+        for p in lin.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))        # "sum over local problems" gradients
+        total = mt.allreduce_gradients(lin.parameters(), n_local=rank + 1)       # rank 0: 1 problem, rank 1: 2 problems
+        q.put((rank, total, [p.grad.clone().numpy() for p in lin.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """ONE all-reduce per learn step: gradient of the mean per-problem loss over all ranks' problems, on every rank."""
+    import socket
+    import torch.multiprocessing as tmp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = tmp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, total, grads in got:
+        assert total == 3.0
+        for g in grads:
+            np.testing.assert_allclose(g, (1.0 + 2.0) / 3.0)
