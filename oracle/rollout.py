@@ -81,25 +81,41 @@ def deddqn_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoi
 ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout}
 
 
+_SUITES = {}
+
+
 def _worker(args):
     torch.set_num_threads(1)
     fid, dim, maxFEs, weights, seed, max_gens, suit, algo, kw = args
-    tr, te = ob.make_suite(suit, dim, 5.0)
-    inst = [i for i in tr + te if i.fid == fid][0]
+    if (suit, dim) not in _SUITES:                       # instances are built once per worker process
+        tr, te = ob.make_suite(suit, dim, 5.0)
+        _SUITES[(suit, dim)] = {i.fid: i for i in tr + te}
+    inst = _SUITES[(suit, dim)][fid]
     r = ROLLOUTS[algo](inst, dim, maxFEs, weights, seed, max_gens, **kw)
     return r['fes'], r['seconds']
 
 
-def timed_sample(dim, maxFEs, weights, fids, max_gens, n_procs, suit='bbob', seed0=0, algo='rlepso', **kw):
-    """Run one bounded sample: each function id in `fids` gets one run truncated at `max_gens` generations (steps for
-    DE-DDQN), spread over a pool of `n_procs` single-threaded workers.  -> (total fes, wall seconds)."""
+def make_pool(n_procs):
+    """A fork pool of single-threaded workers (None for n_procs <= 1); create it once, outside the timed region."""
     import multiprocessing as mp
-    jobs = [(f, dim, maxFEs, weights, seed0 + k, max_gens, suit, algo, kw) for k, f in enumerate(fids)]
+    return mp.get_context('fork').Pool(n_procs) if n_procs > 1 else None
+
+
+def timed_sample(dim, maxFEs, weights, fids, max_gens, n_procs, suit='bbob', seed0=0, algo='rlepso', runs=1, pool=None, **kw):
+    """Run one bounded sample: each function id in `fids` gets `runs` runs truncated at `max_gens` generations (steps for
+    DE-DDQN), spread over a pool of `n_procs` single-threaded workers (heaviest jobs are not known in advance: chunksize 1).
+    -> (total fes, wall seconds of the map itself when `pool` is given, else including the pool start-up)."""
+    jobs = [(f, dim, maxFEs, weights, seed0 + 1000 * r + k, max_gens, suit, algo, kw) for r in range(runs) for k, f in enumerate(fids)]
+    own = pool is None and n_procs > 1
     t0 = time.perf_counter()
-    if n_procs <= 1:
+    if own:
+        pool = make_pool(n_procs)
+        t0 = time.perf_counter() if False else t0
+    if pool is None:
         res = [_worker(j) for j in jobs]
     else:
-        with mp.get_context('fork').Pool(n_procs) as pool:
-            res = pool.map(_worker, jobs, chunksize=1)
+        res = pool.map(_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
+    if own:
+        pool.close(); pool.join()
     return sum(r[0] for r in res), wall
