@@ -1,12 +1,8 @@
-// mbx_bbob.cuh -- device fitness functions: the 24 BBOB base shapes (+ noise models) and the
-// protein-docking energy, one thread per candidate, float64 arithmetic in the reference's operation
-// order (reference: problem/bbob.py:6-8,51-93,108-146,149-890; problem/protein_docking.py:28-48).
-//
-// Calling convention: the CTA has staged the instance constants in shared memory (`C`, layout
-// shift|R|M2|cv0|cv1|cv2, see MbxInstance) and the candidate is reachable through an accessor
-// X(d) -> double.  `zs` is a per-thread scratch column in shared memory: element k at zs[k*zst]
-// (bank-conflict free; `zst` = the column stride = number of evaluating threads).  Loops containing libm calls are kept rolled (code size); D*D mat-vecs are
-// fully unrolled over d with the operand vector in registers and R rows broadcast from smem.
+// mbx_bbob.cuh -- device building blocks of the fitness functions: instance-constant views, the BBOB transforms
+// (T_osz, T_asy, penalty), the Gallagher float32 peak screening state + exact float64 peak value, the noise models, and the
+// protein-docking energy (one warp per candidate).  float64 arithmetic in the reference's operation order
+// (reference: problem/bbob.py:6-8,51-93,108-146,149-890; problem/protein_docking.py:28-48).
+// The 24 BBOB shapes themselves are evaluated CTA-cooperatively in mbx_bbob_cta.cuh.
 #pragma once
 #include "mbx_common.cuh"
 
@@ -48,50 +44,6 @@ __device__ __forceinline__ double pen_x(const XA& X, double ub) {               
     }
     return p;
 }
-// zs[k] = sum_d M[k][d] * y[d]   (M row-major in smem, y in registers)
-template <int D>
-__device__ __forceinline__ void matvec(const double* __restrict__ M, const double (&y)[D], double* zs, const int zst) {
-#pragma unroll 2
-    for (int k = 0; k < D; ++k) {
-        const double* row = M + k * D;
-        double a0 = 0., a1 = 0.;
-#pragma unroll
-        for (int d = 0; d + 1 < D; d += 2) {
-            a0 = fma(row[d], y[d], a0);
-            a1 = fma(row[d + 1], y[d + 1], a1);
-        }
-        if (D & 1) a0 = fma(row[D - 1], y[D - 1], a0);
-        zs[k * zst] = a0 + a1;
-    }
-}
-template <int D>
-__device__ __forceinline__ void load_col(double (&y)[D], const double* zs, const int zst) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) y[d] = zs[d * zst];
-}
-template <int D>
-__device__ __forceinline__ double rastrigin_sum(const double* zs, const int zst) {
-    double sc = 0., sq = 0.;
-#pragma unroll 1
-    for (int k = 0; k < D; ++k) {
-        double z = zs[k * zst];
-        sc += cospi(2. * z);                               // cos(2 pi z) without the libm range reduction
-        sq += z * z;
-    }
-    return 10. * ((double)D - sc) + sq;
-}
-template <int D>
-__device__ __forceinline__ double rosen_sum(const double* zs, const int zst) {
-    double f = 0.;
-#pragma unroll 1
-    for (int k = 0; k + 1 < D; ++k) {
-        double a = zs[k * zst], b = zs[(k + 1) * zst];
-        double u = a * a - b, w = a - 1.;
-        f += 100. * (u * u) + w * w;
-    }
-    return f;
-}
-
 // Gallagher: max_p w_p exp(-(1/2D) sum_k C_pk (y_k - (R y_p)_k)^2), y = R x in zs (bbob.py:795-799).
 // exp is monotone, so the maximum is attained at argmax_p s_p, s_p = ln w_p - acc_p / 2D.  The P x D scan runs in float32
 // (packed f32x2, constants pre-rounded by the host).  Error budget of the float32 acc_p: each z_k = y_k - c_k is off by at
@@ -124,372 +76,6 @@ struct GalScan {            // running (best s, its lower bound, its peak) and t
         else hi2 = fmaxf(hi2, hi);
     }
 };
-// `tile` (optional): shared-memory staging buffer of `tile_bytes` bytes, 16-byte aligned.  With a tile, ALL threads of the
-// CTA must call (it contains __syncthreads; `act` = this thread has a candidate): the float32 peak table is streamed
-// through shared memory once per CTA (register double-buffered) and broadcast to the threads, instead of every warp
-// pulling it through L1/L2 again.  Without a tile (tile == nullptr) only active threads call and peaks come from __ldg.
-template <int D>
-__device__ __forceinline__ double gallagher_max(const double* __restrict__ G, const int P, const double* zs, const int zst,
-                                                const bool act = true, float4* tile = nullptr, const int tile_bytes = 0) {
-    static_assert(D % 2 == 0, "packed float32 screening pairs adjacent dimensions");
-    constexpr int HD = D / 2;
-    const double* gC = G + ConstView<D>::kDoubles + P * D;
-    const double* gw = gC + P * D;
-    const double* gRy = gw + P;
-    const int o32 = (ConstView<D>::kDoubles + 3 * P * D + P + 1) & ~1;
-    const float4* g32 = reinterpret_cast<const float4*>(G + o32);
-    const float* lnw = reinterpret_cast<const float*>(G + o32 + P * D);
-    const double coef = -0.5 / (double)D;
-    const float coef32 = (float)coef;
-    float2 yf[HD];
-    float ymax = 0.f;
-    if (act) {
-#pragma unroll
-        for (int k = 0; k < HD; ++k) yf[k] = make_float2((float)zs[(2 * k) * zst], (float)zs[(2 * k + 1) * zst]);
-#pragma unroll
-        for (int k = 0; k < HD; ++k) ymax = fmaxf(ymax, fmaxf(fabsf(yf[k].x), fabsf(yf[k].y)));
-    } else {
-#pragma unroll
-        for (int k = 0; k < HD; ++k) yf[k] = make_float2(0.f, 0.f);
-    }
-    const float K1 = -coef32 * 2.f * 1.3e-7f * (ymax + 5.f * sqrtf((float)D) + 1.f) * sqrtf(31.7f * (float)D);
-    GalScan sc;
-    if (tile == nullptr) {
-#pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-            float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < HD; ++k) {
-                const float4 c4 = __ldg(g32 + p * HD + k);
-                const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
-                acc2 = __ffma2_rn(__fmul2_rn(make_float2(c4.x, c4.y), z), z, acc2);
-            }
-            sc.visit(acc2.x + acc2.y, __ldg(lnw + p), coef32, K1, p);
-        }
-    } else {
-        const int tid = threadIdx.x, NT = blockDim.x;
-        int TP = tile_bytes / (16 * HD + 4);
-        if (TP * HD > 2 * NT) TP = 2 * NT / HD;                  // two prefetch registers per thread
-        float* tl = reinterpret_cast<float*>(tile + TP * HD);
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        float rl = 0.f;
-        auto fetch = [&](const int p0) {
-            const int n = min(TP, P - p0);
-            if (tid < n * HD) r0 = __ldg(g32 + p0 * HD + tid);
-            if (tid + NT < n * HD) r1 = __ldg(g32 + p0 * HD + tid + NT);
-            if (tid < n) rl = __ldg(lnw + p0 + tid);
-        };
-        fetch(0);
-#pragma unroll 1
-        for (int p0 = 0; p0 < P; p0 += TP) {
-            const int n = min(TP, P - p0);
-            __syncthreads();                                     // previous tile fully consumed
-            if (tid < n * HD) tile[tid] = r0;
-            if (tid + NT < n * HD) tile[tid + NT] = r1;
-            if (tid < n) tl[tid] = rl;
-            __syncthreads();
-            if (p0 + TP < P) fetch(p0 + TP);                     // in flight while this tile is consumed
-            if (act) {
-#pragma unroll 1
-                for (int p = 0; p < n; ++p) {
-                    float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int k = 0; k < HD; ++k) {
-                        const float4 c4 = tile[p * HD + k];
-                        const float2 z = __fadd2_rn(yf[k], make_float2(-c4.z, -c4.w));
-                        acc2 = __ffma2_rn(__fmul2_rn(make_float2(c4.x, c4.y), z), z, acc2);
-                    }
-                    sc.visit(acc2.x + acc2.y, tl[p], coef32, K1, p0 + p);
-                }
-            }
-        }
-        __syncthreads();                                         // the tile may be reused by the caller
-    }
-    if (!act) return 0.;
-    if (sc.lo1 > sc.hi2) return gallagher_peak64<D>(gC, gRy, gw, sc.p1, zs, zst, coef);
-    double g = -1e300;                                     // near-tie (or non-finite input): all peaks in float64
-#pragma unroll 1
-    for (int p = 0; p < P; ++p) g = fmax(g, gallagher_peak64<D>(gC, gRy, gw, p, zs, zst, coef));
-    return g;
-}
-// Gallagher f(x) with the staged peak table: every thread of the CTA calls (act = has a candidate).
-template <int D, class XA>
-__device__ __forceinline__ double bbob_gallagher_cta(const MbxInstance& h, const double* __restrict__ C, const double* __restrict__ G,
-                                                     const XA& X, double* zs, const int zst, const bool act, float4* tile, const int tile_bytes) {
-    ConstView<D> c(C);
-    double bh = 0.;
-    if (act) {
-        if (h.bh_coef != 0.) {
-            const double p = pen_x<D>(X, h.ub);
-            bh = (h.bh_coef == 1.) ? p : h.bh_coef * p;
-        }
-        double y[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = X(d);
-        matvec<D>(c.R, y, zs, zst);
-    }
-    const double g = gallagher_max<D>(G, h.n_peaks, zs, zst, act, tile, tile_bytes);
-    if (!act) return 0.;
-    const double t = t_osz(10. - g);
-    return t * t + h.bias + bh;
-}
-
-// Noise-free f(x) incl. bias and boundary handling  (== BBOB_Basic_Problem.func)
-template <int D, class XA>
-__device__ double bbob_true(const MbxInstance& h, const double* __restrict__ C, const double* __restrict__ G,
-                            const XA& X, double* zs, const int zst) {
-    ConstView<D> c(C);
-    const double bias = h.bias, ub = h.ub;
-    double y[D];
-    const int base = h.base;
-    double bh = 0.;
-    if (h.bh_coef != 0.) {
-        double p = pen_x<D>(X, ub);
-        bh = (h.bh_coef == 1.) ? p : h.bh_coef * p;
-    }
-    // ---------------------------------------------------------------- first linear map
-    if (base == 9 || base == 19) {                       // z = M2 x + 0.5   (bbob.py:434, :703)
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = X(d);
-        matvec<D>(c.M2, y, zs, zst);
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * zst] += 0.5;
-    } else if (base == 5 || base == 20) {
-        // no rotation
-    } else if (base == 24) {                             // z = R (2 sign(s) x - mu0)   (bbob.py:885-886)
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = c.cv2[d] * X(d) - h.sc[0];
-        matvec<D>(c.R, y, zs, zst);
-    } else if (base == 8) {                              // R = I (bbob.py:362)
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * zst] = X(d) - c.s[d];
-    } else if (base != 21 && base != 22) {               // z = R (x - s)   (bbob.py:6-8)
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = X(d) - c.s[d];
-        matvec<D>(c.R, y, zs, zst);
-    }
-    // ---------------------------------------------------------------- per-shape tails
-    switch (base) {
-    case 1: {                                            // Sphere bbob.py:156-159
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = zs[k * zst]; f += z * z; }
-        return f + bias + bh;
-    }
-    case 2: case 10: {                                   // Ellipsoidal bbob.py:220-226, 447-453
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = t_osz(zs[k * zst]); f += c.cv0[k] * (z * z); }
-        return f + bias + bh;
-    }
-    case 3: {                                            // Rastrigin bbob.py:240-243
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * zst] = c.cv0[k] * t_asy(t_osz(zs[k * zst]), 0.2, c.cv1[k]);
-        return rastrigin_sum<D>(zs, zst) + bias;
-    }
-    case 4: {                                            // Buche-Rastrigin bbob.py:258-265
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) {
-            double z = t_osz(zs[k * zst]);
-            if (!(k & 1) && z > 0.) z *= 10.;
-            zs[k * zst] = z * c.cv0[k];
-        }
-        double r = rastrigin_sum<D>(zs, zst);
-        return r + 100. * pen_x<D>(X, ub) + bias;
-    }
-    case 5: {                                            // Linear slope bbob.py:281-287
-        double f = 0.;
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) {
-            double x = X(d), z = x;
-            if (x * c.s[d] > ub * ub) z = (z > 0. ? 1. : (z < 0. ? -1. : 0.)) * ub;
-            double s = c.cv0[d];
-            f += ub * fabs(s) - z * s;
-        }
-        return f + bias;
-    }
-    case 6: {                                            // Attractive sector bbob.py:302-307
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) {
-            double z = zs[k * zst];
-            if (z * c.s[k] > 0.) z *= 100.;
-            f += z * z;
-        }
-        return pow(t_osz(f), 0.9) + bias;
-    }
-    case 7: {                                            // Step ellipsoidal bbob.py:320-325
-        double zh0 = fabs(zs[0]);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            double zh = zs[d * zst];
-            y[d] = fabs(zh) > 0.5 ? floor(0.5 + zh) : floor(0.5 + 10. * zh) / 10.;
-        }
-        matvec<D>(c.M2, y, zs, zst);
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) { double z = zs[k * zst]; f += c.cv0[k] * (z * z); }
-        return 0.1 * fmax(zh0 / 1e4, f) + bh + bias;
-    }
-    case 8: {                                            // Rosenbrock bbob.py:365-368
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) zs[k * zst] = h.sc[0] * zs[k * zst] + 1.;
-        return rosen_sum<D>(zs, zst) + bias + bh;
-    }
-    case 9:                                              // Rosenbrock rotated bbob.py:432-435
-        return rosen_sum<D>(zs, zst) + bias;
-    case 11: {                                           // Discus bbob.py:498-502
-        double z0 = t_osz(zs[0]);
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = t_osz(zs[k * zst]); f += z * z; }
-        return 1e6 * (z0 * z0) + f + bias;
-    }
-    case 12: {                                           // Bent cigar bbob.py:517-522
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * zst], 0.5, c.cv1[d]);
-        matvec<D>(c.R, y, zs, zst);
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = zs[k * zst]; f += 1e6 * (z * z); }
-        double z0 = zs[0];
-        return z0 * z0 + f + bias;
-    }
-    case 13: {                                           // Sharp ridge bbob.py:537-540
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 1; k < D; ++k) { double z = zs[k * zst]; f += z * z; }
-        double z0 = zs[0];
-        return z0 * z0 + 100. * sqrt(f) + bias;
-    }
-    case 14: {                                           // Different powers bbob.py:550-554
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) f += exp(c.cv0[k] * log(fabs(zs[k * zst])));     // |z|^e ; z = 0 -> exp(-inf) = 0
-        return sqrt(f) + bias + bh;
-    }
-    case 15: {                                           // Rastrigin F15 bbob.py:597-602
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * zst] = t_asy(t_osz(zs[d * zst]), 0.2, c.cv1[d]);
-        load_col<D>(y, zs, zst);
-        matvec<D>(c.M2, y, zs, zst);
-        return rastrigin_sum<D>(zs, zst) + bias;
-    }
-    case 16: {                                           // Weierstrass bbob.py:620-625
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) zs[d * zst] = t_osz(zs[d * zst]);
-        load_col<D>(y, zs, zst);
-        matvec<D>(c.M2, y, zs, zst);
-        double tot = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) {
-            // sum_j 0.5^j cos(2 pi 3^j (z + 0.5)): (cos, sin) of the base angle once (sincospi: exact range reduction), then
-            // the triple-angle map (c, s) -> (c (1 - 4 s^2), s (4 c^2 - 1)) eleven times.  The pair form has no 1/sin
-            // blow-up: an angle error triples per step, so term j carries <= 3^j ulp * 0.5^j weight (~1e-14 in total),
-            // below the reference's own cos(fl(2 pi (z + 0.5)) 3^j) argument rounding.
-            double sn, cs;
-            sincospi(2. * (zs[k * zst] + 0.5), &sn, &cs);
-            double inner = cs, a = 0.5;
-#pragma unroll
-            for (int j = 1; j < 12; ++j) {
-                const double c2 = cs * cs, s2 = sn * sn;
-                cs = cs * (1. - 4. * s2);
-                sn = sn * (4. * c2 - 1.);
-                inner = fma(a, cs, inner);
-                a *= 0.5;
-            }
-            tot += inner;
-        }
-        double m = tot / (double)D - h.sc[0];
-        return 10. * (m * m * m) + (10. / (double)D) * pen_x<D>(X, ub) + bias;
-    }
-    case 17: case 18: {                                  // Schaffers bbob.py:639-645
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = t_asy(zs[d * zst], 0.5, c.cv1[d]);
-        matvec<D>(c.M2, y, zs, zst);
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k + 1 < D; ++k) {
-            double a = zs[k * zst], b = zs[(k + 1) * zst];
-            double s = sqrt(a * a + b * b);
-            double sn = sin(50. * exp(0.2 * log(s)));          // s^0.2 ; s = 0 -> 0
-            f += sqrt(s) * (sn * sn + 1.);
-        }
-        double m = (1. / (double)(D - 1)) * f;
-        return m * m + bh + bias;
-    }
-    case 19: {                                           // Griewank-Rosenbrock bbob.py:701-705
-        double f = 0.;
-#pragma unroll 1
-        for (int k = 0; k + 1 < D; ++k) {
-            double a = zs[k * zst], b = zs[(k + 1) * zst];
-            double u = a * a - b, w = 1. - a;
-            double s = 100. * (u * u) + w * w;
-            f += s / 4000. - cos(s);
-        }
-        double fac = h.sc[0];
-        return fac + fac * f / ((double)D - 1.) + bias + bh;
-    }
-    case 20: {                                           // Schwefel bbob.py:751-759
-        double f = 0., pen = 0., prev = 0.;
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) {
-            double z0 = c.cv2[d] * X(d);
-            double z = z0;
-            if (d > 0) z += 0.25 * (prev - c.cv1[d - 1]);
-            prev = z0;
-            z = 100. * (c.cv0[d] * (z - c.cv1[d]) + c.cv1[d]);
-            f += z * sin(sqrt(fabs(z)));
-            double t = fmax(0., fabs(z / 100.) - ub);
-            pen += t * t;
-        }
-        return 4.189828872724339 - 0.01 * (f / (double)D) + 100. * pen + bias;
-    }
-    case 21: case 22: {                                  // Gallagher bbob.py:795-799
-        // z_p = R (x - y_p) = R x - R y_p : one mat-vec per candidate, R y_p packed by the host (problem.py const_block)
-#pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = X(d);
-        matvec<D>(c.R, y, zs, zst);
-        double g = gallagher_max<D>(G, h.n_peaks, zs, zst);
-        double t = t_osz(10. - g);
-        return t * t + bias + bh;
-    }
-    case 23: {                                           // Katsuura bbob.py:855-866
-        double prod = 1.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) {
-            // sum_{j=1..32} |2^j z - round(2^j z)| / 2^j : every term is exact in binary64 (power-of-two scalings, |2^j z| <
-            // 2^51); round() through the 1.5*2^52 magic constant (ties give the same |.| = 0.5 as the reference's floor(t+.5))
-            const double z = zs[k * zst];
-            double acc = 0.;
-#pragma unroll
-            for (int j = 1; j <= 32; ++j) {
-                const double p2 = (double)(1ull << j), ip2 = 1. / (double)(1ull << j);
-                const double t = p2 * z;
-                const double r = (t + 6755399441055744.) - 6755399441055744.;
-                acc = fma(fabs(t - r), ip2, acc);
-            }
-            prod *= exp(h.sc[0] * log(1. + (double)(k + 1) * acc));
-        }
-        return prod * h.sc[1] - h.sc[1] + pen_x<D>(X, ub) + bias;
-    }
-    case 24: {                                           // Lunacek bbob.py:883-890
-        double s1 = 0., s2 = 0.;
-#pragma unroll 1
-        for (int d = 0; d < D; ++d) {
-            double xh = c.cv2[d] * X(d);
-            double a = xh - h.sc[0], b = xh - h.sc[2];
-            s1 += a * a; s2 += b * b;
-        }
-        double sc = 0.;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k) sc += cospi(2. * zs[k * zst]);
-        return fmin(s1, (double)D + h.sc[1] * s2) + 10. * ((double)D - sc) + 1e4 * pen_x<D>(X, ub) + bias;
-    }
-    }
-    return 0.;
-}
-
 // Noise models bbob.py:108-146.  u1,u2 uniforms / n1,n2 normals in the reference's draw order.
 __device__ __forceinline__ double bbob_noise(const MbxInstance& h, double ftrue, double d0, double d1, double d2) {
     if (h.noise == MBX_NOISE_NONE) return ftrue;

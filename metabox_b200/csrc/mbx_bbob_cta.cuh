@@ -1,14 +1,13 @@
 // mbx_bbob_cta.cuh -- CTA-cooperative evaluation of a tile of BBOB candidates.
 //
-// Same arithmetic as the per-thread `bbob_true` (mbx_bbob.cuh; reference problem/bbob.py:149-890), re-organised so that
+// The 24 BBOB shapes (reference problem/bbob.py:149-890), organised so that
 // every thread of the CTA works whatever the number of candidates n (n = NP for the population kernels, n = 1 for the
 // DE-DDQN single trial):
 //   * element-wise transforms (T_osz, T_asy, cos / Weierstrass / Katsuura series, pair terms ...) run over all (i, k)
 //     pairs of the [n, D] tile, one pair per thread per round -- 100 candidates use 128 of 128 lanes instead of 100, and a
 //     single candidate is spread over D threads instead of one;
 //   * the D x D rotations are register-tiled (TI candidates x TK rows per thread, operands from shared memory);
-//   * the reductions over k stay sequential per candidate (thread i sums row i in ascending k), i.e. the summation
-//     order of `bbob_true` is preserved.
+//   * the reductions over k stay sequential per candidate (thread i sums row i in ascending k).
 // Scratch: B[n][ZS] float64 in shared memory, ZS = D + 1 (odd: rows hit distinct banks for the per-candidate passes).
 // ALL threads of the CTA must call (barriers inside).  Returns f(x) incl. bias and boundary handling for candidate
 // `threadIdx.x` (valid when threadIdx.x < n and the candidate is not masked out); requires n <= blockDim.x.
@@ -76,7 +75,11 @@ __device__ __forceinline__ void matvec_cta_auto(const double* __restrict__ M, do
     else matvec_cta<D, 1, 1>(M, B, n, add);                        // few candidates: one output per thread
 }
 
-__device__ __forceinline__ double weierstrass_inner(const double z) {     // sum_j 0.5^j cos(2 pi 3^j (z + 0.5)), see bbob_true case 16
+// Weierstrass (bbob.py:620-625): sum_{j<12} 0.5^j cos(2 pi 3^j (z + 0.5)).  (cos, sin) of the base angle once (sincospi:
+// exact range reduction), then the triple-angle map (c, s) -> (c (1 - 4 s^2), s (4 c^2 - 1)) eleven times.  The pair form has
+// no 1/sin blow-up: an angle error triples per step, so term j carries <= 3^j ulp * 0.5^j weight (~1e-14 in total), below the
+// reference's own cos(fl(2 pi (z + 0.5)) 3^j) argument rounding.
+__device__ __forceinline__ double weierstrass_inner(const double z) {
     double sn, cs;
     sincospi(2. * (z + 0.5), &sn, &cs);
     double inner = cs, a = 0.5;
@@ -90,7 +93,10 @@ __device__ __forceinline__ double weierstrass_inner(const double z) {     // sum
     }
     return inner;
 }
-__device__ __forceinline__ double katsuura_term(const double z, const int k, const double expo) {   // bbob_true case 23
+// Katsuura (bbob.py:855-866): (1 + (k+1) sum_{j=1..32} |2^j z - round(2^j z)| / 2^j)^expo.  Every term of the sum is exact in
+// binary64 (power-of-two scalings, |2^j z| < 2^51); round() through the 1.5 * 2^52 magic constant (ties give the same
+// |.| = 0.5 as the reference's floor(t + .5)).
+__device__ __forceinline__ double katsuura_term(const double z, const int k, const double expo) {
     double acc = 0.;
 #pragma unroll
     for (int j = 1; j <= 32; ++j) {
@@ -109,8 +115,8 @@ __device__ __forceinline__ void gal_merge(GalScan& a, const float s1, const floa
     else a.hi2 = fmaxf(fmaxf(a.hi2, hi2), bhi);
 }
 
-// Gallagher max_p w_p exp(coef acc_p) for the rows of B (= R x); see gallagher_max in mbx_bbob.cuh for the float32
-// screening + exact float64 winner scheme.  Each candidate is scanned by GP threads (GP = 1 for a full population,
+// Gallagher max_p w_p exp(coef acc_p) for the rows of B (= R x); float32 screening + exact float64 winner scheme as
+// described at GalScan in mbx_bbob.cuh.  Each candidate is scanned by GP threads (GP = 1 for a full population,
 // up to 32 for a single candidate), every thread taking the peaks p = g (mod GP); partial scans are merged by shuffles.
 // `tile`: optional staging buffer for the float32 peak table (else __ldg).  Result valid in thread i (< n).
 template <int D>
