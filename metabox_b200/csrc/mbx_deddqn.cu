@@ -10,6 +10,17 @@
 #include "mbx_eval.cuh"
 #include "mbx_launch.h"
 
+#ifdef MBX_PROFILE
+extern "C" int mbx_prof_read_deddqn(unsigned long long* h16, int reset) {
+    if (cudaMemcpyFromSymbol(h16, g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return MBX_ECUDA;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return MBX_ECUDA;
+    }
+    return MBX_OK;
+}
+#endif
+
 #define DD_GEN_MAX 10
 #define DD_W 50
 #define DD_WS 8           // doubles per window entry: action, om0..om3, trial_cost, seq, pad
@@ -56,12 +67,16 @@ __device__ __forceinline__ double dd_block_sum(double v, double* red) {
 __device__ __forceinline__ int dd_rank(const float* c, int i, int NP) {
     const float ci = c[i];
     int r = 0;
-    for (int j = 0; j < NP; ++j) {
-        const float cj = c[j];
-        const bool before = isnan(ci) ? (!isnan(cj) || j < i) : (cj < ci || (cj == ci && j < i));
-        r += before ? 1 : 0;
+    if (isnan(ci)) {
+        for (int j = 0; j < NP; ++j) { const float cj = c[j]; r += (!isnan(cj) || j < i) ? 1 : 0; }
+        return r;
     }
-    return r;
+    int lt = 0, eq = 0;                                   // a NaN c[j] fails both comparisons: it sorts after ci
+#pragma unroll 4
+    for (int j = 0; j < i; ++j) { const float cj = c[j]; lt += cj < ci ? 1 : 0; eq += cj == ci ? 1 : 0; }
+#pragma unroll 4
+    for (int j = i + 1; j < NP; ++j) lt += c[j] < ci ? 1 : 0;
+    return lt + eq;
 }
 
 // fitness of ONE candidate (float32 tile `x`), noise applied.  ALL threads of the CTA call: the BBOB path is the
@@ -141,11 +156,23 @@ __device__ void dd_features(const MbxRunConfig& cfg, const MbxDdqnState& S, int 
         const double* ox = S.om_max + (((size_t)b * 4 + op) * 4 + m) * DD_GEN_MAX;
         double f19 = 0., f35 = 0., f67 = 0.;
         int tot = 0;
-        for (int g = 0; g < G; ++g) {
-            const int n = nt[g], k = ns[g];
-            tot += n;
-            if (n > 0) f19 += (double)k / (double)n;
-            if (k > 0) { f35 += os[g]; f67 += ox[g]; }
+#pragma unroll
+        for (int g0 = 0; g0 < DD_GEN_MAX; g0 += 5) {                      // loads of 5 slots in flight together
+            int nv[5], kv[5]; double ov[5], xv[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const bool on = g0 + j < G;
+                nv[j] = on ? nt[g0 + j] : 0; kv[j] = on ? ns[g0 + j] : 0; ov[j] = on ? os[g0 + j] : 0.; xv[j] = on ? ox[g0 + j] : 0.;
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                if (g0 + j < G) {
+                    const int n = nv[j], k = kv[j];
+                    tot += n;
+                    if (n > 0) f19 += (double)k / (double)n;
+                    if (k > 0) { f35 += ov[j]; f67 += xv[j]; }
+                }
+            }
         }
         if (tot > 0) f35 = f35 / (double)tot;
         double f51 = 0.;
@@ -236,6 +263,7 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
                    float* __restrict__ feature, float* __restrict__ reward, float* __restrict__ dbg) {
     const int b = blockIdx.x;
     if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
+    PROF_INIT
     using L = DdqnSmem<D, KIND>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MbxInstance* sh = reinterpret_cast<MbxInstance*>(smem_raw + L::oHdr);
@@ -252,7 +280,17 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     int32_t* ints = S.ints + (size_t)b * 8;
     if (a < 0 || a > 3) { if (tid == 0) ints[DD_I_ERR] = 1; return; }      // reference: ValueError('Action error') (:153)
     const MbxInstance* gi = inst + lane_inst[b];
-    stage_instance<D, KIND>(gi, consts, sh, sC);
+    // one candidate per step touches each constant about once: BBOB constants are read straight from global memory (L1/L2
+    // resident, shared by all lanes of the instance) instead of staging 15 KB per CTA per step; the protein energy re-reads
+    // its basis per atom and keeps the staged copy
+    const double* cC = sC;
+    if (KIND == MBX_KIND_PROTEIN) stage_instance<D, KIND>(gi, consts, sh, sC);
+    else {
+        const int* hs = reinterpret_cast<const int*>(gi);
+        int* hd = reinterpret_cast<int*>(sh);
+        for (int k = tid; k < (int)(sizeof(MbxInstance) / 4); k += MBX_NT) hd[k] = hs[k];
+        cC = consts + gi->off;
+    }
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     float* X = S.X + base;
     float* Xg = S.X_gbest + (size_t)b * D;
@@ -296,6 +334,7 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         }
     }
     __syncthreads();
+    PROF_MARK(0);
     const MbxInstance& h = *sh;
     const double lb = h.lb, ub = h.ub;
     // ---- mutation + clip (:144-155); Cr = 1 => trial = donor (:157) -------------------------------------------------
@@ -315,38 +354,44 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         if (dbg) dbg[(size_t)b * (D + 1) + d] = t32;
     }
     __syncthreads();
+    PROF_MARK(1);
     // ---- median of the (pre-selection) costs (:172), then the fitness of the trial with the whole CTA (:159-163) ----------
     for (int i = tid; i < NP; i += MBX_NT) {
         const int rk = dd_rank(sc, i, NP);
         if (rk == (NP - 1) / 2) mf[1] = sc[i];
         if (rk == NP / 2) mf[2] = sc[i];
     }
+    __syncthreads();
+    PROF_MARK(2);
     {
-        const double f = dd_eval_one<D, KIND>(h, sC, consts + gi->off, trial, scratch, ph, 0u, (uint32_t)fes0, lane,
+        const double f = dd_eval_one<D, KIND>(h, cC, consts + gi->off, trial, scratch, ph, 0u, (uint32_t)fes0, lane,
                                               cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 : nullptr, 1);
         if (tid == 0) mf[0] = (float)f;
     }
     __syncthreads();
+    PROF_MARK(3);
     const float tc = mf[0];
     const float cp = sc[p];
     const double dtc = (double)tc;
-    // ---- thread 0: reward, credit records, window, stagnation, selection flags (:165-201) -------------------------------
+    // ---- reward, credit records (threads 1..4: one offspring metric each; their read-modify-writes of the history run in
+    //      parallel with thread 0's window bookkeeping), window, stagnation, selection flags (:165-201) ---------------------
+    const double med = ((double)mf[1] + (double)mf[2]) / 2.;              // np.median: mean of the middle pair
+    const double om[4] = {(double)cp - dtc, (double)cpb - dtc, (double)cgb - dtc, med - dtc};
+    if (tid >= 1 && tid <= 4) {
+        const int m = tid - 1;
+        const double omv = m == 0 ? om[0] : (m == 1 ? om[1] : (m == 2 ? om[2] : om[3]));
+        if (omv > 0.) {
+            const size_t k = (((size_t)b * 4 + a) * 4 + m) * DD_GEN_MAX;
+            const int n = S.n_succ[k];
+            S.om_sum[k] = n ? S.om_sum[k] + omv : omv;
+            S.om_max[k] = n ? fmax(S.om_max[k], omv) : omv;
+            S.n_succ[k] = n + 1;
+        }
+    }
+    if (tid == 5) S.n_tot[((size_t)b * 4 + a) * DD_GEN_MAX] += 1;
     if (tid == 0) {
         if (dbg) dbg[(size_t)b * (D + 1) + D] = tc;
         reward[b] = (float)fmax((double)cp - dtc, 0.);
-        S.n_tot[((size_t)b * 4 + a) * DD_GEN_MAX] += 1;
-        const double med = ((double)mf[1] + (double)mf[2]) / 2.;          // np.median: mean of the middle pair
-        double om[4] = {(double)cp - dtc, (double)cpb - dtc, (double)cgb - dtc, med - dtc};
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            if (om[m] > 0.) {
-                const size_t k = (((size_t)b * 4 + a) * 4 + m) * DD_GEN_MAX;
-                const int n = S.n_succ[k];
-                S.om_sum[k] = n ? S.om_sum[k] + om[m] : om[m];
-                S.om_max[k] = n ? fmax(S.om_max[k], om[m]) : om[m];
-                S.n_succ[k] = n + 1;
-            }
-        }
         // window OM_W (:176-186): when full drop the oldest entry of the same operator, else the entry with the largest
         // trial cost (first in list order on ties); the new entry goes to the end of the list
         int slot = wlen;
@@ -379,6 +424,7 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         mi[10] = replaced; mi[11] = newg;
     }
     __syncthreads();
+    PROF_MARK(4);
     const int replaced = mi[10], newg = mi[11];
     wlen = mi[12];
     if (replaced) {
@@ -419,8 +465,10 @@ deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         }
         S.log_index[b] = lg; S.curve_len[b] = clen; S.fes[b] = fes; S.done[b] = done ? 1 : 0;
     }
+    PROF_MARK(5);
     dd_features<D>(cfg, S, b, sc, red, swin, p2, gen, stag, prow, wlen, fes, cgb, cgw, cpb, mi + 5, lb, ub,
                    feature + (size_t)b * DD_NFEAT);
+    PROF_MARK(6);
 }
 
 // =====================================================================================================
