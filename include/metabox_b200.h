@@ -48,13 +48,14 @@ extern "C" {
  * constants buffer.  BBOB constants layout at `off`:
  *     shift[D] | R[D*D] | M2[D*D] | cv0[D] | cv1[D] | cv2[D] | (Gallagher) y[P*D] | C[P*D] | w[P] | Ry[P*D] (= R y_p)
  * protein layout at `off`:
- *     coor_init[300] | basis[12*300] | inv_sqrt_eig[12] | q[100] | e4[100] (= e_i^(1/4)) | r[100]   */
+ *     coor_init[300] | basis[12*300] | inv_sqrt_eig[12] | q[100] | e4[100] (= e_i^(1/4)) | r[100] |
+ *     candidate pair list: n_peaks x uint16 (i << 8 | j), the atom pairs that can come within the 9 A cut-off   */
 typedef struct MbxInstance {
     int32_t kind;          /* MBX_KIND_*                                         */
     int32_t base;          /* BBOB base shape 1..24 (noisy ids map to their base) */
     int32_t dim;
     int32_t noise;         /* MBX_NOISE_*                                        */
-    int32_t n_peaks;       /* Gallagher: 101 / 21, else 0                        */
+    int32_t n_peaks;       /* Gallagher: 101 / 21; protein: # candidate atom pairs; else 0 */
     int32_t has_optimum;   /* 0 for protein (`optimum is None`)                  */
     int32_t fid;           /* reference function id (1..24, 101..130), 0 protein */
     int32_t pad_;

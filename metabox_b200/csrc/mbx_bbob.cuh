@@ -112,8 +112,15 @@ __device__ __forceinline__ void noise_draws(const Philox& ph, int kind, uint32_t
 #define MBX_PROT_ATOMS 100
 #define MBX_PROT_DOUBLES (300 + 12 * 300 + 12 + 300)
 #define MBX_PROT_WARP_SCRATCH 400
+// Static pair pruning: the host lists the atom pairs (i < j) that can come within the 9 A cut-off for SOME x in
+// [lb, ub]^12 (initial distance minus both atoms' maximal displacement <= 9, problem.py Protein_Docking.const_block); the
+// other pairs (46-64 % for the shipped complexes) are masked out by the reference for every in-bounds candidate, so
+// skipping them is exact.  Candidates outside the bounds (only reachable through mbx_eval) take all 4950 pairs.
+// sqrt and the two divisions by d are replaced by one rsqrt: d = d2 * rsqrt(d2), r/d = r * rsqrt(d2) (~1 ulp apart).
 template <class XA>
-__device__ double protein_energy_warp(const double* __restrict__ C, const XA& X, double* ws, int lane) {
+__device__ double protein_energy_warp(const double* __restrict__ C, const XA& X, double* ws, int lane,
+                                      const unsigned short* __restrict__ plist = nullptr, const int n_pairs = 0,
+                                      const double bound = 1.5) {
     const double* coor0 = C;
     const double* basis = C + 300;
     const double* ise = C + 300 + 3600;
@@ -121,8 +128,9 @@ __device__ double protein_energy_warp(const double* __restrict__ C, const XA& X,
     const double* e4 = q + 100;
     const double* r = e4 + 100;
     double xs[12];
+    bool inb = true;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) xs[k] = X(k) * ise[k];
+    for (int k = 0; k < 12; ++k) { const double xk = X(k); inb = inb && (fabs(xk) <= bound); xs[k] = xk * ise[k]; }
     __syncwarp();
     for (int a = lane; a < 300; a += 32) {
         double acc = 0.;
@@ -137,25 +145,37 @@ __device__ double protein_energy_warp(const double* __restrict__ C, const XA& X,
         ws[300 + a] = x * x + y * y + z * z;
     }
     __syncwarp();
+    auto pair_term = [&](const int i, const int j) -> double {
+        const double p3 = fma(ws[i], ws[j], fma(ws[100 + i], ws[100 + j], ws[200 + i] * ws[200 + j]));
+        const double d2 = ws[300 + i] - 2. * p3 + ws[300 + j] + 0.01;
+        if (!(d2 > 0.0120 && d2 < 81.001)) return 0.;             // certainly outside (0.11, 9): no sqrt needed
+        const double inv = rsqrt(d2), d = d2 * inv;
+        const bool near = (d > 0.11) && (d < 7.0);
+        const bool far = (d > 7.0) && (d < 9.0);
+        if (!(near || far)) return 0.;
+        const double rr = (r[i] + r[j]) / 2.;
+        const double t1 = rr * inv;
+        const double t2 = t1 * t1, t6 = t2 * t2 * t2;
+        const double coeff = (q[i] * q[j]) * (0.25 * inv) + (e4[i] * e4[j]) * (t6 * t6 - t6);
+        double term = 10. * coeff;
+        if (far) { const double g = 9. - d; term = term * (g * g * (-12. + 2. * d) / 8.); }
+        return term;
+    };
     double part = 0.;
+    if (inb && plist != nullptr && n_pairs > 0) {
 #pragma unroll 1
-    for (int p = lane; p < 4950; p += 32) {
-        int cidx = p / 99, t = p - cidx * 99;
-        int i, j;
-        if (t < 99 - cidx) { i = cidx; j = cidx + 1 + t; }
-        else { i = 99 - cidx; j = i + 1 + (t - (99 - cidx)); }
-        double p3 = fma(ws[i], ws[j], fma(ws[100 + i], ws[100 + j], ws[200 + i] * ws[200 + j]));
-        double d = sqrt(ws[300 + i] - 2. * p3 + ws[300 + j] + 0.01);
-        bool near = (d > 0.11) && (d < 7.0);
-        bool far = (d > 7.0) && (d < 9.0);
-        if (near || far) {
-            double rr = (r[i] + r[j]) / 2.;
-            double t1 = rr / d;
-            double t2 = t1 * t1, t6 = t2 * t2 * t2;
-            double coeff = (q[i] * q[j]) / (4. * d) + (e4[i] * e4[j]) * (t6 * t6 - t6);
-            double term = 10. * coeff;
-            if (far) { double g = 9. - d; term = term * (g * g * (-12. + 2. * d) / 8.); }
-            part += term;
+        for (int p = lane; p < n_pairs; p += 32) {
+            const unsigned int ij = __ldg(plist + p);
+            part += pair_term((int)(ij >> 8), (int)(ij & 255u));
+        }
+    } else {
+#pragma unroll 1
+        for (int p = lane; p < 4950; p += 32) {
+            int cidx = p / 99, t = p - cidx * 99;
+            int i, j;
+            if (t < 99 - cidx) { i = cidx; j = cidx + 1 + t; }
+            else { i = 99 - cidx; j = i + 1 + (t - (99 - cidx)); }
+            part += pair_term(i, j);
         }
     }
 #pragma unroll

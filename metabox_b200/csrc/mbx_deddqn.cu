@@ -90,7 +90,7 @@ __device__ __forceinline__ double dd_eval_one(const MbxInstance& h, const double
     if (KIND == MBX_KIND_PROTEIN) {
         if (threadIdx.x < 32) {
             XF32 X{x};
-            f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31);
+            f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31, reinterpret_cast<const unsigned short*>(gC + MBX_PROT_DOUBLES), h.n_peaks, h.ub);
         }
     } else {
         f = bbob_eval_cta<D, float>(h, sC, gC, x, 1, scratch, nullptr, nullptr, 0);

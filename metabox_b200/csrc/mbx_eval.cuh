@@ -45,8 +45,9 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
         for (int i = w; i < n; i += (MBX_NT >> 5)) {
             if (only_mask && !only_mask[i]) continue;
             double e;
-            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l); }
-            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l); }
+            const unsigned short* plist = reinterpret_cast<const unsigned short*>(gC + MBX_PROT_DOUBLES);   // candidate pair list
+            if (sizeof(TX) == 4) { XF32 X{reinterpret_cast<const float*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l, plist, h.n_peaks, h.ub); }
+            else { XF64 X{reinterpret_cast<const double*>(tile) + i * D}; e = protein_energy_warp(sC, X, ws, l, plist, h.n_peaks, h.ub); }
             if (l == 0) out[i] = (TO)e;
         }
     } else {

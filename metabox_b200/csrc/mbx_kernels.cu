@@ -130,7 +130,7 @@ random_search_kernel(const MbxInstance* __restrict__ inst, const double* __restr
                 if (threadIdx.x == 0 && clen < MBX_CURVE_LEN) mycurve[clen] = gbest;
                 clen = min(clen + 1, MBX_CURVE_LEN);
             }
-            done = h.has_optimum ? (gbest <= 1e-8f || fes >= cfg.maxFEs) : (fes >= cfg.maxFEs);
+            done = h.has_optimum ? ((double)gbest <= 1e-8 || fes >= cfg.maxFEs) : (fes >= cfg.maxFEs);
             if (done) {                                  // random_search.py:52-57
                 if (clen >= cfg.n_logpoint + 1) { if (threadIdx.x == 0) mycurve[clen - 1] = gbest; }
                 else { if (threadIdx.x == 0) mycurve[clen] = gbest; clen += 1; }

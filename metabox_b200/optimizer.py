@@ -213,7 +213,7 @@ class Random_search(Basic_Optimizer):
     def __init__(self, config):
         super().__init__(config)
         self.__config = config
-        self.__NP = 100
+        self.__NP = int(getattr(config, 'rs_NP', 100))            # the reference hard-codes 100 (random_search.py:13)
         self.log_interval = config.log_interval
         self.cost, self.log_index = None, None
 

@@ -263,12 +263,29 @@ class Protein_Docking(Basic_Problem):
         # the shipped epsilons are all negative, so e_i e_j > 0 (mixed signs would be NaN in the reference too)
         if not (np.all(self.e_vec >= 0) or np.all(self.e_vec <= 0)):
             raise ValueError('protein epsilons of mixed sign: sqrt(e_i*e_j) is undefined')
-        return np.concatenate([self.coor_init.reshape(-1), self.basis.reshape(-1), 1.0 / np.sqrt(self.eigval),
-                               self.q_vec, np.sqrt(np.sqrt(np.abs(self.e_vec))), self.r_vec])
+        blk = np.concatenate([self.coor_init.reshape(-1), self.basis.reshape(-1), 1.0 / np.sqrt(self.eigval),
+                              self.q_vec, np.sqrt(np.sqrt(np.abs(self.e_vec))), self.r_vec])
+        pairs = self.candidate_pairs()
+        lst = np.zeros((len(pairs) + 3) // 4 * 4, dtype=np.uint16)
+        lst[:len(pairs)] = (pairs[:, 0].astype(np.uint16) << 8) | pairs[:, 1].astype(np.uint16)
+        return np.concatenate([blk, lst.view(np.float64)])
+
+    def candidate_pairs(self):
+        """Atom pairs (i < j) that can come within the 9 A cut-off of protein_docking.py:36-37 for SOME x in [lb, ub]^12:
+        initial distance minus the maximal displacement of both atoms (sum_k ub / sqrt(eig_k) * |basis_k,atom|) <= 9.  For
+        every in-bounds candidate the reference masks the other pairs out, so the kernel may skip them (exactly)."""
+        c = self.coor_init.reshape(self.n_atoms, 3)
+        B = self.basis.reshape(self.dim, self.n_atoms, 3)
+        disp = np.sum(max(abs(self.lb), abs(self.ub)) / np.sqrt(self.eigval)[:, None] * np.linalg.norm(B, axis=2), axis=0)
+        d0 = np.linalg.norm(c[:, None, :] - c[None, :, :], axis=2)
+        i, j = np.triu_indices(self.n_atoms, 1)
+        keep = d0[i, j] - disp[i] - disp[j] <= 9.0 + 1e-6
+        return np.stack([i[keep], j[keep]], axis=1)
 
     def header(self, off):
         h = np.zeros((), dtype=_lib.INSTANCE_DTYPE)
         h['kind'], h['dim'], h['lb'], h['ub'], h['off'] = self.kind, self.dim, self.lb, self.ub, off
+        h['n_peaks'] = len(self.candidate_pairs())                # protein: number of candidate pairs after the block
         return h
 
     def func(self, x, seed=0, gen=0):

@@ -140,3 +140,26 @@ def test_problem_object_api_and_edge_cases():
     assert big.shape == (1, 1000) and np.all(np.isfinite(big))
     one = np.stack([p.eval(r) for r in np.random.RandomState(0).uniform(-5, 5, size=(1000, 10))[:5]])
     np.testing.assert_array_equal(one, big[0, :5])
+
+
+def test_protein_in_bounds_pair_pruning_and_out_of_bounds_fallback():
+    """In-bounds candidates use the host's candidate-pair list (pairs that can never come within the 9 A cut-off are
+    skipped, exactly); candidates outside [-1.5, 1.5]^12 (reachable through mbx_eval only) take all 4950 pairs.  Both vs
+    the oracle's dense [100,100] evaluation."""
+    from metabox_b200 import problem as mp
+    from oracle import protein as op
+    G = np.load(os.path.join(GOLDEN, 'protein.npz'))
+    ids = [str(p) for p in G['ids']]
+    args = lambda p: [G[f'{k}_{p}'] for k in ('coor_init', 'q', 'e', 'r', 'basis', 'eigval')]
+    probs = [mp.Protein_Docking(*args(p), p) for p in ids]
+    pack = mp.InstancePack(probs)
+    n_pairs = [len(P.candidate_pairs()) for P in probs]
+    assert all(0 < n < 4950 for n in n_pairs), n_pairs                      # the list really prunes
+    g = np.random.RandomState(9)
+    Xin = g.uniform(-1.5, 1.5, (len(ids), 24, 12)); Xin[:, 0] = 1.5; Xin[:, 1] = -1.5     # incl. the corners of the box
+    Xout = g.uniform(-4.0, 4.0, (len(ids), 24, 12)); Xout[:, 0, 3] = 1.5000001
+    for X in (Xin, Xout):
+        E = pack.eval_lanes(np.arange(len(ids)), X)
+        for k, p in enumerate(ids):
+            I = op.ProteinInstance(p, *args(p))
+            np.testing.assert_allclose(E[k], op.energy(I, X[k]), rtol=1e-9, atol=1e-9, err_msg=p)

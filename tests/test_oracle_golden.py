@@ -246,6 +246,20 @@ def test_deddqn_steps_match_reference():
     assert n_total >= 900 and n_gen2 >= 100 and n_evict >= 300 and n_done >= 1
 
 
+# ----------------------------------------------------------------------------------------- Random_search
+def test_random_search_episodes_match_reference():
+    """`Random_search.run_episode` of the reference (float32 storage contract, np.random.seed(5)) vs the oracle replaying the
+    same draws, incl. a noisy function (draw order: positions, then the noise model's draws inside problem.eval)."""
+    from oracle import random_search as ors
+    G = load('rs.npz')
+    for fid, dim in ((1, 10), (15, 10), (8, 30), (102, 10)):
+        I, ev, optimum, lb, ub, nc = _problem_for(str(fid), dim)
+        np.random.seed(5)
+        r = ors.run_episode(dim, 2000 * dim, 50, 2000 * dim // 50, ev, optimum, lb, ub, ors.NumpyTape(100, dim, nc))
+        assert r['fes'] == int(G[f'f32/{fid}_{dim}/fes'])
+        np.testing.assert_allclose(np.array(r['cost'], dtype=np.float64), G[f'f32/{fid}_{dim}/cost'], rtol=1e-6, atol=1e-10)
+
+
 # ----------------------------------------------------------------------------------------- GLEET
 def _gleet_state_from(G, pre):
     from oracle import gleet as og
