@@ -350,7 +350,8 @@ def main():
                          'timed': 'separate instrumented (eager, unstriped) sweep of the same workload right after the timed region; '
                                   'kernel_share_of_step = step-kernel time / duration of that sweep',
                          'note': f'algorithmic bytes = {W["bytes_per_eval"]} B/eval x evals charged by the step launches; see DESIGN.md section 4 '
-                                 'for what actually bounds the kernel (FP64 ALU / latency, not HBM)'},
+                                 'for what actually bounds the kernel (instruction issue: 62 % of issue slots busy, DRAM 4.5 % in the ncu capture '
+                                 'profiles/r1e_ncu_rlepso_step_d30.txt; not HBM)'},
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches), 'clocks': clk,
         }
