@@ -35,6 +35,8 @@ WORKLOADS = {
                 desc='LDE rollouts, BBOB-noisy 30 fns'),
     'deddqn': dict(suit='bbob', subset='difficult-test', NP=100, bytes_per_eval=32 * DIM + 404,
                    kernel='deddqn_step_kernel<30,BBOB>', desc='DE-DDQN rollouts, BBOB difficult test set 18 fns'),
+    'gleet': dict(suit='bbob', subset='all', NP=100, bytes_per_eval=24 * DIM + 204, kernel='gleet_step_kernel<30,BBOB>',
+                  desc='GLEET backbone rollouts (stand-in per-particle MLP policy 27->64->1), BBOB 24 fns'),
 }
 METRIC = 'candidate evals/sec on BBOB dim=30 pop=100'
 
@@ -46,7 +48,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
-                    help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3')
+                    help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3; '
+                         'gleet = the GLEET backbone (SURVEY 8f N1) with a stand-in policy')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -110,7 +113,7 @@ def policy_weights(workload):
     """Shipped policies (extracted from the reference pickles into tests/golden/agents.npz).  The shipped LDE policy
     only fits NP = 50 (lde_agent.py:37); the NP = 100 workload uses a randomly initialised policy of the right width."""
     p = os.path.join(ROOT, 'tests', 'golden', 'agents.npz')
-    if workload == 'lde' or not os.path.exists(p):
+    if workload in ('lde', 'gleet') or not os.path.exists(p):
         return None, 'random init (seed 0)'
     G = np.load(p)
     pre = workload + '/'
@@ -174,6 +177,11 @@ def build_policy(workload, dev, NP):
     import torch
     from metabox_b200 import agent as magent
     torch.manual_seed(0)
+    if workload == 'gleet':
+        # the reference's GLEET actor is an attention network (out of scope); any torch callable state[B,NP,27] -> action[B,NP]
+        # plugs in -- the bench uses a small per-particle MLP with a sigmoid head
+        net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(1))
+        return net.to(dev).eval(), 'stand-in per-particle MLP 27->64->1 (random init, seed 0)'
     net = {'rlepso': magent.RLEPSO_Actor, 'deddqn': magent.DE_DDQN_Net}[workload]() if workload != 'lde' else magent.LDE_PolicyNet(NP=NP)
     w_np, wsrc = policy_weights(workload)
     if w_np:
@@ -189,6 +197,8 @@ def make_sweep(workload, pack, lanes, net, seed, lane_base, NP, stripes=1, **kw)
         return msweep.RLEPSO_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
     if workload == 'lde':
         return msweep.LDE_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, NP=NP, **kw)
+    if workload == 'gleet':
+        return msweep.GLEET_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
     return msweep.DE_DDQN_Sweep(pack, lanes, net, MAXFES, 50, seed=seed, lane_base=lane_base, **kw)
 
 
@@ -332,6 +342,7 @@ def main():
         except Exception:
             pass
         state_mb = {'rlepso': n_local * (3 * NP * DIM + 3 * NP) * 4, 'lde': n_local * (NP * DIM + NP) * 4,
+                    'gleet': n_local * (3 * NP * DIM + 3 * NP + 9 * NP) * 4,
                     'deddqn': n_local * ((NP * DIM + NP) * 4 + 8800)}[args.workload] / 1e6
         out = {
             'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world,

@@ -78,7 +78,28 @@ def deddqn_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoi
     return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes - fes0, ret=R, gens=steps, seconds=time.perf_counter() - t0)
 
 
-ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout}
+def gleet_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One GLEET-backbone rollout with bench.py's stand-in policy (per-particle MLP 27 -> 64 -> 1, sigmoid; seed 0)."""
+    from . import gleet as og
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(0))
+    np.random.seed(run_seed)
+    cfg = og.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    t0 = time.perf_counter()
+    S, state = og.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, og.NumpyTape(cfg.NP, dim, nc))
+    R, gens, done = 0., 0, False
+    with torch.no_grad():
+        while not done and (max_gens is None or gens < max_gens):
+            action = net(torch.as_tensor(state, dtype=torch.float32)).numpy()
+            S, state, reward, done = og.update(cfg, S, action, ev, inst.optimum, inst.lb, inst.ub, og.NumpyTape(cfg.NP, dim, nc))
+            R += float(reward)
+            gens += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=gens, seconds=time.perf_counter() - t0)
+
+
+ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout, 'gleet': gleet_rollout}
 
 
 _SUITES = {}
