@@ -157,7 +157,9 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
         }
         sc.visit(acc2.x + acc2.y, lw, coef32, K1, p);
     };
-    if (tile == nullptr) {
+    int TP = tile != nullptr ? tile_bytes / (16 * HD + 4) : 0;     // peaks per staged tile; a tile too small for one peak is not used
+    if (TP * HD > 2 * (int)blockDim.x) TP = 2 * (int)blockDim.x / HD;                // two prefetch registers per thread
+    if (TP < 1) {
         if (act) {
 #pragma unroll 1
             for (int p = g; p < P; p += GP) {
@@ -172,8 +174,6 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
             }
         }
     } else {
-        int TP = tile_bytes / (16 * HD + 4);
-        if (TP * HD > 2 * NT) TP = 2 * NT / HD;                  // two prefetch registers per thread
         float* tl = reinterpret_cast<float*>(tile + TP * HD);
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         float rl = 0.f;
