@@ -329,3 +329,59 @@ def test_landscape_features_match_reference():
         if b >= 0 and abs(f[5] - 0.5) > 1e-9:
             assert int(0.5 <= f[5] <= 1) == b, key; n_bool += 1             # :212-217
     assert n_bool >= 40
+
+
+# ----------------------------------------------------------------------------------------- RL_PSO
+def _rlpso_s0(G, key):
+    from oracle import rl_pso as orp
+    pre = f'{key}/s0/'
+    return orp.State(x=G[pre + 'x'], v=G[pre + 'v'], pbest_x=G[pre + 'pbest_x'], c_cost=G[pre + 'c_cost'], pbest=G[pre + 'pbest'],
+                     gbest_x=G[pre + 'gbest_x'], gbest_val=np.float32(G[pre + 'gbest_val']), gbest_idx=int(G[pre + 'gbest_idx']), w=0.9,
+                     max_cost=np.float32(G[pre + 'max_cost']), cur_index=0, fes=len(G[pre + 'c_cost']), log_index=1,
+                     curve=[np.float32(G[pre + 'gbest_val'])])
+
+
+def _rlpso_cmp_step(N, state, reward, done, G, key, t, tag):
+    j = (t - 1) % len(N.c_cost)
+    k = t - 1
+    np.testing.assert_array_equal(N.x[j], G[f'{key}/row_x'][k], err_msg=f'{tag} x row')
+    np.testing.assert_array_equal(N.v[j], G[f'{key}/row_v'][k], err_msg=f'{tag} v row')
+    np.testing.assert_array_equal(N.pbest_x[j], G[f'{key}/row_pbest_x'][k], err_msg=f'{tag} pbest_x row')
+    np.testing.assert_array_equal(N.gbest_x, G[f'{key}/gbest_x'][k], err_msg=f'{tag} gbest_x')
+    np.testing.assert_allclose(N.c_cost[j], G[f'{key}/row_c_cost'][k], rtol=1e-6, atol=1e-10, err_msg=f'{tag} cost')
+    np.testing.assert_allclose(N.pbest[j], G[f'{key}/row_pbest'][k], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(float(N.gbest_val), G[f'{key}/gbest_val'][k], rtol=1e-6, atol=1e-10)
+    assert N.gbest_idx == int(G[f'{key}/gbest_idx'][k]) and N.w == float(G[f'{key}/w'][k]), tag
+    assert N.fes == int(G[f'{key}/fes'][k]) and N.log_index == int(G[f'{key}/log_index'][k]) and len(N.curve) == int(G[f'{key}/curve_len'][k]), tag
+    np.testing.assert_allclose(float(N.curve[-1]), G[f'{key}/curve_last'][k], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(state, G[f'{key}/state'][k], rtol=1e-6, atol=1e-7, err_msg=f'{tag} state')
+    np.testing.assert_allclose(reward, G[f'{key}/reward'][k], rtol=2e-5, atol=1e-9, err_msg=f'{tag} reward')
+    assert done == bool(G[f'{key}/done'][k]), tag
+
+
+def test_rl_pso_steps_match_reference():
+    """230 consecutive single-particle steps of the real RL_PSO_Optimizer per case (float32 storage contract, seeded
+    np.random) vs the oracle replaying the same draws: the updated row, gbest and the inertia chain bit-exact."""
+    from oracle import rl_pso as orp
+    G = load('rl_pso.npz')
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = orp.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, state = orp.init_population(cfg, ev, optimum, lb, ub, orp.NumpyTape(cfg.NP, dim, nc))
+        S0 = _rlpso_s0(G, key)
+        for k in ('x', 'v', 'pbest_x', 'gbest_x'):
+            np.testing.assert_array_equal(getattr(S, k), getattr(S0, k), err_msg=f'{key} init {k}')
+        np.testing.assert_allclose(S.c_cost, S0.c_cost, rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(float(S.max_cost), float(S0.max_cost), rtol=1e-6)
+        np.testing.assert_allclose(state, G[f'{key}/s0/state'], rtol=1e-6, atol=1e-7)
+        S = S0                                                       # carry the reference's (float32) costs forward
+        for t in range(1, int(G['n_steps']) + 1):
+            np.random.seed(int(G[f'{key}/seed'][t - 1]))
+            S, state, reward, done = orp.update(cfg, S, G[f'{key}/action'][t - 1], ev, optimum, lb, ub, orp.NumpyTape(cfg.NP, dim, nc))
+            _rlpso_cmp_step(S, state, reward, done, G, key, t, f'{key} step {t}')
+            # teacher forcing of the float32 costs (the reference's value may differ in the last float32 bit)
+            j = (t - 1) % cfg.NP
+            S.c_cost[j] = G[f'{key}/row_c_cost'][t - 1]; S.pbest[j] = G[f'{key}/row_pbest'][t - 1]
+            S.gbest_val = np.float32(G[f'{key}/gbest_val'][t - 1])
