@@ -256,6 +256,39 @@ int mbx_gleet_step(const MbxInstance* d_inst, const double* d_consts, const int3
                    float* d_state, float* d_reward, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * RL_PSO backbone (PSO family, ONE particle per step, scalar action) -- replaces RL_PSO_Optimizer.init_population /
+ * update / __get_state (optimizer/rl_pso_optimizer.py:32-62, 79-148, 64-65) for B lanes at once; fixed configuration
+ * NP = 100, c = 2.05, w = 0.9 decaying by 0.5 / (maxFEs / NP) per step (:10-24).  State (device, updated in place):
+ *   x, v, pbest_x [B,NP,D] f32 ; c_cost, pbest [B,NP] f32 ; gbest_x [B,D] f32 ; gbest_val, max_cost [B] f32 (max_cost =
+ *   max of the initial costs, :44) ; w [B] f64 ; gbest_idx, cur_index, fes, log_index, curve_len [B] i32 ;
+ *   curve [B, MBX_CURVE_LEN] f32 ; done [B] u8                                                                   */
+typedef struct MbxRlPsoState {
+    float *x, *v, *pbest_x, *c_cost, *pbest;
+    float *gbest_x, *gbest_val, *max_cost;
+    double* w;
+    int32_t *gbest_idx, *cur_index, *fes, *log_index, *curve_len;
+    float* curve;
+    uint8_t* done;
+} MbxRlPsoState;
+
+/* Recorded draws (device, float64; null when use_tape=0): init_pos_u, init_vel_u [B,NP,D] ; rand1 [B] (this step's
+ * np.random.rand()) ; noise [B,3,n] with n = NP for init and n = 1 for a step.                                       */
+typedef struct MbxRlPsoTape {
+    const double *init_pos_u, *init_vel_u, *rand1, *noise;
+} MbxRlPsoTape;
+
+/* d_state [B, 2D] f32 = gbest_position | current_position[cur_index] (:64-65) */
+int mbx_rl_pso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxRlPsoState* st, const MbxRlPsoTape* tape, float* d_state, int B,
+                    void* stream);
+
+/* d_action [B] f32 (the reference feeds it unclamped as rand2) ; outputs d_state [B,2D] f32 (of the NEXT particle),
+ * d_reward [B] f32 ((cost_before - cost_after) / (max_cost - gbest)), st->done.  Finished lanes: reward = 0.         */
+int mbx_rl_pso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
+                    const MbxRunConfig* cfg, const MbxRlPsoState* st, const MbxRlPsoTape* tape, const float* d_action,
+                    float* d_state, float* d_reward, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Landscape features of sampled walks -- replaces cal_fdc / cal_rie / cal_acf / cal_nop
  * (optimizer/dedqn_optimizer.py:8-76) and the DFDC / DRIE statistics of RL_HPSDE
  * (optimizer/rl_hpsde_optimizer.py:169-216) for B walks at once.

@@ -78,6 +78,15 @@ class MbxGleetTape(C.Structure):
     _fields_ = [(n, _P) for n in ('init_pos_u', 'init_vel_u', 'rand1', 'rand2', 'noise')]
 
 
+class MbxRlPsoState(C.Structure):
+    _fields_ = [(n, _P) for n in ('x', 'v', 'pbest_x', 'c_cost', 'pbest', 'gbest_x', 'gbest_val', 'max_cost', 'w', 'gbest_idx',
+                                  'cur_index', 'fes', 'log_index', 'curve_len', 'curve', 'done')]
+
+
+class MbxRlPsoTape(C.Structure):
+    _fields_ = [(n, _P) for n in ('init_pos_u', 'init_vel_u', 'rand1', 'noise')]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/metabox_b200.h declares
@@ -104,6 +113,10 @@ SIGNATURES = {
                                  C.c_int, _P]),
     'mbx_gleet_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxGleetState), C.POINTER(MbxGleetTape), _P,
                                  _P, _P, C.c_int, _P]),
+    'mbx_rl_pso_init': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxRlPsoState), C.POINTER(MbxRlPsoTape), _P,
+                                  C.c_int, _P]),
+    'mbx_rl_pso_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxRlPsoState), C.POINTER(MbxRlPsoTape), _P,
+                                  _P, _P, C.c_int, _P]),
     'mbx_landscape_features': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }

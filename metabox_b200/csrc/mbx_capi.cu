@@ -167,4 +167,27 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
     return mbx_launch_landscape(d_sample, d_cost, d_ref, B, S, D, d_out, (cudaStream_t)stream);
 }
 
+
+int mbx_rl_pso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxRlPsoState* st, const MbxRlPsoTape* tape, float* d_state, int B, void* stream) {
+    int rc = check_cfg("mbx_rl_pso_init", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_state, "mbx_rl_pso_init: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_pos_u && tape->init_vel_u), "mbx_rl_pso_init: use_tape without tape");
+    return mbx_launch_rl_pso_init(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_state, B, (cudaStream_t)stream);
+}
+
+int mbx_rl_pso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                    const MbxRlPsoState* st, const MbxRlPsoTape* tape, const float* d_action, float* d_state, float* d_reward,
+                    int B, void* stream) {
+    int rc = check_cfg("mbx_rl_pso_step", cfg, B);
+    if (rc) return rc;
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_action && d_state && d_reward, "mbx_rl_pso_step: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->rand1), "mbx_rl_pso_step: use_tape without tape");
+    return mbx_launch_rl_pso_step(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_action, d_state, d_reward, B,
+                                  (cudaStream_t)stream);
+}
+
 }  // extern "C"

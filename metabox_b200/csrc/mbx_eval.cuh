@@ -71,6 +71,34 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
     }
 }
 
+// fitness of ONE candidate (float32 tile `x`), noise applied.  ALL threads of the CTA call: the BBOB path is the
+// CTA-cooperative evaluator (the D dimensions of the single trial are spread over D threads, mbx_bbob_cta.cuh), the
+// protein path uses warp 0.  The result is valid in thread 0.
+template <int D, int KIND>
+__device__ __forceinline__ double cta_eval_one(const MbxInstance& h, const double* sC, const double* gC, const float* x,
+                                              double* scratch, const Philox& ph, uint32_t idx, uint32_t gen, uint32_t lane,
+                                              const double* noise_tape, int tape_stride) {
+    double f = 0.;
+    if (KIND == MBX_KIND_PROTEIN) {
+        if (threadIdx.x < 32) {
+            XF32 X{x};
+            f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31, reinterpret_cast<const unsigned short*>(gC + MBX_PROT_DOUBLES), h.n_peaks, h.ub);
+        }
+    } else {
+        f = bbob_eval_cta<D, float>(h, sC, gC, x, 1, scratch, nullptr, nullptr, 0);
+        if (threadIdx.x == 0) {
+            if (h.noise != MBX_NOISE_NONE) {
+                double d0, d1, d2;
+                if (noise_tape) { d0 = noise_tape[0]; d1 = noise_tape[tape_stride]; d2 = noise_tape[2 * tape_stride]; }
+                else noise_draws(ph, h.noise, idx, gen, lane, MBX_TAG_NOISE, d0, d1, d2);
+                f = bbob_noise(h, f, d0, d1, d2);
+            }
+            if (h.has_optimum) f = f - h.optimum;
+        }
+    }
+    return f;
+}
+
 // =====================================================================================================
 // shared-memory plan of the population kernels
 // =====================================================================================================

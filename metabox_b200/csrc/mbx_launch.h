@@ -46,3 +46,9 @@ int mbx_launch_gleet_step(int kind, const MbxInstance* inst, const double* const
                           float* state, float* reward, int B, cudaStream_t st);
 int mbx_launch_landscape(const double* sample, const double* cost, const double* ref, int B, int S, int D, double* out,
                          cudaStream_t st);
+int mbx_launch_rl_pso_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlPsoState* s, const MbxRlPsoTape* tape, float* state, int B,
+                           cudaStream_t st);
+int mbx_launch_rl_pso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                           const MbxRunConfig* cfg, const MbxRlPsoState* s, const MbxRlPsoTape* tape, const float* action,
+                           float* state, float* reward, int B, cudaStream_t st);

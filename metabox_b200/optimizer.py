@@ -616,3 +616,117 @@ class GLEET_Optimizer(Learnable_Optimizer):
         state, reward, done = self._engine.update(a.to(self._engine.device))
         self._sync()
         return state[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())
+
+
+# ======================================================================================== RL_PSO
+class RL_PSO_Engine:
+    """B lanes of the RL_PSO backbone (rl_pso_optimizer.py:32-148) on one GPU: one particle per step.  `feature` is the
+    [B, 2D] state (gbest_position | current_position of the next particle); the action is [B] float32."""
+    NP = 100
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None, lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)
+        self.NP = int(NP or RL_PSO_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.x, self.v, self.pbest_x = z(B, NPn, D), z(B, NPn, D), z(B, NPn, D)
+        self.c_cost, self.pbest = z(B, NPn), z(B, NPn)
+        self.gbest_x, self.gbest_val, self.max_cost = z(B, D), z(B), z(B)
+        self.w = z(B, dt=torch.float64)
+        self.gbest_idx, self.cur_index, self.fes, self.log_index, self.curve_len = (z(B, dt=i32) for _ in range(5))
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, 2 * D), z(B)
+        self._state = _lib.MbxRlPsoState(*[t.data_ptr() for t in (
+            self.x, self.v, self.pbest_x, self.c_cost, self.pbest, self.gbest_x, self.gbest_val, self.max_cost, self.w,
+            self.gbest_idx, self.cur_index, self.fes, self.log_index, self.curve_len, self.curve, self.done)])
+
+    def _cfg(self, use_tape):
+        return _run_config(self.pack.kind, self.NP, self.dim, self.maxFEs, self.n_logpoint, self.log_interval, use_tape,
+                           self.seed, self.lane_base)
+
+    def init_population(self, tape=None):
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxRlPsoTape, tape, self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_rl_pso_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                            _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rl_pso_init')
+        return self.feature
+
+    def update(self, action, tape=None):
+        """action [B] (or [B,1]) float32 device tensor -> (state [B,2D], reward [B], done [B] uint8), all on device."""
+        import torch
+        action = action.reshape(-1)
+        if action.shape[0] != self.B:
+            raise ValueError(f'RL_PSO action must have one value per lane ({self.B}), got {tuple(action.shape)}')
+        if action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxRlPsoTape, tape, self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_rl_pso_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                            C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(action),
+                                            _lib.ptr(self.feature), _lib.ptr(self.reward), self.B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rl_pso_step')
+        return self.feature, self.reward, self.done
+
+    cost_curves = RLEPSO_Engine.cost_curves
+    load_state = RLEPSO_Engine.load_state
+
+    def read_state(self, b):
+        keys = ('x', 'v', 'pbest_x', 'c_cost', 'pbest', 'gbest_x', 'gbest_val', 'gbest_idx', 'max_cost', 'w', 'cur_index', 'fes',
+                'log_index', 'curve_len', 'curve', 'done')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class RL_PSO_Optimizer(Learnable_Optimizer):
+    """Drop-in for `RL_PSO_Optimizer` (rl_pso_optimizer.py:6-148): one problem, numpy in / numpy out."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        config.w_decay = True
+        config.c = 2.05
+        config.NP = 100
+        self.__config = config
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self._engine = None
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = RL_PSO_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, cfg.NP)
+        state = self._engine.init_population()
+        self._sync()
+        return state[0].cpu().numpy().astype(np.float64)
+
+    def _sync(self):
+        e = self._engine
+        self.fes = int(e.fes[0].item())
+        self.log_index = int(e.log_index[0].item())
+        self.cost = e.cost_curves(pad=False)[0]
+
+    def update(self, action, problem):
+        import torch
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1))
+        state, reward, done = self._engine.update(a.to(self._engine.device))
+        self._sync()
+        return state[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .optimizer import DE_DDQN_Engine, GLEET_Engine, LDE_Engine, RLEPSO_Engine
+from .optimizer import DE_DDQN_Engine, GLEET_Engine, LDE_Engine, RL_PSO_Engine, RLEPSO_Engine
 
 
 def lane_table(n_instances, n_runs):
@@ -220,6 +220,19 @@ class GLEET_Sweep(_Sweep):
 
     def _policy(self, feat):
         return self.policy(feat)
+
+
+class RL_PSO_Sweep(_Sweep):
+    """RL_PSO_Agent.rollout_episode (rl_pso_agent.py:116-124): `policy(state [B,2D]) -> action [B]`, one FE per step."""
+
+    def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=500, time_kernels=False,
+                 graph=True, steps_per_graph=10):
+        eng = RL_PSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
+        self.policy = policy
+
+    def _policy(self, feat):
+        return self.policy(feat).reshape(-1)
 
 
 class StripedSweep:
