@@ -53,11 +53,14 @@ def parse():
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--stripes', type=int, default=3, help='independent lane stripes per GPU, each on its own CUDA stream + graph')
+    ap.add_argument('--stripes', type=int, default=None,
+                    help='independent lane stripes per GPU, each on its own CUDA stream + graph (default 3; deddqn 6)')
     ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
     if a.runs is None:
         a.runs = 256                                  # C3: 256 runs in lockstep
+    if a.stripes is None:
+        a.stripes = 6 if a.workload == 'deddqn' else 3       # the 1-FE-per-step chain is latency bound: more chains in flight
     if a.cpu_gens is None:
         a.cpu_gens = 3000 if a.workload == 'deddqn' else 100
     return a
