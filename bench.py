@@ -55,12 +55,17 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--stripes', type=int, default=None,
                     help='independent lane stripes per GPU, each on its own CUDA stream + graph (default 3; deddqn 6)')
+    ap.add_argument('--lane-order', default=None, choices=['instance-major', 'run-major', 'stripe-balanced'],
+                    help='order of the (instance, run) lanes inside a GPU (default: instance-major; lde: stripe-balanced = every '
+                         'stripe gets ~runs/stripes runs of every function, instance-major inside)')
     ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
     if a.runs is None:
         a.runs = 256                                  # C3: 256 runs in lockstep
     if a.stripes is None:
         a.stripes = 6 if a.workload == 'deddqn' else 3       # the 1-FE-per-step chain is latency bound: more chains in flight
+    if a.lane_order is None:
+        a.lane_order = 'stripe-balanced' if a.workload == 'lde' else 'instance-major'     # measured: profiles/, DESIGN.md section 6
     if a.cpu_gens is None:
         a.cpu_gens = 3000 if a.workload == 'deddqn' else 100
     return a
@@ -238,6 +243,11 @@ def main():
     pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
     net, wsrc = build_policy(args.workload, dev, NP)
     inst, run = msweep.lane_table(len(problems), args.runs)
+    if args.lane_order == 'run-major':                        # every contiguous stripe / rank sees the same mix of functions
+        inst = np.ascontiguousarray(inst.reshape(len(problems), args.runs).T.reshape(-1))
+    elif args.lane_order == 'stripe-balanced':                # every stripe gets ~runs/stripes runs of EVERY function, instance-major
+        parts = [np.array_split(np.arange(args.runs), args.stripes) for _ in problems]          # inside (constants stay L1/L2-hot)
+        inst = np.concatenate([np.full(len(parts[k][s_]), k, dtype=np.int32) for s_ in range(args.stripes) for k in range(len(problems))])
     n_local = len(inst)
     lane_base = rank * n_local                                # weak scaling: every rank gets its own n_fns x runs lanes
     seed = 20261017
@@ -353,7 +363,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': f'{W["desc"]} x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
                                    'one step = one complete sweep (init + all generations + all-gather)',
-                       'lanes_per_gpu': n_local, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
+                       'lanes_per_gpu': n_local, 'lane_order': args.lane_order, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
                        'launch': 'eager' if args.no_graph else f'policy forward + fused step replayed from one CUDA graph per step; {args.stripes} lane stripe(s) on separate streams',
                        'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
                        'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
