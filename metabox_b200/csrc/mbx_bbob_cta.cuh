@@ -44,7 +44,9 @@ __device__ __forceinline__ void matvec_cta(const double* __restrict__ M, double*
 #pragma unroll
             for (int j = 0; j < TI; ++j) yr[j] = B + min(it * TI + j, n - 1) * ZS;
             const double* mr = M + kt * TK * D;
-#pragma unroll 2
+            // one output per thread (single candidate; M may live in global memory): all D operand loads in flight at once
+            constexpr int UNR = (TI * TK == 1) ? D : 2;
+#pragma unroll UNR
             for (int d = 0; d < D; ++d) {
                 double yv[TI], mv[TK];
 #pragma unroll

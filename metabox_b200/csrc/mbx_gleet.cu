@@ -21,7 +21,7 @@ struct GlLayout {
     __host__ __device__ GlLayout(int np, int D, int kConst, int scratchDoubles) {
         NP = np; NPp = (np + 3) & ~3;
         size_t scr = (size_t)scratchDoubles;
-        const size_t pbd = ((size_t)NPp * D * sizeof(float) + 7) / 8;
+        const size_t pbd = ((size_t)NPp * (D + 27) * sizeof(float) + 7) / 8;   // pbest_x + the [NP, 27] state staging of P4
         if (pbd > scr) scr = pbd;
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
         oA = oConst + sizeof(double) * kConst;               // pbest_x f32 [NP*D]  /  eval scratch f64
@@ -284,11 +284,13 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     // ---- P4: observe + carried features -> state [NP, 27]  (:128-158, :297-300) --------------------------------------------------
     const double mc = (double)S.max_cost[b];
     float* out = state + pb * 3 * GL_NFEAT;
+    // the [NP, 27] state is assembled in shared memory (second half of region A, free here) and written out coalesced
+    float* stage = V.pbx + (size_t)L.NPp * D;
     if (tid < NP) {
         const int i = tid;
         double f[GL_NFEAT];
         gl_observe<D>(cfg, V.xs, V.pbx, V.gx, i, (double)V.cc[i], (double)V.pf32[i], (double)gbest, mc, V.pni[i], no_improve, fes, lb, ub, f);
-        float* o = out + i * 3 * GL_NFEAT;
+        float* o = stage + i * 3 * GL_NFEAT;
         float* pfeat = S.pbest_feature + (pb + i) * GL_NFEAT;
         const bool fresh = V.pni[i] == 0;                          // exploration state follows the particle while it improves
 #pragma unroll
@@ -307,9 +309,9 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     }
     if (no_improve != 0 && tid < GL_NFEAT) V.gf[tid] = S.gbest_feature[(size_t)b * GL_NFEAT + tid];
     __syncthreads();
-    if (tid < NP) {
-#pragma unroll
-        for (int k = 0; k < GL_NFEAT; ++k) out[tid * 3 * GL_NFEAT + 2 * GL_NFEAT + k] = V.gf[k];
+    for (int e = tid; e < NP * 3 * GL_NFEAT; e += MBX_NT) {
+        const int k = e % (3 * GL_NFEAT);
+        out[e] = (k >= 2 * GL_NFEAT) ? V.gf[k - 2 * GL_NFEAT] : stage[e];
     }
     // ---- P5: bookkeeping (:277-312) --------------------------------------------------------------------------------------------
     if (tid == 0) {
