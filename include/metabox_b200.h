@@ -289,6 +289,39 @@ int mbx_rl_pso_step(const MbxInstance* d_inst, const double* d_consts, const int
                     float* d_state, float* d_reward, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * QLPSO backbone (PSO family, ONE particle per step; the integer action 0..3 selects a ring neighbourhood of 4 / 8 / 16 /
+ * 30 particles) -- replaces QLPSO_Optimizer.init_population / update (optimizer/qlpso_optimizer.py:74-89, 91-126) for B
+ * lanes at once; fixed configuration NP = 30, C = 1.49618, W = 0.729844 (:22-25); NP <= 128.  State (device, in place):
+ *   x, v, pbest_x [B,NP,D] f32 ; cost [B,NP] f32 (current costs) ; gbest_cost [B] f32 ; diversity [B] f64 (mean distance
+ *   to the centroid, numpy reduction order, :45-46) ; q_state [B,NP] i32 (last action of every particle, random 0..3 at
+ *   start) ; pointer, fes, log_index, curve_len [B] i32 ; curve [B, MBX_CURVE_LEN] f32 ; done [B] u8                  */
+typedef struct MbxQlpsoState {
+    float *x, *v, *pbest_x, *cost, *gbest_cost;
+    double* diversity;
+    int32_t *q_state, *pointer, *fes, *log_index, *curve_len;
+    float* curve;
+    uint8_t* done;
+} MbxQlpsoState;
+
+/* Recorded draws (device; null when use_tape=0): init_pos_u [B,NP,D] f64 ; init_state [B,NP] i32 ; rand2 [B,2] f64 (this
+ * step's two np.random.rand() scalars, neighbourhood term first) ; noise [B,3,n] f64, n = NP for init, 1 for a step.   */
+typedef struct MbxQlpsoTape {
+    const double* init_pos_u;
+    const int32_t* init_state;
+    const double *rand2, *noise;
+} MbxQlpsoTape;
+
+/* d_state [B] i32 = q_state of the particle the next action applies to (:89) */
+int mbx_qlpso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxQlpsoState* st, const MbxQlpsoTape* tape, int32_t* d_state, int B, void* stream);
+
+/* d_action [B] i32 in 0..3 (anything else: the particle is its own neighbourhood) ; outputs d_state [B] i32 (of the NEXT
+ * particle), d_reward [B] f32 in {2, 1, 0, -2} (cal_reward, :7-16), st->done.  Finished lanes: reward = 0.           */
+int mbx_qlpso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxQlpsoState* st, const MbxQlpsoTape* tape, const int32_t* d_action, int32_t* d_state,
+                   float* d_reward, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Landscape features of sampled walks -- replaces cal_fdc / cal_rie / cal_acf / cal_nop
  * (optimizer/dedqn_optimizer.py:8-76) and the DFDC / DRIE statistics of RL_HPSDE
  * (optimizer/rl_hpsde_optimizer.py:169-216) for B walks at once.

@@ -87,6 +87,15 @@ class MbxRlPsoTape(C.Structure):
     _fields_ = [(n, _P) for n in ('init_pos_u', 'init_vel_u', 'rand1', 'noise')]
 
 
+class MbxQlpsoState(C.Structure):
+    _fields_ = [(n, _P) for n in ('x', 'v', 'pbest_x', 'cost', 'gbest_cost', 'diversity', 'q_state', 'pointer', 'fes', 'log_index',
+                                  'curve_len', 'curve', 'done')]
+
+
+class MbxQlpsoTape(C.Structure):
+    _fields_ = [(n, _P) for n in ('init_pos_u', 'init_state', 'rand2', 'noise')]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/metabox_b200.h declares
@@ -117,6 +126,10 @@ SIGNATURES = {
                                   C.c_int, _P]),
     'mbx_rl_pso_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxRlPsoState), C.POINTER(MbxRlPsoTape), _P,
                                   _P, _P, C.c_int, _P]),
+    'mbx_qlpso_init': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxQlpsoState), C.POINTER(MbxQlpsoTape), _P,
+                                 C.c_int, _P]),
+    'mbx_qlpso_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxQlpsoState), C.POINTER(MbxQlpsoTape), _P,
+                                 _P, _P, C.c_int, _P]),
     'mbx_landscape_features': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }

@@ -169,3 +169,33 @@ class LDE_PolicyNet(nn.Module):
         mu, sigma, h2, c2 = self.lstm_cell(x, h, c)
         eps = torch.randn_like(mu) if noise is None else noise
         return torch.clip(mu + sigma * eps, 0, 1), h2, c2
+
+
+# ------------------------------------------------------------------------------------------ QLPSO
+class QLPSO_QTable(nn.Module):
+    """Tabular policy of QLPSO_Agent (qlpso_agent.py:17-37): a [4, 4] Q-table; the action is sampled from
+    softmax(Q[state]) (`__get_action`, :33-36).  `forward(q_state [B] int, u=None) -> action [B] int32`; `u` are uniforms
+    in [0, 1) (inverse-CDF sampling, so that a sweep can draw them from its own generator under CUDA-graph capture).
+    `td_update` is the reference's learning rule (:47-48) for batches of transitions, applied in order."""
+    takes_uniform = True
+
+    def __init__(self, q_table=None, n_states=4, n_actions=4):
+        super().__init__()
+        q = torch.zeros(n_states, n_actions, dtype=torch.float64) if q_table is None else torch.as_tensor(q_table, dtype=torch.float64)
+        self.register_buffer('q_table', q.clone())
+
+    @torch.no_grad()
+    def forward(self, state, u=None):
+        prob = torch.softmax(self.q_table, dim=1)[state.long()]                       # exp(q) / exp(q).sum()  (:34-35)
+        if u is None:
+            u = torch.rand(state.shape[0], device=state.device, dtype=torch.float32)
+        cdf = torch.cumsum(prob, dim=1)
+        a = (u.to(cdf.dtype)[:, None] >= cdf).sum(dim=1).clamp(max=self.q_table.shape[1] - 1)
+        return a.to(torch.int32)
+
+    @torch.no_grad()
+    def td_update(self, state, action, reward, next_state, alpha, gamma=0.8):
+        """Q[s][a] += alpha * (r + gamma * max Q[s'] - Q[s][a]) for each transition in turn (qlpso_agent.py:47-48)."""
+        q = self.q_table
+        for s, a, r, n in zip(state.tolist(), action.tolist(), reward.tolist(), next_state.tolist()):
+            q[s, a] += alpha * (r + gamma * q[n].max() - q[s, a])

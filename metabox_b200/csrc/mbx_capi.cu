@@ -190,4 +190,28 @@ int mbx_rl_pso_step(const MbxInstance* d_inst, const double* d_consts, const int
                                   (cudaStream_t)stream);
 }
 
+int mbx_qlpso_init(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxQlpsoState* st, const MbxQlpsoTape* tape, int32_t* d_state, int B, void* stream) {
+    int rc = check_cfg("mbx_qlpso_init", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(cfg->NP <= 128, "mbx_qlpso_init: NP=%d > 128", cfg->NP);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_state, "mbx_qlpso_init: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->init_pos_u && tape->init_state), "mbx_qlpso_init: use_tape without tape");
+    return mbx_launch_qlpso_init(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_state, B, (cudaStream_t)stream);
+}
+
+int mbx_qlpso_step(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxQlpsoState* st, const MbxQlpsoTape* tape, const int32_t* d_action, int32_t* d_state, float* d_reward,
+                   int B, void* stream) {
+    int rc = check_cfg("mbx_qlpso_step", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(cfg->NP <= 128, "mbx_qlpso_step: NP=%d > 128", cfg->NP);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_action && d_state && d_reward, "mbx_qlpso_step: null pointer");
+    MBX_REQUIRE(!cfg->use_tape || (tape && tape->rand2), "mbx_qlpso_step: use_tape without tape");
+    return mbx_launch_qlpso_step(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, tape, d_action, d_state, d_reward, B,
+                                 (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -22,6 +22,7 @@
 #define MBX_TAG_DDQN_D 11u
 #define MBX_TAG_GLEET_P 12u
 #define MBX_TAG_RLPSO 13u
+#define MBX_TAG_QLPSO 14u
 #define MBX_GEN_INIT 0xFFFFFFFFu
 
 // Phase profiling build (python -m metabox_b200.build --profile -> libmbx_prof.so, never the product library): thread 0 of

@@ -46,6 +46,12 @@ int mbx_launch_gleet_step(int kind, const MbxInstance* inst, const double* const
                           float* state, float* reward, int B, cudaStream_t st);
 int mbx_launch_landscape(const double* sample, const double* cost, const double* ref, int B, int S, int D, double* out,
                          cudaStream_t st);
+int mbx_launch_qlpso_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                          const MbxRunConfig* cfg, const MbxQlpsoState* s, const MbxQlpsoTape* tape, int32_t* state, int B,
+                          cudaStream_t st);
+int mbx_launch_qlpso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
+                          const MbxRunConfig* cfg, const MbxQlpsoState* s, const MbxQlpsoTape* tape, const int32_t* action,
+                          int32_t* state, float* reward, int B, cudaStream_t st);
 int mbx_launch_rl_pso_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                            const MbxRunConfig* cfg, const MbxRlPsoState* s, const MbxRlPsoTape* tape, float* state, int B,
                            cudaStream_t st);

@@ -730,3 +730,115 @@ class RL_PSO_Optimizer(Learnable_Optimizer):
         state, reward, done = self._engine.update(a.to(self._engine.device))
         self._sync()
         return state[0].cpu().numpy().astype(np.float64), float(reward[0].item()), bool(done[0].item())
+
+
+# ======================================================================================== QLPSO
+class QLPSO_Engine:
+    """B lanes of the QLPSO backbone (qlpso_optimizer.py:74-126) on one GPU: one particle per step.  `feature` is the [B]
+    int32 Q-state (last action of the particle the next action applies to); the action is [B] int32 in 0..3."""
+    NP = 30
+
+    def __init__(self, pack: InstancePack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, NP=None, lane_base=0):
+        import torch
+        self.pack, self.device = pack, pack.device
+        self.lane_base = int(lane_base)
+        self.NP = int(NP or QLPSO_Engine.NP)
+        self.dim = pack.dim
+        self.B = len(lane_inst)
+        self.maxFEs, self.n_logpoint = int(maxFEs), int(n_logpoint)
+        self.log_interval = int(log_interval or maxFEs // n_logpoint)
+        self.seed = int(seed)
+        dev, B, NPn, D = self.device, self.B, self.NP, self.dim
+        if isinstance(lane_inst, torch.Tensor):
+            self.lane_inst = lane_inst.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            self.lane_inst = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.x, self.v, self.pbest_x = z(B, NPn, D), z(B, NPn, D), z(B, NPn, D)
+        self.cost, self.gbest_cost = z(B, NPn), z(B)
+        self.diversity = z(B, dt=torch.float64)
+        self.q_state = z(B, NPn, dt=i32)
+        self.pointer, self.fes, self.log_index, self.curve_len = (z(B, dt=i32) for _ in range(4))
+        self.curve = z(B, _lib.CURVE_LEN)
+        self.done = z(B, dt=torch.uint8)
+        self.feature, self.reward = z(B, dt=i32), z(B)
+        self._state = _lib.MbxQlpsoState(*[t.data_ptr() for t in (
+            self.x, self.v, self.pbest_x, self.cost, self.gbest_cost, self.diversity, self.q_state, self.pointer, self.fes,
+            self.log_index, self.curve_len, self.curve, self.done)])
+
+    _cfg = RL_PSO_Engine._cfg
+
+    @property
+    def gbest_val(self):                                          # (name shared with the other engines: sweeps, Tester)
+        return self.gbest_cost
+
+    def init_population(self, tape=None):
+        import torch
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxQlpsoTape, tape, self.device, int_fields=('init_state',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_qlpso_init(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                           C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(self.feature), self.B,
+                                           _lib.stream_ptr())
+        _lib.check(rc, 'mbx_qlpso_init')
+        return self.feature
+
+    def update(self, action, tape=None):
+        """action [B] (or [B,1]) integer device tensor -> (q-state [B] int32, reward [B] float32, done [B] uint8), on device."""
+        import torch
+        action = action.reshape(-1)
+        if action.shape[0] != self.B:
+            raise ValueError(f'QLPSO action must have one value per lane ({self.B}), got {tuple(action.shape)}')
+        if action.dtype != torch.int32 or not action.is_contiguous() or action.device != self.device:
+            action = action.to(device=self.device, dtype=torch.int32).contiguous()
+        cfg = self._cfg(tape is not None)
+        ts, keep = _tape_struct(_lib.MbxQlpsoTape, tape, self.device, int_fields=('init_state',))
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_qlpso_step(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst),
+                                           C.byref(cfg), C.byref(self._state), C.byref(ts), _lib.ptr(action),
+                                           _lib.ptr(self.feature), _lib.ptr(self.reward), self.B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_qlpso_step')
+        return self.feature, self.reward, self.done
+
+    cost_curves = RLEPSO_Engine.cost_curves
+    load_state = RLEPSO_Engine.load_state
+
+    def read_state(self, b):
+        keys = ('x', 'v', 'pbest_x', 'cost', 'gbest_cost', 'diversity', 'q_state', 'pointer', 'fes', 'log_index', 'curve_len',
+                'curve', 'done')
+        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+
+
+class QLPSO_Optimizer(Learnable_Optimizer):
+    """Drop-in for `QLPSO_Optimizer` (qlpso_optimizer.py:19-126): one problem, numpy in / python scalars out."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        config.NP = 30
+        config.C = 1.49618
+        config.W = 0.729844
+        self.__config = config
+        self.fes = None
+        self.cost = None
+        self.log_index = None
+        self.log_interval = config.log_interval
+        self._engine = None
+
+    def init_population(self, problem):
+        pack = problem._pack if getattr(problem, '_pack', None) is not None else InstancePack([problem])
+        cfg = self.__config
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + int(np.random.randint(0, 2 ** 31 - 1))
+        self._engine = QLPSO_Engine(pack, [problem._index], cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, seed, cfg.NP)
+        state = self._engine.init_population()
+        self._sync()
+        return int(state[0].item())
+
+    _sync = RL_PSO_Optimizer._sync
+
+    def update(self, action, problem):
+        import torch
+        a = torch.as_tensor(np.asarray(action, dtype=np.int32).reshape(-1))
+        state, reward, done = self._engine.update(a.to(self._engine.device))
+        self._sync()
+        return int(state[0].item()), int(reward[0].item()), bool(done[0].item())

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .optimizer import DE_DDQN_Engine, GLEET_Engine, LDE_Engine, RL_PSO_Engine, RLEPSO_Engine
+from .optimizer import DE_DDQN_Engine, GLEET_Engine, LDE_Engine, QLPSO_Engine, RL_PSO_Engine, RLEPSO_Engine
 
 
 def lane_table(n_instances, n_runs):
@@ -232,6 +232,25 @@ class RL_PSO_Sweep(_Sweep):
         self.policy = policy
 
     def _policy(self, feat):
+        return self.policy(feat).reshape(-1)
+
+
+class QLPSO_Sweep(_Sweep):
+    """QLPSO_Agent.rollout_episode (qlpso_agent.py:66-75): `policy(q_state [B] int32) -> action [B] integer`, one FE per step.
+    A policy with `takes_uniform = True` is called as `policy(q_state, u=...)` with uniforms from the sweep's own generator
+    (graph-safe sampling, see QLPSO_QTable)."""
+
+    def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=500, time_kernels=False,
+                 graph=True, steps_per_graph=10):
+        eng = QLPSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
+        self.policy = policy
+        self.finite_reward = True                    # rewards are 2 / 1 / 0 / -2
+
+    def _policy(self, feat):
+        if getattr(self.policy, 'takes_uniform', False):
+            u = torch.rand(feat.shape[0], generator=self.gen, device=feat.device, dtype=torch.float32)
+            return self.policy(feat, u=u).reshape(-1)
         return self.policy(feat).reshape(-1)
 
 

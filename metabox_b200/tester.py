@@ -22,7 +22,8 @@ import time
 import numpy as np
 
 N_RUNS_TEST, N_RUNS_ROLLOUT = 51, 5           # tester.py:121, :318
-AGENT_ALGO = {'RLEPSO_Agent': 'rlepso', 'LDE_Agent': 'lde', 'DE_DDQN_Agent': 'deddqn', 'GLEET_Agent': 'gleet', 'RL_PSO_Agent': 'rl_pso'}
+AGENT_ALGO = {'RLEPSO_Agent': 'rlepso', 'LDE_Agent': 'lde', 'DE_DDQN_Agent': 'deddqn', 'GLEET_Agent': 'gleet', 'RL_PSO_Agent': 'rl_pso',
+              'QLPSO_Agent': 'qlpso'}
 
 
 def cal_t0(dim, fes):
@@ -75,6 +76,8 @@ def _make_sweep(algo, pack, lanes, policy, config, seed, lane_base, stripes):
             return ms.GLEET_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
         if algo == 'rl_pso':                                  # policy: state [B,2D] -> action [B]
             return ms.RL_PSO_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
+        if algo == 'qlpso':                                   # policy: q_state [B] int32 -> action [B] in 0..3
+            return ms.QLPSO_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
         return ms.DE_DDQN_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
 
     return ms.StripedSweep(make, lanes, lane_base, stripes) if stripes > 1 and len(lanes) > stripes else make(lanes, lane_base)
@@ -110,7 +113,7 @@ def rows_to_results(rows, problems, n_runs, agent_name, out):
 class Tester:
     """`Tester(config, policies).test()` -- config fields used: problem, difficulty, dim, maxFEs, n_logpoint,
     log_interval, upperbound, test_log_dir, agent_for_cp (names out of RLEPSO_Agent / LDE_Agent / DE_DDQN_Agent / GLEET_Agent /
-    RL_PSO_Agent),
+    RL_PSO_Agent / QLPSO_Agent),
     t_optimizer_for_cp (only 'Random_search' has a B200 path).  `policies`: {agent name: torch module on the GPU}."""
 
     def __init__(self, config, policies, device=None, data_folder=None):

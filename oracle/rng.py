@@ -29,6 +29,7 @@ TAG_DDQN = 10       # per step : w0..w3 + second block -> 5 indices r, j_rand   
 TAG_DDQN_D = 11     # per d    : crossover u                                                    (DE-DDQN)
 TAG_GLEET_P = 12    # per i    : w0 -> rand1, w1 -> rand2                                         (GLEET)
 TAG_RLPSO = 13      # per step : w0 -> rand1                                                      (RL_PSO)
+TAG_QLPSO = 14      # per step : w0, w1 -> the two scalars of the velocity; init: per i w0 & 3 -> q-state (QLPSO)
 GEN_INIT = 0xFFFFFFFF
 
 _M0 = np.uint64(0xD2511F53)

@@ -385,3 +385,52 @@ def test_rl_pso_steps_match_reference():
             j = (t - 1) % cfg.NP
             S.c_cost[j] = G[f'{key}/row_c_cost'][t - 1]; S.pbest[j] = G[f'{key}/row_pbest'][t - 1]
             S.gbest_val = np.float32(G[f'{key}/gbest_val'][t - 1])
+
+
+# ------------------------------------------------------------------------------------------ QLPSO
+def _qlpso_s0(G, key):
+    from oracle import qlpso as oq
+    pre = f'{key}/s0/'
+    return oq.State(x=G[pre + 'x'], v=G[pre + 'v'], pbest_x=G[pre + 'pbest_x'], cost=G[pre + 'cost'],
+                    gbest_cost=np.float32(G[pre + 'gbest_cost']), diversity=float(G[pre + 'diversity']),
+                    q_state=G[pre + 'q_state'].astype(np.int32), pointer=0, fes=len(G[pre + 'cost']), log_index=1,
+                    curve=[np.float32(G[pre + 'gbest_cost'])])
+
+
+def test_qlpso_steps_match_reference():
+    """100 consecutive single-particle steps of the real QLPSO_Optimizer per case (float32 storage contract, seeded
+    np.random) vs the oracle replaying the same draws: the updated row and the float64 diversity bit-exact, the integer
+    reward and the returned Q-state equal, costs to 1e-6."""
+    from oracle import qlpso as oq
+    G = load('qlpso.npz')
+    seen_rewards = set()
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = oq.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, qs = oq.init_population(cfg, ev, optimum, lb, ub, oq.NumpyTape(cfg.NP, dim, nc))
+        S0 = _qlpso_s0(G, key)
+        for k in ('x', 'v', 'pbest_x', 'q_state'):
+            np.testing.assert_array_equal(getattr(S, k), getattr(S0, k), err_msg=f'{key} init {k}')
+        np.testing.assert_allclose(S.cost, S0.cost, rtol=1e-6, atol=1e-10)
+        assert S.diversity == S0.diversity and qs == int(G[f'{key}/s0/ret_state'])
+        S = S0                                                       # carry the reference's (float32) costs forward
+        for t in range(1, int(G['n_steps']) + 1):
+            k = t - 1
+            j = k % cfg.NP
+            tag = f'{key} step {t}'
+            np.random.seed(int(G[f'{key}/seed'][k]))
+            S, qs, reward, done = oq.update(cfg, S, G[f'{key}/action'][k], ev, optimum, lb, ub, oq.NumpyTape(cfg.NP, dim, nc))
+            np.testing.assert_array_equal(S.x[j], G[f'{key}/row_x'][k], err_msg=f'{tag} x row')
+            np.testing.assert_array_equal(S.v[j], G[f'{key}/row_v'][k], err_msg=f'{tag} v row')
+            np.testing.assert_array_equal(S.pbest_x[j], G[f'{key}/row_pbest_x'][k], err_msg=f'{tag} pbest row')
+            np.testing.assert_allclose(S.cost[j], G[f'{key}/row_cost'][k], rtol=1e-6, atol=1e-10, err_msg=f'{tag} cost')
+            np.testing.assert_allclose(float(S.gbest_cost), G[f'{key}/gbest_cost'][k], rtol=1e-6, atol=1e-10)
+            assert S.diversity == float(G[f'{key}/diversity'][k]), tag
+            assert reward == int(G[f'{key}/reward'][k]) and qs == int(G[f'{key}/next_state'][k]) and done == bool(G[f'{key}/done'][k]), tag
+            assert S.fes == int(G[f'{key}/fes'][k]) and S.log_index == int(G[f'{key}/log_index'][k]) and len(S.curve) == int(G[f'{key}/curve_len'][k]), tag
+            np.testing.assert_allclose(float(S.curve[-1]), G[f'{key}/curve_last'][k], rtol=1e-6, atol=1e-10)
+            seen_rewards.add(reward)
+            S.cost[j] = G[f'{key}/row_cost'][k]; S.gbest_cost = np.float32(G[f'{key}/gbest_cost'][k])
+    assert seen_rewards == {2, 1, 0, -2}
