@@ -78,6 +78,11 @@ class RLEPSO_Actor(nn.Module):
         sigma = (torch.tanh(self.sigma_net(x)) + 1.) / 2. * (self.max_sigma - self.min_sigma) + self.min_sigma
         return mu, sigma
 
+    def log_prob(self, x, action):
+        """sum over the 35 coefficients of log N(action; mu, sigma) (rlepso_agent.py:26-35, `fixed_action` path); differentiable."""
+        mu, sigma = self.distribution(x)
+        return torch.distributions.Normal(mu, sigma).log_prob(action).sum(-1)
+
     @torch.no_grad()
     def forward(self, x, noise=None):
         """x [..., 1] -> action [..., 35].  `noise` (standard normal, same shape as the action) can be
@@ -85,6 +90,17 @@ class RLEPSO_Actor(nn.Module):
         mu, sigma = self.distribution(x)
         eps = torch.randn_like(mu) if noise is None else noise
         return torch.clamp(mu + sigma * eps, min=0, max=1)
+
+
+class RLEPSO_Critic(nn.Module):
+    """Value head 1 -> 16 -> 8 -> 1 (rlepso_agent.py:49-61); forward(x [..., 1]) -> value [...]."""
+
+    def __init__(self):
+        super().__init__()
+        self.value_head = MLP(_mlp_cfg([RLEPSO_Actor.feature_dim, 16, 8, 1]))
+
+    def forward(self, x):
+        return self.value_head(x).squeeze(-1)
 
 
 class RLEPSO_Agent:

@@ -1,4 +1,5 @@
-"""Sharded training rollouts for the LDE agent (BASELINE config C4 "LDE train rollout ... sharded").
+"""Sharded training rollouts for the LDE agent (REINFORCE) and the RLEPSO agent (PPO) (BASELINE config C4
+"LDE train rollout ... sharded").  The RLEPSO part is at the end of the file.
 
 Reference: `LDE_Agent.train_episode` (`src/agent/lde_agent.py:85-145`): per problem, TRAJECTORY_NUM = 20 trajectories of
 TRAJECTORY_LENGTH = 50 environment steps are collected with the current policy (`sampler`, no gradient), then ONE batched
@@ -21,8 +22,8 @@ import numpy as np
 import torch
 
 from . import sweep as ms
-from .agent import LDE_PolicyNet
-from .optimizer import LDE_Engine
+from .agent import LDE_PolicyNet, RLEPSO_Actor, RLEPSO_Critic
+from .optimizer import LDE_Engine, RLEPSO_Engine
 
 TRAJECTORY_NUM, TRAJECTORY_LENGTH, GAMMA, LR_MODEL = 20, 50, 0.99, 0.005      # lde_agent.py:36-42
 
@@ -50,22 +51,25 @@ def reinforce_loss(net, inputs, actions, hs, cs, rewards, weight, lanes_per_prob
     return -(term.sum(dim=(0, 2)) / n).sum(), P                                 # :129  loss = -mean(log_prob * reward)
 
 
-def allreduce_gradients(params, n_local, group=None):
+def allreduce_gradients(params, n_local, group=None, extra=None):
     """Sum the flattened gradients and the problem counts over the ranks, divide: every rank ends up with the gradient of
-    the mean per-problem loss.  ONE collective per learn step.  Works on any backend (NCCL on GPUs, gloo in the CPU tests)."""
+    the mean per-problem loss.  ONE collective per learn step.  Works on any backend (NCCL on GPUs, gloo in the CPU tests).
+    `extra`: optional list of local scalars summed in the same collective -> returns (total, [sums])."""
     import torch.distributed as dist
     params = [p for p in params if p.requires_grad]
+    tail = [float(v) for v in (extra or [])] + [float(n_local)]
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] +
-                     [torch.tensor([float(n_local)], device=params[0].device, dtype=params[0].dtype)])
+                     [torch.tensor(tail, device=params[0].device, dtype=params[0].dtype)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    total = float(flat[-1].item())
+    sums = flat[-len(tail):].tolist()
+    total = float(sums[-1])
     off = 0
     for p in params:
         k = p.numel()
         p.grad = (flat[off:off + k] / max(total, 1.0)).reshape(p.shape).clone()
         off += k
-    return total
+    return total if extra is None else (total, sums[:-1])
 
 
 class LDE_Trainer:
@@ -126,3 +130,136 @@ class LDE_Trainer:
         self.learn_steps += 1
         return {'loss': info['loss'] / max(1, n_local), 'return': info['ret'], 'learn_steps': self.learn_steps,
                 'gbest': info['gbest'], 'normalizer': info['normalizer'], 'problems': int(total)}
+
+
+# ======================================================================================== RLEPSO (PPO)
+N_STEP, K_EPOCHS, EPS_CLIP, PPO_GAMMA, PPO_LR = 10, 3, 0.1, 0.999, 1e-5          # rlepso_agent.py:72-79
+
+
+def ppo_targets(rewards, weight, bootstrap, gamma=PPO_GAMMA):
+    """n-step targets (rlepso_agent.py:219-231): R_t = r_t + gamma R_{t+1}, R_T = critic(state after the segment), per lane.
+    rewards / weight [T, L], bootstrap [L] (detached).  Steps after a lane has finished (weight 0) leave its chain untouched."""
+    out = torch.empty_like(rewards)
+    run = bootstrap
+    for t in range(rewards.shape[0] - 1, -1, -1):
+        run = torch.where(weight[t] > 0, run * gamma + rewards[t], run)
+        out[t] = run
+    return out
+
+
+def ppo_losses(actor, critic, states, actions, old_logp, rewards, weight, next_state, old_value=None, eps_clip=EPS_CLIP,
+               gamma=PPO_GAMMA):
+    """One K-epoch of the reference's PPO update (rlepso_agent.py:196-253) for L lanes at once.
+    states [T,L,1], actions [T,L,35], old_logp / rewards / weight [T,L], next_state [L,1]; old_value: detached values of the
+    first epoch (None in the first epoch).  -> (reinforce_loss, baseline_loss, values.detach(), n_lanes): each loss is the SUM
+    over the lanes with at least one live step of the reference's per-episode mean over that lane's steps."""
+    logp = actor.log_prob(states, actions)                                   # [T, L]
+    value = critic(states)                                                   # [T, L]
+    with torch.no_grad():
+        target = ppo_targets(rewards, weight, critic(next_state), gamma)
+    ratios = torch.exp(logp - old_logp.detach())
+    adv = target - value.detach()
+    surr = torch.min(ratios * adv, torch.clamp(ratios, 1 - eps_clip, 1 + eps_clip) * adv)
+    if old_value is None:
+        verr = (value - target) ** 2
+    else:
+        vclip = old_value + torch.clamp(value - old_value, -eps_clip, eps_clip)
+        verr = torch.max((value - target) ** 2, (vclip - target) ** 2)
+    n_t = weight.sum(0)
+    live = n_t > 0
+    n_t = n_t.clamp(min=1.0)
+    reinforce = -((surr * weight).sum(0) / n_t)[live].sum()
+    baseline = ((verr * weight).sum(0) / n_t)[live].sum()
+    return reinforce, baseline, value.detach(), int(live.sum().item())
+
+
+class RLEPSO_Trainer:
+    """`RLEPSO_Trainer(config, train_problems).train_episodes(problem_ids)` -- `RLEPSO_Agent.train_episode`
+    (rlepso_agent.py:113-292) for many problems at once: every problem is a lane of `RLEPSO_Engine`, all lanes advance in
+    lockstep in segments of n_step = 10 generations (policy sampling + fused step kernel on the GPU, nothing leaves the
+    device), and after each segment K_epochs = 3 clipped-PPO updates of actor and critic (two Adam optimizers, lr 1e-5)
+    are made from the mean of the per-lane losses.  With torch.distributed initialised the problems are sharded over the
+    ranks and the actor + critic gradients travel in ONE all-reduce per update (the same collective carries the number of
+    lanes still running, so every rank leaves the loop in the same segment).  One problem on one rank is the reference's
+    update rule.  config fields: dim, maxFEs, n_logpoint, log_interval, optional max_learning_step."""
+
+    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None):
+        from .problem import InstancePack
+        self.config, self.seed = config, int(seed)
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.problems = list(problems)
+        self.pack = InstancePack(self.problems, self.device)
+        self.actor = (actor if actor is not None else RLEPSO_Actor()).to(self.device)
+        self.critic = (critic if critic is not None else RLEPSO_Critic()).to(self.device)
+        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=PPO_LR)
+        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=PPO_LR)
+        self.learning_time = 0
+        self.episodes = 0
+
+    def _params(self):
+        return list(self.actor.parameters()) + list(self.critic.parameters())
+
+    @torch.no_grad()
+    def collect_segment(self, eng, n_step=N_STEP):
+        """n_step generations of all lanes with the current policy -> states [T,L,1], actions [T,L,35], logp, rewards, weight."""
+        S, A, LP, R, W = [], [], [], [], []
+        for _ in range(n_step):
+            alive = (eng.done == 0).to(torch.float32)
+            x = eng.feature.reshape(eng.B, 1).clone()
+            a = self.actor(x)
+            S.append(x); A.append(a); LP.append(self.actor.log_prob(x, a)); W.append(alive)
+            _, reward, _ = eng.update(a)
+            R.append(reward.clone() * alive)
+        st = lambda xs: torch.stack(xs, dim=0)
+        return dict(states=st(S), actions=st(A), logp=st(LP), rewards=st(R), weight=st(W),
+                    next_state=eng.feature.reshape(eng.B, 1).clone())
+
+    def train_episodes(self, problem_ids):
+        """Full episodes of `problem_ids` (sharded over the ranks).  -> info dict like train_episode's (:284-292) with
+        per-problem lists plus 'segments' and the last losses."""
+        import torch.distributed as dist
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        lo, hi = ms.shard_range(len(problem_ids), rank, world)
+        mine = np.asarray(list(problem_ids[lo:hi]), dtype=np.int32)
+        cfg = self.config
+        max_ls = getattr(cfg, 'max_learning_step', None)
+        eng = RLEPSO_Engine(self.pack, mine, cfg.maxFEs, cfg.n_logpoint, getattr(cfg, 'log_interval', None),
+                            seed=self.seed + 104729 * self.episodes, lane_base=lo)
+        if len(mine):
+            eng.init_population()
+        ret = torch.zeros(len(mine), device=self.device)
+        segments, last, stop = 0, (0.0, 0.0), False
+        running = 1.0
+        while running > 0 and not stop:
+            seg = self.collect_segment(eng) if len(mine) else None
+            if seg is not None:
+                ret += seg['rewards'].sum(0)
+            old_value = None
+            for _k in range(K_EPOCHS):
+                self.optimizer_actor.zero_grad(set_to_none=True)
+                self.optimizer_critic.zero_grad(set_to_none=True)
+                n_local, alive_after = 0, 0.0
+                if seg is not None:
+                    rl, bl, val, n_local = ppo_losses(self.actor, self.critic, seg['states'], seg['actions'], seg['logp'],
+                                                      seg['rewards'], seg['weight'], seg['next_state'], old_value)
+                    if old_value is None:
+                        old_value = val
+                    if n_local:
+                        bl.backward()                                        # :257-258 (two separate backward passes)
+                        rl.backward()
+                        last = (float(rl.item()) / n_local, float(bl.item()) / n_local)
+                    alive_after = float((eng.done == 0).sum().item())
+                total, (running,) = allreduce_gradients(self._params(), n_local, extra=[alive_after])
+                if total > 0:
+                    self.optimizer_actor.step()
+                    self.optimizer_critic.step()
+                    self.learning_time += 1
+                if max_ls is not None and self.learning_time >= max_ls:
+                    stop = True
+                    break
+            segments += 1
+        self.episodes += 1
+        curves = eng.cost_curves(pad=False) if len(mine) else []
+        return {'normalizer': [c[0] for c in curves], 'gbest': [c[-1] for c in curves], 'return': ret.tolist(),
+                'learn_steps': self.learning_time, 'segments': segments, 'reinforce_loss': last[0], 'baseline_loss': last[1],
+                'done': bool(max_ls is not None and self.learning_time >= max_ls)}

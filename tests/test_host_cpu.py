@@ -258,7 +258,8 @@ def _grad_worker(rank, world, port, q):
         lin = torch.nn.Linear(3, 2)
         for p in lin.parameters():
             p.grad = torch.full_like(p, float(rank + 1))        # "sum over local problems" gradients
-        total = mt.allreduce_gradients(lin.parameters(), n_local=rank + 1)       # rank 0: 1 problem, rank 1: 2 problems
+        total, (alive,) = mt.allreduce_gradients(lin.parameters(), n_local=rank + 1, extra=[10.0 * (rank + 1)])   # rank 0: 1 problem, rank 1: 2
+        assert alive == 30.0                                     # extra scalars ride in the same collective (PPO: lanes still running)
         q.put((rank, total, [p.grad.clone().numpy() for p in lin.parameters()]))
     finally:
         dist.destroy_process_group()
@@ -282,3 +283,64 @@ def test_gradient_allreduce_world2_gloo():
         assert total == 3.0
         for g in grads:
             np.testing.assert_allclose(g, (1.0 + 2.0) / 3.0)
+
+
+def _reference_ppo_epoch(actor, critic, states, actions, old_logp, rewards, next_state, old_value, gamma=0.999, eps_clip=0.1):
+    """Literal per-episode restatement of rlepso_agent.py:196-253 (one lane, python loops over the segment)."""
+    import torch
+    t_time = states.shape[0]
+    logprobs, bl_val = [], []
+    for tt in range(t_time):
+        mu, sigma = actor.distribution(states[tt])
+        logprobs.append(torch.sum(torch.distributions.Normal(mu, sigma).log_prob(actions[tt])))
+        bl_val.append(critic(states[tt]).squeeze())
+    logprobs, bl_val = torch.stack(logprobs).view(-1), torch.stack(bl_val).view(-1)
+    R = critic(next_state).detach().squeeze()
+    Reward = []
+    for r in list(rewards)[::-1]:
+        R = R * gamma + r
+        Reward.append(R)
+    Reward = torch.stack(Reward[::-1], 0).view(-1)
+    ratios = torch.exp(logprobs - old_logp.detach())
+    advantages = Reward - bl_val.detach()
+    reinforce_loss = -torch.min(ratios * advantages, torch.clamp(ratios, 1 - eps_clip, 1 + eps_clip) * advantages).mean()
+    if old_value is None:
+        baseline_loss = ((bl_val - Reward) ** 2).mean()
+    else:
+        vpredclipped = old_value + torch.clamp(bl_val - old_value, -eps_clip, eps_clip)
+        baseline_loss = torch.max((bl_val - Reward) ** 2, (vpredclipped - Reward) ** 2).mean()
+    return reinforce_loss, baseline_loss, bl_val.detach()
+
+
+def test_rlepso_ppo_losses_match_the_reference_formulas():
+    import torch
+    from metabox_b200 import agent as ma, trainer as mt
+    torch.manual_seed(1)
+    actor, critic = ma.RLEPSO_Actor(), ma.RLEPSO_Critic()
+    T, L = 10, 5
+    states, actions = torch.rand(T, L, 1), torch.rand(T, L, 35)
+    rewards, nxt = torch.sign(torch.randn(T, L)), torch.rand(L, 1)
+    with torch.no_grad():
+        old_logp = actor.log_prob(states, actions) + 0.3 * torch.randn(T, L)         # a policy that has already moved
+    weight = torch.ones(T, L)
+    weight[6:, 2] = 0                                                                 # lane 2 finished after 6 generations
+    for old_value in (None, torch.rand(T, L)):
+        rl, bl, val, n = mt.ppo_losses(actor, critic, states, actions, old_logp, rewards * weight, weight, nxt, old_value)
+        want_r, want_b = 0., 0.
+        for b in range(L):
+            tt = 6 if b == 2 else T
+            r, v, _ = _reference_ppo_epoch(actor, critic, states[:tt, b], actions[:tt, b], old_logp[:tt, b], rewards[:tt, b], nxt[b],
+                                           None if old_value is None else old_value[:tt, b])
+            want_r, want_b = want_r + r, want_b + v
+        assert n == L
+        np.testing.assert_allclose(float(rl.detach()), float(want_r.detach()), rtol=2e-5)
+        np.testing.assert_allclose(float(bl.detach()), float(want_b.detach()), rtol=2e-5)
+        ps = list(actor.parameters()) + list(critic.parameters())
+        g1 = torch.autograd.grad(rl + bl, ps, retain_graph=True, allow_unused=True)
+        g2 = torch.autograd.grad(want_r + want_b, ps, allow_unused=True)
+        for a, b in zip(g1, g2):
+            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=3e-4, atol=3e-6)
+    # a lane without live steps contributes nothing
+    w0 = weight.clone(); w0[:, 4] = 0
+    _, _, _, n = mt.ppo_losses(actor, critic, states, actions, old_logp, rewards * w0, w0, nxt)
+    assert n == L - 1
