@@ -136,14 +136,6 @@ class DE_DDQN_Net(MLP):
     def act(self, state):
         return torch.argmax(self.forward(state), dim=-1)
 
-    def packed_weights(self):
-        """Flat float32 buffer [W0|b0|W1|b1|...] (row-major [out,in]) consumed by the persistent DE-DDQN kernel."""
-        ws = []
-        for k in range(5):
-            lin = getattr(self.net, f'layer{k}-linear')
-            ws += [lin.weight.detach().reshape(-1), lin.bias.detach().reshape(-1)]
-        return torch.cat(ws).to(torch.float32).contiguous()
-
 
 # ------------------------------------------------------------------------------------------ LDE
 class LDE_PolicyNet(nn.Module):

@@ -52,15 +52,16 @@ def test_tester_writes_reference_layout(tmp_path):
     assert out['test'] is R or out['test'] == R
 
 
-def test_tester_runs_gleet_and_rl_pso_backbones_with_callable_policies(tmp_path):
+def test_tester_runs_gleet_rl_pso_and_qlpso_backbones_with_callable_policies(tmp_path):
     import torch
-    from metabox_b200 import tester as mt
-    cfg = _config(tmp_path, agent_for_cp=['GLEET_Agent', 'RL_PSO_Agent'], t_optimizer_for_cp=[], maxFEs=600, log_interval=12)
+    from metabox_b200 import agent as ma, tester as mt
+    cfg = _config(tmp_path, agent_for_cp=['GLEET_Agent', 'RL_PSO_Agent', 'QLPSO_Agent'], t_optimizer_for_cp=[], maxFEs=600, log_interval=12)
     pol = {'GLEET_Agent': lambda s: torch.sigmoid(s[..., 1] - s[..., 2]),                 # [B,NP,27] -> [B,NP]
-           'RL_PSO_Agent': lambda s: torch.sigmoid(s[:, 0])}                              # [B,2D] -> [B]
+           'RL_PSO_Agent': lambda s: torch.sigmoid(s[:, 0]),                              # [B,2D] -> [B]
+           'QLPSO_Agent': ma.QLPSO_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda()}   # [B] int -> [B] int
     R = mt.Tester(cfg, pol).test(n_runs=2, random_search_baseline=False)['test']
     for p in R['cost']:
-        assert set(R['cost'][p]) == {'GLEET_Agent', 'RL_PSO_Agent'}
+        assert set(R['cost'][p]) == {'GLEET_Agent', 'RL_PSO_Agent', 'QLPSO_Agent'}
         for a in R['cost'][p]:
             assert len(R['cost'][p][a]) == 2 and all(len(c) == 51 for c in R['cost'][p][a])
             assert all(f >= 600 or c[-1] <= 1e-8 for f, c in zip(R['fes'][p][a], R['cost'][p][a]))
