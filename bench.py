@@ -78,7 +78,12 @@ class ClockSampler:
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+
+    def mark(self):
+        """Rows sampled from here on count (the sampler is started before the warm-up so that nvidia-smi's own start-up --
+        NVML initialisation over all GPUs of the box -- does not fall into the timed region)."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -95,10 +100,11 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        rows = self.rows[self.first:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
                     if v.lower().startswith('active'):
@@ -265,12 +271,13 @@ def main():
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
     sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph)
-    for _ in range(args.warmup):
-        one_sweep(sw)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        one_sweep(sw)
     barrier()
+    clocks.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     fes_total, launches = 0, 0
