@@ -1,4 +1,5 @@
 """CPU: host-side logic of the product (instance construction, packing, C-ABI surface).  No compute calls."""
+import argparse
 import ctypes
 import os
 import re
@@ -344,3 +345,95 @@ def test_rlepso_ppo_losses_match_the_reference_formulas():
     w0 = weight.clone(); w0[:, 4] = 0
     _, _, _, n = mt.ppo_losses(actor, critic, states, actions, old_logp, rewards * w0, w0, nxt)
     assert n == L - 1
+
+
+class _FakeRlepsoEngine:
+    """CPU stand-in with the engine surface RLEPSO_Trainer uses: lane k of the GLOBAL lane table finishes after 4 + 9 k
+    generations, rewards are +-1 (0 once finished), the feature is the consumed budget."""
+
+    def __init__(self, pack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, lane_base=0):
+        import torch
+        self.B = len(lane_inst)
+        self.life = torch.tensor([4 + 9 * (lane_base + k) for k in range(self.B)], dtype=torch.int64)
+        self.gen = torch.zeros(self.B, dtype=torch.int64)
+        self.feature = torch.zeros(self.B)
+        self.done = torch.zeros(self.B, dtype=torch.uint8)
+        self.g = torch.Generator().manual_seed(seed + lane_base)
+
+    def init_population(self):
+        return self.feature
+
+    def update(self, action):
+        import torch
+        assert action.shape == (self.B, 35)
+        alive = self.done == 0
+        self.gen += alive.long()
+        r = torch.where(torch.rand(self.B, generator=self.g) < action.mean(1), 1.0, -1.0) * alive
+        self.done = (self.gen >= self.life).to(torch.uint8)
+        self.feature = self.gen.float() / 40.0
+        return self.feature, r, self.done
+
+    def cost_curves(self, pad=False):
+        return [[10.0, 1.0] for _ in range(self.B)]
+
+
+def _ppo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from metabox_b200 import problem as mp, trainer as mt
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        mp.InstancePack = lambda problems, device=None: None            # no GPU in this test: host logic only
+        mt.RLEPSO_Engine = _FakeRlepsoEngine
+        torch.manual_seed(0)                                             # identical initial weights on every rank
+        cfg = argparse.Namespace(dim=10, maxFEs=4000, n_logpoint=50, log_interval=80)
+        T = mt.RLEPSO_Trainer(cfg, [None] * 5, seed=1, device='cpu')
+        info = T.train_episodes([0, 1, 2, 3, 4])                         # rank 0: lanes 0-2 (<= 22 gens), rank 1: lanes 3, 4 (<= 40 gens)
+        flat = torch.cat([p.detach().reshape(-1) for p in T._params()])
+        q.put((rank, info['segments'], info['learn_steps'], len(info['gbest']), flat.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rlepso_ppo_loop_world2_gloo_ranks_stay_in_step():
+    """Ranks whose lanes finish in different segments still make the same number of collectives and identical updates."""
+    import socket
+    import torch.multiprocessing as tmp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = tmp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ppo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=90) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, seg0, ls0, n0, w0), (r1, seg1, ls1, n1, w1) = got
+    assert seg0 == seg1 == 4 and ls0 == ls1 == 12                        # longest lane: 4 + 9*4 = 40 generations = 4 segments x 3 epochs
+    assert (n0, n1) == (3, 2)
+    np.testing.assert_array_equal(w0, w1)                                # the same all-reduced gradients -> the same weights
+
+
+def test_qlpso_qtable_policy_on_cpu():
+    """Tabular QLPSO policy (qlpso_agent.py:33-36, 47-48): softmax sampling by inverse CDF, TD rule."""
+    import torch
+    from metabox_b200 import agent as ma
+    qt = np.array([[0., 1., 2., 3.], [0., 0., 0., 0.], [5., 0., 0., 0.], [-1., -1., 4., -1.]])
+    q = ma.QLPSO_QTable(qt)
+    g = torch.Generator().manual_seed(0)
+    n = 100000
+    state = torch.randint(0, 4, (n,), generator=g, dtype=torch.int32)
+    a = q(state, u=torch.rand(n, generator=g))
+    assert a.dtype == torch.int32 and int(a.min()) >= 0 and int(a.max()) <= 3
+    for s in range(4):
+        want = np.exp(qt[s]) / np.exp(qt[s]).sum()
+        got = torch.bincount(a[state == s].long(), minlength=4).float().numpy()
+        np.testing.assert_allclose(got / got.sum(), want, atol=0.012)
+    assert int(q(torch.tensor([2]), u=torch.tensor([0.0]))[0]) == 0 and int(q(torch.tensor([0]), u=torch.tensor([0.999999]))[0]) == 3
+    ref = qt.copy()
+    for s, act, r, nx in [(0, 1, 2., 3), (3, 2, -2., 0), (0, 1, 1., 0)]:
+        ref[s][act] += 0.7 * (r + 0.8 * ref[nx].max() - ref[s][act])
+    q.td_update(torch.tensor([0, 3, 0]), torch.tensor([1, 2, 1]), torch.tensor([2., -2., 1.]), torch.tensor([3, 0, 0]), alpha=0.7)
+    np.testing.assert_allclose(q.q_table.numpy(), ref, rtol=1e-12)
