@@ -115,7 +115,7 @@ def test_policy_forward_matches_reference_kats():
     net = ma.load_reference_weights(ma.DE_DDQN_Net(), sub('deddqn/'))
     q = net(torch.as_tensor(G['deddqn_kat/x']))
     np.testing.assert_allclose(q.detach().numpy(), G['deddqn_kat/q'], rtol=1e-4, atol=1e-5)
-    assert net.packed_weights().numel() == 99 * 100 + 100 + 3 * (100 * 100 + 100) + 100 * 4 + 4
+    assert sum(p.numel() for p in net.parameters()) == 99 * 100 + 100 + 3 * (100 * 100 + 100) + 100 * 4 + 4
     lde = ma.load_reference_weights(ma.LDE_PolicyNet(), sub('lde/'))
     x, h, c = (torch.as_tensor(G[f'lde_kat/{k}']) for k in ('x', 'h', 'c'))
     mu, sigma, h2, c2 = lde.forward(x, h, c)                                 # nn.LSTM path (reference layout [1,B,*])
