@@ -36,7 +36,7 @@ WORKLOADS = {
     'deddqn': dict(suit='bbob', subset='difficult-test', NP=100, bytes_per_eval=32 * DIM + 404,
                    kernel='deddqn_step_kernel<30,BBOB>', desc='DE-DDQN rollouts, BBOB difficult test set 18 fns'),
     'gleet': dict(suit='bbob', subset='all', NP=100, bytes_per_eval=24 * DIM + 204, kernel='gleet_step_kernel<30,BBOB>',
-                  desc='GLEET backbone rollouts (stand-in per-particle MLP policy 27->64->1), BBOB 24 fns'),
+                  desc='GLEET rollouts, BBOB 24 fns'),
 }
 METRIC = 'candidate evals/sec on BBOB dim=30 pop=100'
 
@@ -49,7 +49,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
                     help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3; '
-                         'gleet = the GLEET backbone (SURVEY 8f N1) with a stand-in policy')
+                         'gleet = the GLEET backbone (SURVEY 8f N1), policy chosen by --gleet-policy')
+    ap.add_argument('--gleet-policy', default='actor', choices=['actor', 'stand-in'],
+                    help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor); "
+                         'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -123,11 +126,18 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def policy_weights(workload):
-    """Shipped policies (extracted from the reference pickles into tests/golden/agents.npz).  The shipped LDE policy
+def policy_weights(workload, gleet_policy='actor'):
+    """Shipped policies (extracted from the reference pickles into tests/golden/agents.npz / agents2.npz).  The shipped LDE policy
     only fits NP = 50 (lde_agent.py:37); the NP = 100 workload uses a randomly initialised policy of the right width."""
     p = os.path.join(ROOT, 'tests', 'golden', 'agents.npz')
-    if workload in ('lde', 'gleet') or not os.path.exists(p):
+    if workload == 'gleet':
+        p2 = os.path.join(ROOT, 'tests', 'golden', 'agents2.npz')
+        if gleet_policy != 'actor' or not os.path.exists(p2):
+            return None, 'stand-in per-particle MLP 27->64->1 (random init, seed 0)'
+        G = np.load(p2)
+        return ({k[len('gleet/'):]: np.asarray(G[k]) for k in G.files if k.startswith('gleet/')},
+                'GLEET attention actor, reference rollout checkpoint 20 (bbob_easy)')
+    if workload == 'lde' or not os.path.exists(p):
         return None, 'random init (seed 0)'
     G = np.load(p)
     pre = workload + '/'
@@ -153,7 +163,7 @@ def run_reference(args, rank, world):
     import torch
     from oracle import agents as oag, rollout as orr
     W = WORKLOADS[args.workload]
-    w_np, wsrc = policy_weights(args.workload)
+    w_np, wsrc = policy_weights(args.workload, args.gleet_policy)
     if w_np:
         w = {k: torch.as_tensor(v) for k, v in w_np.items()}
     else:
@@ -187,13 +197,20 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
-def build_policy(workload, dev, NP):
+def build_policy(workload, dev, NP, gleet_policy='actor'):
     import torch
     from metabox_b200 import agent as magent
     torch.manual_seed(0)
+    if workload == 'gleet' and gleet_policy == 'actor':
+        net = magent.GLEET_Actor()
+        w_np, wsrc = policy_weights(workload, gleet_policy)
+        if w_np:
+            magent.load_reference_weights(net, w_np)
+        else:
+            wsrc = 'GLEET attention actor, random init (seed 0)'
+        return net.to(dev).eval(), wsrc
     if workload == 'gleet':
-        # the reference's GLEET actor is an attention network (out of scope); any torch callable state[B,NP,27] -> action[B,NP]
-        # plugs in -- the bench uses a small per-particle MLP with a sigmoid head
+        # any torch callable state[B,NP,27] -> action[B,NP] plugs in: a small per-particle MLP with a sigmoid head
         net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(1))
         return net.to(dev).eval(), 'stand-in per-particle MLP 27->64->1 (random init, seed 0)'
     net = {'rlepso': magent.RLEPSO_Actor, 'deddqn': magent.DE_DDQN_Net}[workload]() if workload != 'lde' else magent.LDE_PolicyNet(NP=NP)
@@ -247,7 +264,7 @@ def main():
     tr, te = mp.BBOB_Dataset.get_datasets(W['suit'], DIM, 5, difficulty='difficult' if W['subset'] == 'difficult-test' else 'easy')
     problems = te.data if W['subset'] == 'difficult-test' else tr.data + te.data
     pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
-    net, wsrc = build_policy(args.workload, dev, NP)
+    net, wsrc = build_policy(args.workload, dev, NP, args.gleet_policy)
     inst, run = msweep.lane_table(len(problems), args.runs)
     if args.lane_order == 'run-major':                        # every contiguous stripe / rank sees the same mix of functions
         inst = np.ascontiguousarray(inst.reshape(len(problems), args.runs).T.reshape(-1))

@@ -1,10 +1,12 @@
-"""Agent layer: the rollout-time policies of the three configured MetaBBO agents, as plain torch modules
+"""Agent layer: the rollout-time policies of the MetaBBO agents whose backbones are built here, as plain torch modules
 running on the same CUDA stream as the step kernels (north star: "the small src/agent policy MLP/LSTM
-left as a torch call on the same stream").  Learning updates (PPO / DDQN / REINFORCE) stay out of scope.
+left as a torch call on the same stream").  The learning updates live in trainer.py (LDE REINFORCE, RLEPSO PPO).
 
 Reference:  MLP builder `src/agent/networks.py:4-26`; RLEPSO `Actor.forward` `rlepso_agent.py:22-47`,
 rollout loop `:294-303`; DE-DDQN net `de_ddqn_agent.py:21-25`, greedy action `:59-68`, rollout `:108-117`;
-LDE `PolicyNet` `lde_agent.py:8-29`, rollout `:147-163`.
+LDE `PolicyNet` `lde_agent.py:8-29`, rollout `:147-163`; GLEET attention actor / critic `gleet_agent.py:307-469` on
+`networks.py:47-356`, rollout `:293-303`; RL_PSO `PolicyNetwork` `rl_pso_agent.py:9-45`, rollout `:116-124`;
+QLPSO Q-table `qlpso_agent.py:17-48`.
 
 Module / parameter names mirror the reference so that a `state_dict` extracted from a reference pickle
 (see tests/golden/make_golden_de.py: `agents.npz`) loads with `load_reference_weights`.
@@ -43,7 +45,8 @@ def _mlp_cfg(sizes, last_act='None'):
 
 def load_reference_weights(module: nn.Module, weights: dict, prefix=''):
     """weights: {reference state_dict key: array}.  Name-mangled private attributes of the reference
-    (`_Actor__mu_net`) are mapped onto this module's public names (`mu_net`)."""
+    (`_Actor__mu_net`) are mapped onto this module's public names (`mu_net`); a module may list further
+    (reference substring -> own substring) renames in `reference_renames`."""
     own = module.state_dict()
     mapped = {}
     for k, v in weights.items():
@@ -52,6 +55,8 @@ def load_reference_weights(module: nn.Module, weights: dict, prefix=''):
         kk = k[len(prefix):]
         parts = [p.split('__', 1)[1] if p.startswith('_') and '__' in p[1:] else p for p in kk.split('.')]
         kk = '.'.join(parts)
+        for a, b in getattr(module, 'reference_renames', ()):
+            kk = kk.replace(a, b)
         if kk in own:
             mapped[kk] = torch.as_tensor(np.asarray(v)).to(own[kk].dtype).reshape(own[kk].shape)
     missing = set(own) - set(mapped)
@@ -207,3 +212,138 @@ class QLPSO_QTable(nn.Module):
         q = self.q_table
         for s, a, r, n in zip(state.tolist(), action.tolist(), reward.tolist(), next_state.tolist()):
             q[s, a] += alpha * (r + gamma * q[n].max() - q[s, a])
+
+
+# ------------------------------------------------------------------------------------------ GLEET
+class _SwarmNorm(nn.Module):
+    """The reference's 'layer' normalisation (networks.py:68-72): every lane is standardised over ALL of its [NP, E] entries
+    (unbiased variance, eps 1e-5); no affine parameters."""
+
+    def forward(self, x):
+        m = x.mean(dim=(1, 2), keepdim=True)
+        return (x - m) * torch.rsqrt(x.var(dim=(1, 2), keepdim=True) + 1e-05)
+
+
+class GLEET_AttentionBlock(nn.Module):
+    """One `MultiHeadEncoder` (networks.py:256-341): multi-head attention of the queries `q` over the particles `h` + residual on
+    `h` + swarm norm, then a 16 -> 16 -> 16 ReLU feed-forward + residual + swarm norm.  Parameters keep the reference's
+    [heads, in, key] layout (so its checkpoints load); the forward folds the heads into ONE [E, heads*key] projection per
+    operand and lets `scaled_dot_product_attention` do softmax(QK^T / sqrt(key)) V without materialising [B, heads, NP, NP]
+    in HBM when a fused backend takes it."""
+
+    def __init__(self, n_heads=4, embed_dim=16, ff_hidden=16):
+        super().__init__()
+        kd = embed_dim // n_heads
+        self.n_heads, self.embed_dim, self.key_dim = n_heads, embed_dim, kd
+        self.W_query = nn.Parameter(torch.rand(n_heads, embed_dim, kd))
+        self.W_key = nn.Parameter(torch.rand(n_heads, embed_dim, kd))
+        self.W_val = nn.Parameter(torch.rand(n_heads, embed_dim, kd))
+        self.W_out = nn.Parameter(torch.rand(n_heads, kd, embed_dim))
+        self.ff_in = nn.Linear(embed_dim, ff_hidden)
+        self.ff_out = nn.Linear(ff_hidden, embed_dim)
+        self.norm = _SwarmNorm()
+
+    def _project(self, x, W):                                   # [B, N, E] x [H, E, K] -> [B, H, N, K]
+        B, N, E = x.shape
+        return (x @ W.permute(1, 0, 2).reshape(E, -1)).view(B, N, self.n_heads, -1).transpose(1, 2)
+
+    def forward(self, h, q=None):
+        q = h if q is None else q
+        B, N, E = q.shape
+        heads = nn.functional.scaled_dot_product_attention(self._project(q, self.W_query), self._project(h, self.W_key),
+                                                           self._project(h, self.W_val))        # scale = 1/sqrt(key_dim)
+        att = heads.transpose(1, 2).reshape(B, N, -1) @ self.W_out.reshape(-1, E)
+        x = self.norm(att + h)
+        return self.norm(self.ff_out(torch.relu(self.ff_in(x))) + x)
+
+
+_GLEET_RENAMES = (('.0.MHA_sublayer.MHA.', '.'), ('.0.FFandNorm_sublayer.FF.0.', '.ff_in.'), ('.0.FFandNorm_sublayer.FF.2.', '.ff_out.'),
+                  ('embedder.embedder.', 'embedder.'), ('embedder_for_decoder.embedder.', 'embedder_for_decoder.'))
+
+
+class GLEET_Actor(nn.Module):
+    """gleet_agent.py:307-440.  state [B, NP, 27] = 9 population features | 9 exploration (pbest) | 9 exploitation (gbest) features:
+    encoder block over the embedded population features; the two 9-feature groups share the SAME embedder, are concatenated and
+    embedded again, and query the encoder output in the decoder block; per-particle mu / sigma heads 16 -> 32 -> 8 -> 1 (LeakyReLU).
+    action [B, NP] = clamp(Normal(mu, sigma).sample(), 0, 1)."""
+    node_dim, embedding_dim, max_sigma, min_sigma = 9, 16, 0.7, 0.01
+    takes_noise = True
+    reference_renames = _GLEET_RENAMES
+
+    def __init__(self):
+        super().__init__()
+        E = self.embedding_dim
+        self.embedder = nn.Linear(self.node_dim, E, bias=False)
+        self.encoder = GLEET_AttentionBlock(4, E, 16)
+        self.embedder_for_decoder = nn.Linear(2 * E, E, bias=False)
+        self.decoder = GLEET_AttentionBlock(4, E, 16)
+        cfg = [{'in': E, 'out': 32, 'drop_out': 0, 'activation': 'LeakyReLU'}, {'in': 32, 'out': 8, 'drop_out': 0, 'activation': 'LeakyReLU'},
+               {'in': 8, 'out': 1, 'drop_out': 0, 'activation': 'None'}]
+        self.mu_net = MLP(cfg)
+        self.sigma_net = MLP(cfg)
+
+    def logits(self, x):
+        """[B, NP, 27] -> decoder output [B, NP, 16] (what the reference returns for `only_critic=True` and hands to the critic)."""
+        nd = self.node_dim
+        B, N, _ = x.shape
+        em = self.embedder(x.reshape(B, N, 3, nd))                          # one GEMM for the three feature groups
+        enc = self.encoder(em[:, :, 0])
+        return self.decoder(enc, self.embedder_for_decoder(em[:, :, 1:].reshape(B, N, -1)))
+
+    def distribution(self, x):
+        lg = self.logits(x)
+        mu = (torch.tanh(self.mu_net(lg)) + 1.) / 2.
+        sigma = (torch.tanh(self.sigma_net(lg)) + 1.) / 2. * (self.max_sigma - self.min_sigma) + self.min_sigma
+        return mu.squeeze(-1), sigma.squeeze(-1), lg
+
+    def log_prob(self, x, action):
+        """Joint log-probability of the swarm's action [B, NP] (summed over the particles, :425-427); differentiable."""
+        mu, sigma, _ = self.distribution(x)
+        return torch.distributions.Normal(mu, sigma).log_prob(action).sum(-1)
+
+    @torch.no_grad()
+    def forward(self, x, noise=None):
+        """x [B, NP, 27] -> action [B, NP]; `noise` = externally drawn standard normals of the action's shape."""
+        mu, sigma, _ = self.distribution(x)
+        eps = torch.randn_like(mu) if noise is None else noise
+        return torch.clamp(mu + sigma * eps, min=0, max=1)
+
+
+class GLEET_Critic(nn.Module):
+    """gleet_agent.py:442-469: value head 16 -> 32 -> 16 -> 1 (LeakyReLU) on the particle-mean of the decoder output."""
+
+    def __init__(self):
+        super().__init__()
+        self.value_head = MLP([{'in': 16, 'out': 32, 'drop_out': 0, 'activation': 'LeakyReLU'},
+                               {'in': 32, 'out': 16, 'drop_out': 0, 'activation': 'LeakyReLU'},
+                               {'in': 16, 'out': 1, 'drop_out': 0, 'activation': 'None'}])
+
+    def forward(self, logits):
+        return self.value_head(logits.mean(dim=-2)).squeeze(-1)
+
+
+# ------------------------------------------------------------------------------------------ RL_PSO
+class RL_PSO_PolicyNet(nn.Module):
+    """rl_pso_agent.py:9-45: mu / sigma MLPs 2*dim -> 32 -> 8 -> 1 (ReLU); sigma = clamp((tanh+1)/2, 0.01, 0.7); a sample `a` with
+    |a - 0.5| >= 0.5 is replaced by (a + 3 sigma - mu) * (sigma / 6) (the reference's expression, operator precedence included)."""
+    max_sigma, min_sigma = 0.7, 0.01
+    takes_noise = True
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = int(dim)
+        cfg = _mlp_cfg([2 * self.dim, 32, 8, 1])
+        self.mu_net = MLP(cfg)
+        self.sigma_net = MLP(cfg)
+
+    def distribution(self, x):
+        mu = (torch.tanh(self.mu_net(x)) + 1.) / 2.
+        sigma = torch.clamp((torch.tanh(self.sigma_net(x)) + 1.) / 2., min=self.min_sigma, max=self.max_sigma)
+        return mu, sigma
+
+    @torch.no_grad()
+    def forward(self, x, noise=None):
+        """x [B, 2*dim] -> action [B, 1]."""
+        mu, sigma = self.distribution(x)
+        a = mu + sigma * (torch.randn_like(mu) if noise is None else noise)
+        return torch.where(torch.abs(a - 0.5) >= 0.5, (a + 3 * sigma - mu) * (1. / 6 * sigma), a)

@@ -219,6 +219,8 @@ class GLEET_Sweep(_Sweep):
         self.policy = policy
 
     def _policy(self, feat):
+        if getattr(self.policy, 'takes_noise', False):          # agent.GLEET_Actor: noise from the sweep's own generator (graph-safe)
+            return self.policy(feat, noise=self._randn(feat.shape[0], feat.shape[1]))
         return self.policy(feat)
 
 
@@ -232,6 +234,8 @@ class RL_PSO_Sweep(_Sweep):
         self.policy = policy
 
     def _policy(self, feat):
+        if getattr(self.policy, 'takes_noise', False):          # agent.RL_PSO_PolicyNet
+            return self.policy(feat, noise=self._randn(feat.shape[0], 1)).reshape(-1)
         return self.policy(feat).reshape(-1)
 
 

@@ -79,10 +79,16 @@ def deddqn_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoi
 
 
 def gleet_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
-    """One GLEET-backbone rollout with bench.py's stand-in policy (per-particle MLP 27 -> 64 -> 1, sigmoid; seed 0)."""
+    """One GLEET rollout (gleet_agent.py:293-303).  `weights` = the reference actor's state_dict (attention actor, oracle.agents.gleet_act);
+    None -> bench.py's stand-in policy (per-particle MLP 27 -> 64 -> 1, sigmoid; seed 0)."""
     from . import gleet as og
     torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(0))
+    if weights is None:
+        net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(0))
+        act = lambda st: net(torch.as_tensor(st, dtype=torch.float32)).numpy()
+    else:
+        act = lambda st: oag.gleet_act(weights, np.asarray(st, dtype=np.float32))
+    torch.manual_seed(run_seed)
     np.random.seed(run_seed)
     cfg = og.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
     nc = ob.noise_draw_count(inst)
@@ -92,7 +98,7 @@ def gleet_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoin
     R, gens, done = 0., 0, False
     with torch.no_grad():
         while not done and (max_gens is None or gens < max_gens):
-            action = net(torch.as_tensor(state, dtype=torch.float32)).numpy()
+            action = act(state)
             S, state, reward, done = og.update(cfg, S, action, ev, inst.optimum, inst.lb, inst.ub, og.NumpyTape(cfg.NP, dim, nc))
             R += float(reward)
             gens += 1

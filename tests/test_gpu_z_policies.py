@@ -1,0 +1,114 @@
+"""GPU: the GLEET attention actor and the RL_PSO policy network (metabox_b200/agent.py) on the device -- known-answer forwards of the
+unmodified reference (tests/golden/agents2.npz), agreement with the oracle's head-by-head restatement on states the fused GLEET step
+itself produced, and complete sweeps driven by these policies (CUDA-graph replay == eager launches).
+
+This file was added after round 1's GPU minutes were spent: its CPU twin (tests/test_host_cpu.py) is green, the device run is
+pending.  It sorts last so that `pytest -x` reaches every GPU test that has already been validated on a B200 first."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _weights(group):
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    return {k[len(group) + 1:]: G[k] for k in G.files if k.startswith(group + '/')}, G
+
+
+def _pack(dim=10):
+    from metabox_b200 import problem as mp
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', dim, 5)
+    return mp.InstancePack(tr.data + te.data), tr.data + te.data
+
+
+class _Mean:
+    """A policy without sampling noise (graph and eager runs become comparable bit for bit)."""
+
+    def __init__(self, net, pick):
+        self.net, self.pick = net, pick
+
+    def __call__(self, x):
+        import torch
+        return torch.clamp(self.pick(self.net.distribution(x)), 0, 1)
+
+
+def test_gleet_actor_and_rl_pso_net_known_answers_on_the_device():
+    import torch
+    from metabox_b200 import agent as ma
+    W, G = _weights('gleet')
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+    for name in ('a', 'b'):
+        x = torch.as_tensor(G[f'gleet_kat/{name}/x']).cuda()
+        with torch.no_grad():
+            mu, sigma, lg = actor.distribution(x)
+        np.testing.assert_allclose(lg.cpu().numpy(), G[f'gleet_kat/{name}/logits'], rtol=5e-4, atol=5e-5)
+        np.testing.assert_allclose(mu.cpu().numpy(), G[f'gleet_kat/{name}/mu'][..., 0], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(sigma.cpu().numpy(), G[f'gleet_kat/{name}/sigma'][..., 0], rtol=2e-4, atol=2e-5)
+        a = actor(x)
+        assert a.shape == x.shape[:2] and float(a.min()) >= 0 and float(a.max()) <= 1
+    W2, _ = _weights('rl_pso')
+    net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), W2).cuda().eval()
+    a = net(torch.as_tensor(G['rl_pso_kat/x']).cuda(), noise=torch.as_tensor(G['rl_pso_kat/eps']).cuda())
+    np.testing.assert_allclose(a.cpu().numpy(), G['rl_pso_kat/action'], rtol=1e-5, atol=1e-6)
+
+
+def test_gleet_actor_on_states_of_the_fused_step_vs_oracle_restatement():
+    """States come out of the CUDA GLEET step (Philox mode); the device actor's (mu, sigma) must agree with the oracle's head-by-head
+    float32 CPU restatement on exactly those states, generation after generation."""
+    import torch
+    from metabox_b200 import agent as ma, optimizer as mo
+    from oracle import agents as oag
+    W, G = _weights('gleet')
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+    w_cpu = oag.load_weights(G, 'gleet')
+    pack, probs = _pack()
+    eng = mo.GLEET_Engine(pack, np.arange(len(probs)), 20000, 50, seed=11)
+    feat = eng.init_population()
+    for gen in range(6):
+        with torch.no_grad():
+            mu, sigma, _ = actor.distribution(feat)
+        omu, osg, _ = oag.gleet_distribution(w_cpu, feat.cpu().numpy())
+        np.testing.assert_allclose(mu.cpu().numpy(), omu.numpy(), rtol=5e-4, atol=5e-5, err_msg=f'gen {gen}')
+        np.testing.assert_allclose(sigma.cpu().numpy(), osg.numpy(), rtol=5e-4, atol=5e-5, err_msg=f'gen {gen}')
+        feat, _, _ = eng.update(torch.clamp(mu, 0, 1))
+
+
+def test_gleet_sweep_with_the_attention_actor():
+    from metabox_b200 import agent as ma, sweep
+    W, _ = _weights('gleet')
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    mean = _Mean(actor, lambda d: d[0])
+    ra = rows(sweep.GLEET_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=True, poll=8))
+    rb = rows(sweep.GLEET_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=False, poll=8))
+    np.testing.assert_array_equal(ra, rb)
+    # sampled actions (noise from the sweep's own generator, captured with the graph): complete, monotone cost curves
+    sw = sweep.GLEET_Sweep(pack, inst, actor, 3000, 50, seed=9, graph=True, poll=8)
+    r1, r2 = rows(sw), rows(sw)
+    for r in (r1, r2):
+        assert np.all((r[:, 51] >= 3000) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] <= 3100)
+        assert np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()
+    assert not np.array_equal(r1[:, :51], r2[:, :51])            # a second sweep draws fresh action noise
+    # striped over two streams: same Philox keys per global lane; the deterministic policy gives identical rows
+    st = sweep.StripedSweep(lambda ln, lb: sweep.GLEET_Sweep(pack, ln, mean, 3000, 50, seed=9, lane_base=lb, poll=8), inst, 0, 2)
+    np.testing.assert_array_equal(rows(st), ra)
+
+
+def test_rl_pso_sweep_with_the_reference_policy_net():
+    from metabox_b200 import agent as ma, sweep
+    W, _ = _weights('rl_pso')
+    net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), W).cuda().eval()
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    mean = _Mean(net, lambda d: d[0].reshape(-1))
+    ra = rows(sweep.RL_PSO_Sweep(pack, inst, mean, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    rb = rows(sweep.RL_PSO_Sweep(pack, inst, mean, 460, 50, seed=5, graph=False, poll=50))
+    np.testing.assert_array_equal(ra, rb)
+    r = rows(sweep.RL_PSO_Sweep(pack, inst, net, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    assert np.all((r[:, 51] == 460) | (r[:, 50] <= 1e-8)) and np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()

@@ -128,6 +128,44 @@ def test_policy_forward_matches_reference_kats():
     np.testing.assert_allclose(act.numpy(), np.clip(G['lde_kat/mu'][0], 0, 1), rtol=1e-5, atol=1e-6)
 
 
+def test_gleet_and_rl_pso_policies_match_reference_kats():
+    """GLEET attention actor / critic (checkpoint 20 of the shipped rollout agents) and the RL_PSO policy network: weights + forwards of
+    the unmodified reference (tests/golden/agents2.npz, made by make_golden_agents2.py)."""
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    sub = lambda pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet/'))
+    critic = ma.load_reference_weights(ma.GLEET_Critic(), sub('gleet_critic/'))
+    assert sum(p.numel() for p in actor.parameters()) == sum(v.size for v in sub('gleet/').values())
+    assert (actor.max_sigma, actor.min_sigma) == (float(G['gleet_kat/max_sigma']), float(G['gleet_kat/min_sigma']))
+    for name in ('a', 'b'):                                            # [3, 100, 27] and a ragged swarm [2, 7, 27]
+        K = {k: torch.as_tensor(G[f'gleet_kat/{name}/{k}']) for k in ('x', 'logits', 'mu', 'sigma', 'fixed', 'logp', 'value')}
+        mu, sigma, lg = actor.distribution(K['x'])
+        np.testing.assert_allclose(lg.detach().numpy(), K['logits'].numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(mu.detach().numpy(), K['mu'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sigma.detach().numpy(), K['sigma'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
+        lp = actor.log_prob(K['x'], K['fixed'][..., 0])
+        np.testing.assert_allclose(lp.detach().numpy(), K['logp'].numpy().reshape(-1), rtol=1e-4, atol=1e-3)
+        np.testing.assert_allclose(critic(lg).detach().numpy(), K['value'].numpy().reshape(-1), rtol=1e-4, atol=1e-5)
+        a = actor(K['x'], noise=torch.zeros(K['x'].shape[:2]))
+        np.testing.assert_allclose(a.numpy(), np.clip(K['mu'].numpy()[..., 0], 0, 1), rtol=1e-4, atol=1e-5)
+        assert float(actor(K['x']).min()) >= 0 and float(actor(K['x']).max()) <= 1
+    # lanes are independent: a lane's action does not depend on its batch neighbours
+    x = torch.as_tensor(G['gleet_kat/a/x'])
+    np.testing.assert_allclose(actor.distribution(x[1:2])[0].detach().numpy(), actor.distribution(x)[0][1:2].detach().numpy(), rtol=1e-5, atol=1e-6)
+    W = sub('rl_pso/')
+    net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(W['_PolicyNetwork__mu_net.net.layer0-linear.weight'].shape[1] // 2), W)
+    assert (net.max_sigma, net.min_sigma) == (float(G['rl_pso_kat/max_sigma']), float(G['rl_pso_kat/min_sigma']))
+    x = torch.as_tensor(G['rl_pso_kat/x'])
+    mu, sigma = net.distribution(x)
+    np.testing.assert_allclose(mu.detach().numpy(), G['rl_pso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sigma.detach().numpy(), G['rl_pso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    a = net(x, noise=torch.as_tensor(G['rl_pso_kat/eps']))
+    np.testing.assert_allclose(a.numpy(), G['rl_pso_kat/action'], rtol=1e-5, atol=1e-6)          # incl. 3 out-of-range samples
+    assert a.shape == (9, 1)
+
+
 # ----------------------------------------------------------------------------------------- sharding / gather (gloo, world 2)
 def test_shard_ranges_cover_the_lane_table():
     from metabox_b200 import sweep

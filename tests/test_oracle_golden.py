@@ -434,3 +434,29 @@ def test_qlpso_steps_match_reference():
             seen_rewards.add(reward)
             S.cost[j] = G[f'{key}/row_cost'][k]; S.gbest_cost = np.float32(G[f'{key}/gbest_cost'][k])
     assert seen_rewards == {2, 1, 0, -2}
+
+
+def test_gleet_and_rl_pso_policy_restatements_match_reference():
+    """oracle.agents' head-by-head GLEET actor and the RL_PSO policy network against forwards of the unmodified reference
+    (agents2.npz), and a bounded oracle GLEET rollout driven by the attention actor (bench.py's CPU arm for --workload gleet)."""
+    import torch
+    from oracle import agents as oag, rollout as orr
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    w = oag.load_weights(G, 'gleet')
+    for name in ('a', 'b'):
+        mu, sigma, logits = oag.gleet_distribution(w, G[f'gleet_kat/{name}/x'])
+        np.testing.assert_allclose(logits.numpy(), G[f'gleet_kat/{name}/logits'], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(mu.numpy(), G[f'gleet_kat/{name}/mu'][..., 0], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sigma.numpy(), G[f'gleet_kat/{name}/sigma'][..., 0], rtol=1e-4, atol=1e-5)
+    a = oag.gleet_act(w, G['gleet_kat/a/x'][0])
+    assert a.shape == (100,) and a.dtype == np.float32 and a.min() >= 0 and a.max() <= 1
+    w2 = oag.load_weights(G, 'rl_pso')
+    mu, sigma = oag.rl_pso_distribution(w2, G['rl_pso_kat/x'])
+    np.testing.assert_allclose(mu.numpy(), G['rl_pso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sigma.numpy(), G['rl_pso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    assert oag.rl_pso_act(w2, G['rl_pso_kat/x']).shape == (9, 1)
+    tr, te = ob.make_suite('bbob', 10, 5.0)
+    r = orr.gleet_rollout((tr + te)[0], 10, 20000, w, run_seed=3, max_gens=4)
+    assert r['gens'] == 4 and r['fes'] == 500 and np.isfinite(r['cost']).all()
+    r2 = orr.gleet_rollout((tr + te)[0], 10, 20000, w, run_seed=3, max_gens=4)
+    assert r2['cost'] == r['cost']                                           # seeded -> repeatable
