@@ -48,7 +48,7 @@ def rlepso_act(w, state):
 @torch.no_grad()
 def deddqn_q(w, state):
     x = torch.as_tensor(np.asarray(state), dtype=torch.float32)
-    return _mlp(w, '', x, 5) if False else _mlp({('.' + k): v for k, v in w.items()}, '', x, 5)
+    return _mlp({('.' + k): v for k, v in w.items()}, '', x, 5)          # keys are 'net.layer<k>-linear.*' without a module prefix
 
 
 @torch.no_grad()

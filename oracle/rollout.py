@@ -137,7 +137,6 @@ def timed_sample(dim, maxFEs, weights, fids, max_gens, n_procs, suit='bbob', see
     t0 = time.perf_counter()
     if own:
         pool = make_pool(n_procs)
-        t0 = time.perf_counter() if False else t0
     if pool is None:
         res = [_worker(j) for j in jobs]
     else:
