@@ -50,8 +50,9 @@ def parse():
     ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
                     help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3; '
                          'gleet = the GLEET backbone (SURVEY 8f N1), policy chosen by --gleet-policy')
-    ap.add_argument('--gleet-policy', default='actor', choices=['actor', 'stand-in'],
-                    help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor); "
+    ap.add_argument('--gleet-policy', default='actor', choices=['actor', 'fused', 'stand-in'],
+                    help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor, torch); "
+                         'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); "
                          'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
@@ -132,7 +133,7 @@ def policy_weights(workload, gleet_policy='actor'):
     p = os.path.join(ROOT, 'tests', 'golden', 'agents.npz')
     if workload == 'gleet':
         p2 = os.path.join(ROOT, 'tests', 'golden', 'agents2.npz')
-        if gleet_policy != 'actor' or not os.path.exists(p2):
+        if gleet_policy == 'stand-in' or not os.path.exists(p2):
             return None, 'stand-in per-particle MLP 27->64->1 (random init, seed 0)'
         G = np.load(p2)
         return ({k[len('gleet/'):]: np.asarray(G[k]) for k in G.files if k.startswith('gleet/')},
@@ -201,14 +202,17 @@ def build_policy(workload, dev, NP, gleet_policy='actor'):
     import torch
     from metabox_b200 import agent as magent
     torch.manual_seed(0)
-    if workload == 'gleet' and gleet_policy == 'actor':
+    if workload == 'gleet' and gleet_policy in ('actor', 'fused'):
         net = magent.GLEET_Actor()
-        w_np, wsrc = policy_weights(workload, gleet_policy)
+        w_np, wsrc = policy_weights(workload, 'actor')
         if w_np:
             magent.load_reference_weights(net, w_np)
         else:
             wsrc = 'GLEET attention actor, random init (seed 0)'
-        return net.to(dev).eval(), wsrc
+        net = net.to(dev).eval()
+        if gleet_policy == 'fused':
+            return magent.GLEET_FusedActor(net), wsrc + ', fused policy kernel (mbx_gleet_policy)'
+        return net, wsrc + ', torch module'
     if workload == 'gleet':
         # any torch callable state[B,NP,27] -> action[B,NP] plugs in: a small per-particle MLP with a sigmoid head
         net = torch.nn.Sequential(torch.nn.Linear(27, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1), torch.nn.Sigmoid(), torch.nn.Flatten(1))

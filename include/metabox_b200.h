@@ -331,6 +331,23 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
                            double* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * GLEET attention actor, rollout forward -- replaces `Actor.forward` (agent/gleet_agent.py:386-440, called once per
+ * generation from `rollout_episode`, :293-303) on agent/networks.py:47-356 for B swarms at once: embedder, encoder block
+ * (4-head self-attention over the swarm, whole-swarm normalisation, feed-forward), decoder block (the exploration /
+ * exploitation feature groups query the encoder output), mu / sigma heads, action = clamp(mu + sigma * noise, 0, 1).
+ *   d_state   [B,NP,27] f32   the state mbx_gleet_init / mbx_gleet_step write
+ *   d_weights [mbx_gleet_policy_weight_count()] f32, 16-byte aligned, packed as documented in
+ *             metabox_b200/csrc/mbx_gleet_policy.cuh (metabox_b200/agent.py GLEET_Actor.pack() produces it from the reference's
+ *             state_dict); read on every launch, so an optimiser may update it in place between launches
+ *   d_noise   [B,NP] f32 standard-normal draws, or null (action = clamp(mu, 0, 1))
+ *   outputs:  d_action [B,NP] f32 ; optional (null to skip) d_mu [B,NP], d_sigma [B,NP], d_logits [B,NP,16] (the decoder output
+ *             the reference hands to its critic, `to_critic=True`)
+ *   NP <= 128.                                                                                                     */
+int mbx_gleet_policy_weight_count(void);
+int mbx_gleet_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                     float* d_mu, float* d_sigma, float* d_logits, int B, int NP, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

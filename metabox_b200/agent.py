@@ -308,6 +308,72 @@ class GLEET_Actor(nn.Module):
         eps = torch.randn_like(mu) if noise is None else noise
         return torch.clamp(mu + sigma * eps, min=0, max=1)
 
+    @torch.no_grad()
+    def pack(self, out=None):
+        """All parameters as ONE float32 vector in the layout `mbx_gleet_policy` reads (metabox_b200/csrc/mbx_gleet_policy.cuh):
+        embedder^T | encoder block | embedder_for_decoder | decoder block | mu head | sigma head, the per-head attention matrices
+        folded into [16 in][head*4 + k] / [head*4 + k][16 out], every piece starting on a multiple of 4 floats."""
+        def block(b):
+            fold = lambda W: W.permute(1, 0, 2).reshape(self.embedding_dim, -1)
+            return [fold(b.W_query), fold(b.W_key), fold(b.W_val), b.W_out.reshape(-1, self.embedding_dim),
+                    b.ff_in.weight, b.ff_in.bias, b.ff_out.weight, b.ff_out.bias]
+
+        def head(m):
+            lin = [mod for mod in m.net if isinstance(mod, nn.Linear)]
+            return [t for l in lin for t in (l.weight, l.bias)] + [torch.zeros(3, device=lin[0].weight.device)]
+
+        parts = [self.embedder.weight.t()] + block(self.encoder) + [self.embedder_for_decoder.weight] + block(self.decoder) \
+            + head(self.mu_net) + head(self.sigma_net)
+        flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for t in parts])
+        if out is None:
+            return flat.contiguous()
+        out.copy_(flat)
+        return out
+
+
+class GLEET_FusedActor:
+    """`GLEET_Actor`'s rollout forward as ONE CUDA kernel per generation (C ABI `mbx_gleet_policy`, csrc/mbx_gleet_policy.cu): one CTA
+    per swarm, keys / values and weights in shared memory.  Same call convention as the torch module
+    (`policy(state [B,NP,27], noise=None) -> action [B,NP]`, `takes_noise`), so it plugs into `sweep.GLEET_Sweep` / `tester`.  The packed
+    weights are a device buffer the kernel reads on every launch: after an optimiser step on `actor`, call `refresh()` (an in-place
+    copy, so CUDA graphs that captured the launch see the new weights)."""
+    takes_noise = True
+
+    def __init__(self, actor: 'GLEET_Actor'):
+        from . import _lib
+        self.actor = actor
+        self.packed = actor.pack()
+        n = _lib.lib().mbx_gleet_policy_weight_count()
+        if self.packed.numel() != n:
+            raise _lib.MbxError(f'GLEET_Actor.pack() produced {self.packed.numel()} weights, libmbx.so expects {n}')
+        if not self.packed.is_cuda:
+            raise _lib.MbxError('GLEET_FusedActor needs the actor on a CUDA device (there is no CPU path)')
+
+    def refresh(self):
+        self.actor.pack(out=self.packed)
+        return self
+
+    @torch.no_grad()
+    def __call__(self, x, noise=None, outputs=False):
+        """-> action [B,NP]; with `outputs=True` -> (action, mu [B,NP], sigma [B,NP], decoder logits [B,NP,16])."""
+        from . import _lib
+        if x.dim() != 3 or x.shape[2] != 27 or x.dtype != torch.float32 or x.device != self.packed.device:
+            raise ValueError(f'state must be float32 [B, NP, 27] on {self.packed.device}: got {x.dtype} {tuple(x.shape)} on {x.device}')
+        x = x.contiguous()
+        B, NP, _ = x.shape
+        if noise is not None:
+            noise = noise.to(torch.float32).reshape(B, NP).contiguous()
+        action = torch.empty(B, NP, dtype=torch.float32, device=x.device)
+        mu = sigma = logits = None
+        if outputs:
+            mu, sigma = torch.empty_like(action), torch.empty_like(action)
+            logits = torch.empty(B, NP, 16, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().mbx_gleet_policy(_lib.ptr(x), _lib.ptr(self.packed), self.packed.numel(), _lib.ptr(noise), _lib.ptr(action),
+                                             _lib.ptr(mu), _lib.ptr(sigma), _lib.ptr(logits), B, NP, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_gleet_policy')
+        return (action, mu, sigma, logits) if outputs else action
+
 
 class GLEET_Critic(nn.Module):
     """gleet_agent.py:442-469: value head 16 -> 32 -> 16 -> 1 (LeakyReLU) on the particle-mean of the decoder output."""

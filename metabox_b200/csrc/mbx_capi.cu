@@ -1,6 +1,8 @@
 // mbx_capi.cu -- the extern "C" boundary declared in include/metabox_b200.h.
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
+#include "mbx_gleet_policy.cuh"
 #include "mbx_launch.h"
 
 static thread_local char g_err[512] = "";
@@ -165,6 +167,20 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
     if (B == 0) return MBX_OK;
     MBX_REQUIRE(d_sample && d_cost && d_out, "mbx_landscape_features: null pointer");
     return mbx_launch_landscape(d_sample, d_cost, d_ref, B, S, D, d_out, (cudaStream_t)stream);
+}
+
+
+int mbx_gleet_policy_weight_count(void) { return glp::N_WEIGHTS; }
+
+int mbx_gleet_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                     float* d_mu, float* d_sigma, float* d_logits, int B, int NP, void* stream) {
+    MBX_REQUIRE(B >= 0 && NP >= 1 && NP <= 128, "mbx_gleet_policy: bad shape B=%d NP=%d (1 <= NP <= 128)", B, NP);
+    MBX_REQUIRE(n_weights == glp::N_WEIGHTS, "mbx_gleet_policy: %d packed weights, expected %d", n_weights, glp::N_WEIGHTS);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_state && d_weights && d_action, "mbx_gleet_policy: null pointer");
+    MBX_REQUIRE(((uintptr_t)d_weights & 15) == 0 && (!d_logits || ((uintptr_t)d_logits & 15) == 0),
+                "mbx_gleet_policy: d_weights / d_logits must be 16-byte aligned");
+    return mbx_launch_gleet_policy(d_state, d_weights, d_noise, d_action, d_mu, d_sigma, d_logits, B, NP, (cudaStream_t)stream);
 }
 
 

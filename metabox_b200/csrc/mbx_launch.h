@@ -58,3 +58,5 @@ int mbx_launch_rl_pso_init(int kind, const MbxInstance* inst, const double* cons
 int mbx_launch_rl_pso_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                            const MbxRunConfig* cfg, const MbxRlPsoState* s, const MbxRlPsoTape* tape, const float* action,
                            float* state, float* reward, int B, cudaStream_t st);
+int mbx_launch_gleet_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
+                            float* logits, int B, int NP, cudaStream_t st);

@@ -6,6 +6,9 @@ gleet/*      state_dict of `GLEET_Agent.actor` (src/agent/gleet_agent.py:307-440
              `agent_model/rollout/bbob_easy/GLEET_Agent`; gleet_critic/* the critic (:442-469)
 gleet_kat/*  the UNMODIFIED reference actor evaluated on seeded [B, NP, 27] states: decoder logits (`only_critic=True`), mu, sigma,
              log-probability of a fixed action, critic value
+gleet0/*, gleet0_kat/*   the same for checkpoint 0 (the freshly initialised actor, whose mu / sigma heads are not saturated -- the trained
+             checkpoint answers mu ~ 1, sigma ~ 0.7 almost everywhere, which pins the attention stack but hardly the heads); case 'r' of
+             both KAT groups uses states the reference GLEET_Optimizer itself produced (tests/golden/gleet.npz)
 rl_pso/*     state_dict of `RL_PSO_Agent`'s PolicyNetwork (src/agent/rl_pso_agent.py:9-45) from `agent_model/test/bbob_easy`
 rl_pso_kat/* mu / sigma for seeded [B, 2*dim] states (dim 10: the shipped weights are dimension-specific), plus the
              reference's out-of-range action transformation evaluated on hand-built samples
@@ -31,31 +34,39 @@ def _load(path):
         return pickle.load(f)
 
 
+def _gleet(out, g, grp, ckpt, real):
+    ag = _load(f'rollout/bbob_easy/GLEET_Agent/checkpoint{ckpt}.pkl')
+    actor, critic = ag.actor.cpu().float(), ag.critic.cpu().float()
+    for k, v in actor.state_dict().items():
+        out[grp + '/' + k] = v.numpy()
+    for k, v in critic.state_dict().items():
+        out[grp + '_critic/' + k] = v.numpy()
+    for name, B, NP in (('a', 3, 100), ('b', 2, 7), ('r', len(real), real.shape[1])):
+        st = g.rand(B, NP, 27).astype(np.float32)
+        st[..., 0] = g.rand(B, NP) * 3.0                       # cost features are not confined to [0, 1]
+        x = torch.as_tensor(real if name == 'r' else st)
+        logits = actor(x, only_critic=True)
+        mu = (torch.tanh(actor.mu_net(logits)) + 1.) / 2.
+        sigma = (torch.tanh(actor.sigma_net(logits)) + 1.) / 2. * (actor.max_sigma - actor.min_sigma) + actor.min_sigma
+        fixed = torch.as_tensor(g.rand(B, NP, 1).astype(np.float32))
+        _, logp, to_critic = actor(x, fixed_action=fixed, to_critic=True)
+        value = critic(to_critic)[0]
+        for k, v in dict(x=x, logits=logits, mu=mu, sigma=sigma, fixed=fixed, logp=logp, value=value).items():
+            out[f'{grp}_kat/{name}/{k}'] = v.numpy()
+    out[grp + '_kat/max_sigma'] = np.float64(actor.max_sigma); out[grp + '_kat/min_sigma'] = np.float64(actor.min_sigma)
+    print(grp, 'mu range on reference-produced states', float(out[f'{grp}_kat/r/mu'].min()), float(out[f'{grp}_kat/r/mu'].max()),
+          'sigma', float(out[f'{grp}_kat/r/sigma'].min()), float(out[f'{grp}_kat/r/sigma'].max()))
+
+
 def main():
     out = dict(meta=str(dict(numpy=np.__version__, torch=torch.__version__)))
     g = np.random.RandomState(5)
     with torch.no_grad():
         # ------------------------------------------------------------------ GLEET
-        ag = _load('rollout/bbob_easy/GLEET_Agent/checkpoint20.pkl')
-        actor, critic = ag.actor.cpu().double(), ag.critic.cpu().double()
-        for k, v in actor.state_dict().items():
-            out['gleet/' + k] = v.numpy().astype(np.float32)
-        for k, v in critic.state_dict().items():
-            out['gleet_critic/' + k] = v.numpy().astype(np.float32)
-        actor, critic = actor.float(), critic.float()
-        for name, B, NP in (('a', 3, 100), ('b', 2, 7)):
-            st = g.rand(B, NP, 27).astype(np.float32)
-            st[..., 0] = g.rand(B, NP) * 3.0                       # cost features are not confined to [0, 1]
-            x = torch.as_tensor(st)
-            logits = actor(x, only_critic=True)
-            mu = (torch.tanh(actor.mu_net(logits)) + 1.) / 2.
-            sigma = (torch.tanh(actor.sigma_net(logits)) + 1.) / 2. * (actor.max_sigma - actor.min_sigma) + actor.min_sigma
-            fixed = torch.as_tensor(g.rand(B, NP, 1).astype(np.float32))
-            _, logp, to_critic = actor(x, fixed_action=fixed, to_critic=True)
-            value = critic(to_critic)[0]
-            for k, v in dict(x=x, logits=logits, mu=mu, sigma=sigma, fixed=fixed, logp=logp, value=value).items():
-                out[f'gleet_kat/{name}/{k}'] = v.numpy()
-        out['gleet_kat/max_sigma'] = np.float64(actor.max_sigma); out['gleet_kat/min_sigma'] = np.float64(actor.min_sigma)
+        GS = np.load(os.path.join(HERE, 'gleet.npz'))
+        real = np.stack([GS[f'{c}/s{k}/state'] for c, k in (('f1_d10', 0), ('f3_d10', 3), ('f15_d30', 1), ('f21_d10', 2))]).astype(np.float32)
+        _gleet(out, g, 'gleet', 20, real)
+        _gleet(out, g, 'gleet0', 0, real)
         # ------------------------------------------------------------------ RL_PSO
         ag = _load('test/bbob_easy/RL_PSO_Agent.pkl')
         net = ag._RL_PSO_Agent__nets.cpu()
@@ -75,8 +86,7 @@ def main():
             out['rl_pso_kat/' + k] = v.numpy()
         out['rl_pso_kat/max_sigma'] = np.float64(net._PolicyNetwork__max_sigma); out['rl_pso_kat/min_sigma'] = np.float64(net._PolicyNetwork__min_sigma)
     np.savez_compressed(os.path.join(HERE, 'agents2.npz'), **out)
-    print({k: getattr(v, 'shape', None) for k, v in out.items() if k.startswith(('gleet/', 'gleet_critic/', 'rl_pso/'))})
-    print('filtered samples:', int(filt.sum()), 'of', filt.numel())
+    print('rl_pso mu', mu.min().item(), mu.max().item(), 'sigma', sigma.min().item(), sigma.max().item(), 'filtered samples:', int(filt.sum()), 'of', filt.numel())
 
 
 if __name__ == '__main__':

@@ -2,8 +2,10 @@
 unmodified reference (tests/golden/agents2.npz), agreement with the oracle's head-by-head restatement on states the fused GLEET step
 itself produced, and complete sweeps driven by these policies (CUDA-graph replay == eager launches).
 
-This file was added after round 1's GPU minutes were spent: its CPU twin (tests/test_host_cpu.py) is green, the device run is
-pending.  It sorts last so that `pytest -x` reaches every GPU test that has already been validated on a B200 first."""
+The torch-module tests ran green on a B200 (profiles/r1i_gpu_policies_tests.log).  The tests of the FUSED policy kernel
+(`mbx_gleet_policy`, second half of this file) were written after round 1's GPU minutes were spent: the kernel's per-particle
+arithmetic is verified on the host (tests/test_host_cpu.py compiles the same device header with g++), its device run is pending.
+The file sorts last so that `pytest -x` reaches every GPU test that has already been validated on a B200 first."""
 import os
 
 import numpy as np
@@ -38,17 +40,18 @@ class _Mean:
 def test_gleet_actor_and_rl_pso_net_known_answers_on_the_device():
     import torch
     from metabox_b200 import agent as ma
-    W, G = _weights('gleet')
-    actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
-    for name in ('a', 'b'):
-        x = torch.as_tensor(G[f'gleet_kat/{name}/x']).cuda()
-        with torch.no_grad():
-            mu, sigma, lg = actor.distribution(x)
-        np.testing.assert_allclose(lg.cpu().numpy(), G[f'gleet_kat/{name}/logits'], rtol=5e-4, atol=5e-5)
-        np.testing.assert_allclose(mu.cpu().numpy(), G[f'gleet_kat/{name}/mu'][..., 0], rtol=2e-4, atol=2e-5)
-        np.testing.assert_allclose(sigma.cpu().numpy(), G[f'gleet_kat/{name}/sigma'][..., 0], rtol=2e-4, atol=2e-5)
-        a = actor(x)
-        assert a.shape == x.shape[:2] and float(a.min()) >= 0 and float(a.max()) <= 1
+    for grp in ('gleet', 'gleet0'):
+        W, G = _weights(grp)
+        actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+        for name in ('a', 'b', 'r'):
+            x = torch.as_tensor(G[f'{grp}_kat/{name}/x']).cuda()
+            with torch.no_grad():
+                mu, sigma, lg = actor.distribution(x)
+            np.testing.assert_allclose(lg.cpu().numpy(), G[f'{grp}_kat/{name}/logits'], rtol=5e-4, atol=5e-5)
+            np.testing.assert_allclose(mu.cpu().numpy(), G[f'{grp}_kat/{name}/mu'][..., 0], rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(sigma.cpu().numpy(), G[f'{grp}_kat/{name}/sigma'][..., 0], rtol=2e-4, atol=2e-5)
+            a = actor(x)
+            assert a.shape == x.shape[:2] and float(a.min()) >= 0 and float(a.max()) <= 1
     W2, _ = _weights('rl_pso')
     net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), W2).cuda().eval()
     a = net(torch.as_tensor(G['rl_pso_kat/x']).cuda(), noise=torch.as_tensor(G['rl_pso_kat/eps']).cuda())
@@ -112,3 +115,76 @@ def test_rl_pso_sweep_with_the_reference_policy_net():
     np.testing.assert_array_equal(ra, rb)
     r = rows(sweep.RL_PSO_Sweep(pack, inst, net, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
     assert np.all((r[:, 51] == 460) | (r[:, 50] <= 1e-8)) and np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused policy kernel (mbx_gleet_policy)
+def test_fused_gleet_policy_kernel_known_answers_and_torch_module():
+    """One CTA per swarm: against forwards of the unmodified reference (both checkpoints; random, ragged and reference-produced states) and
+    against the torch module on the device under the same action noise."""
+    import torch
+    from metabox_b200 import agent as ma
+    g = torch.Generator(device='cpu').manual_seed(4)
+    for grp in ('gleet', 'gleet0'):
+        W, G = _weights(grp)
+        actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+        fused = ma.GLEET_FusedActor(actor)
+        for name in ('a', 'b', 'r'):
+            x = torch.as_tensor(G[f'{grp}_kat/{name}/x']).cuda()
+            noise = torch.randn(x.shape[:2], generator=g).cuda()
+            act, mu, sigma, lg = fused(x, noise=noise, outputs=True)
+            np.testing.assert_allclose(lg.cpu().numpy(), G[f'{grp}_kat/{name}/logits'], rtol=2e-4, atol=3e-5)
+            np.testing.assert_allclose(mu.cpu().numpy(), G[f'{grp}_kat/{name}/mu'][..., 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sigma.cpu().numpy(), G[f'{grp}_kat/{name}/sigma'][..., 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(act.cpu().numpy(), actor(x, noise=noise).cpu().numpy(), rtol=2e-4, atol=3e-5)
+            assert torch.equal(fused(x, noise=noise), act)                                 # outputs are optional, the action is the same
+            assert torch.equal(fused(x), torch.clamp(mu, 0, 1))                            # null noise -> the mean action
+
+
+def test_fused_gleet_policy_kernel_edge_sizes_errors_and_refresh():
+    import torch
+    from metabox_b200 import _lib, agent as ma
+    W, _ = _weights('gleet0')
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval()
+    fused = ma.GLEET_FusedActor(actor)
+    g = torch.Generator(device='cpu').manual_seed(8)
+    for B, NP in ((1, 1), (3, 2), (2, 5), (5, 37), (2, 128), (700, 100)):
+        x = torch.rand(B, NP, 27, generator=g).cuda()
+        act, mu, sigma, lg = fused(x, outputs=True)
+        with torch.no_grad():
+            m2, s2, l2 = actor.distribution(x)
+        np.testing.assert_allclose(lg.cpu().numpy(), l2.cpu().numpy(), rtol=5e-4, atol=5e-5, err_msg=f'B {B} NP {NP}')
+        np.testing.assert_allclose(mu.cpu().numpy(), m2.cpu().numpy(), rtol=2e-4, atol=2e-5, err_msg=f'B {B} NP {NP}')
+        np.testing.assert_allclose(sigma.cpu().numpy(), s2.cpu().numpy(), rtol=2e-4, atol=2e-5, err_msg=f'B {B} NP {NP}')
+    assert fused(torch.zeros(0, 100, 27).cuda()).shape == (0, 100)                         # empty batch: nothing to launch
+    with pytest.raises(_lib.MbxError):
+        fused(torch.zeros(1, 129, 27).cuda())
+    with pytest.raises(ValueError):
+        fused(torch.zeros(1, 100, 26).cuda())
+    with pytest.raises(ValueError):
+        fused(torch.zeros(1, 100, 27, dtype=torch.float64).cuda())
+    # the kernel reads the packed buffer on every launch: refresh() after a parameter update changes the next action
+    x = torch.rand(4, 100, 27, generator=g).cuda()
+    before = fused(x).clone()
+    with torch.no_grad():
+        actor.mu_net.net[-1].bias.add_(0.5)
+    assert torch.equal(fused(x), before)
+    after = fused.refresh()(x)
+    assert not torch.equal(after, before)
+    np.testing.assert_allclose(after.cpu().numpy(), actor(x, noise=torch.zeros(4, 100).cuda()).cpu().numpy(), rtol=2e-4, atol=3e-5)
+
+
+def test_gleet_sweep_with_the_fused_policy_kernel():
+    """Complete GLEET rollouts with fused step + fused policy: graph replay == eager launches (mean actions), sampled sweeps are sane."""
+    from metabox_b200 import agent as ma, sweep
+    W, _ = _weights('gleet')
+    fused = ma.GLEET_FusedActor(ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval())
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    mean = lambda st: fused(st)                                                          # no noise -> deterministic
+    ra = rows(sweep.GLEET_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=True, poll=8))
+    rb = rows(sweep.GLEET_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=False, poll=8))
+    np.testing.assert_array_equal(ra, rb)
+    r = rows(sweep.GLEET_Sweep(pack, inst, fused, 3000, 50, seed=9, graph=True, poll=8))
+    assert np.all((r[:, 51] >= 3000) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] <= 3100)
+    assert np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()

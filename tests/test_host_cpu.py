@@ -129,28 +129,31 @@ def test_policy_forward_matches_reference_kats():
 
 
 def test_gleet_and_rl_pso_policies_match_reference_kats():
-    """GLEET attention actor / critic (checkpoint 20 of the shipped rollout agents) and the RL_PSO policy network: weights + forwards of
-    the unmodified reference (tests/golden/agents2.npz, made by make_golden_agents2.py)."""
+    """GLEET attention actor / critic (checkpoints 20 and 0 of the shipped rollout agents) and the RL_PSO policy network: weights +
+    forwards of the unmodified reference (tests/golden/agents2.npz, made by make_golden_agents2.py).  Case 'r' = states the reference
+    GLEET_Optimizer produced; checkpoint 0 keeps mu / sigma away from saturation, so the heads are pinned too."""
     import torch
     from metabox_b200 import agent as ma
     G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
     sub = lambda pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
-    actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet/'))
-    critic = ma.load_reference_weights(ma.GLEET_Critic(), sub('gleet_critic/'))
-    assert sum(p.numel() for p in actor.parameters()) == sum(v.size for v in sub('gleet/').values())
-    assert (actor.max_sigma, actor.min_sigma) == (float(G['gleet_kat/max_sigma']), float(G['gleet_kat/min_sigma']))
-    for name in ('a', 'b'):                                            # [3, 100, 27] and a ragged swarm [2, 7, 27]
-        K = {k: torch.as_tensor(G[f'gleet_kat/{name}/{k}']) for k in ('x', 'logits', 'mu', 'sigma', 'fixed', 'logp', 'value')}
-        mu, sigma, lg = actor.distribution(K['x'])
-        np.testing.assert_allclose(lg.detach().numpy(), K['logits'].numpy(), rtol=2e-4, atol=2e-5)
-        np.testing.assert_allclose(mu.detach().numpy(), K['mu'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
-        np.testing.assert_allclose(sigma.detach().numpy(), K['sigma'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
-        lp = actor.log_prob(K['x'], K['fixed'][..., 0])
-        np.testing.assert_allclose(lp.detach().numpy(), K['logp'].numpy().reshape(-1), rtol=1e-4, atol=1e-3)
-        np.testing.assert_allclose(critic(lg).detach().numpy(), K['value'].numpy().reshape(-1), rtol=1e-4, atol=1e-5)
-        a = actor(K['x'], noise=torch.zeros(K['x'].shape[:2]))
-        np.testing.assert_allclose(a.numpy(), np.clip(K['mu'].numpy()[..., 0], 0, 1), rtol=1e-4, atol=1e-5)
-        assert float(actor(K['x']).min()) >= 0 and float(actor(K['x']).max()) <= 1
+    for grp in ('gleet', 'gleet0'):
+        actor = ma.load_reference_weights(ma.GLEET_Actor(), sub(grp + '/'))
+        critic = ma.load_reference_weights(ma.GLEET_Critic(), sub(grp + '_critic/'))
+        assert sum(p.numel() for p in actor.parameters()) == sum(v.size for v in sub(grp + '/').values())
+        assert (actor.max_sigma, actor.min_sigma) == (float(G[grp + '_kat/max_sigma']), float(G[grp + '_kat/min_sigma']))
+        for name in ('a', 'b', 'r'):                                   # [3, 100, 27], a ragged swarm [2, 7, 27], reference states [4, 100, 27]
+            K = {k: torch.as_tensor(G[f'{grp}_kat/{name}/{k}']) for k in ('x', 'logits', 'mu', 'sigma', 'fixed', 'logp', 'value')}
+            mu, sigma, lg = actor.distribution(K['x'])
+            np.testing.assert_allclose(lg.detach().numpy(), K['logits'].numpy(), rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(mu.detach().numpy(), K['mu'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sigma.detach().numpy(), K['sigma'].numpy()[..., 0], rtol=1e-4, atol=1e-5)
+            lp = actor.log_prob(K['x'], K['fixed'][..., 0])
+            np.testing.assert_allclose(lp.detach().numpy(), K['logp'].numpy().reshape(-1), rtol=1e-4, atol=1e-3)
+            np.testing.assert_allclose(critic(lg).detach().numpy(), K['value'].numpy().reshape(-1), rtol=1e-4, atol=1e-5)
+            a = actor(K['x'], noise=torch.zeros(K['x'].shape[:2]))
+            np.testing.assert_allclose(a.numpy(), np.clip(K['mu'].numpy()[..., 0], 0, 1), rtol=1e-4, atol=1e-5)
+            assert float(actor(K['x']).min()) >= 0 and float(actor(K['x']).max()) <= 1
+    assert float(np.ptp(G['gleet0_kat/r/mu'])) > 0.1 and float(G['gleet0_kat/r/sigma'].max()) < 0.6       # unsaturated heads
     # lanes are independent: a lane's action does not depend on its batch neighbours
     x = torch.as_tensor(G['gleet_kat/a/x'])
     np.testing.assert_allclose(actor.distribution(x[1:2])[0].detach().numpy(), actor.distribution(x)[0][1:2].detach().numpy(), rtol=1e-5, atol=1e-6)
@@ -164,6 +167,74 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
     a = net(x, noise=torch.as_tensor(G['rl_pso_kat/eps']))
     np.testing.assert_allclose(a.numpy(), G['rl_pso_kat/action'], rtol=1e-5, atol=1e-6)          # incl. 3 out-of-range samples
     assert a.shape == (9, 1)
+
+
+def _emul_lib(tmp_path_factory=None):
+    """g++ build of tests/emul/gleet_policy_host.cpp (the device header compiled for the host); cached per session in a temp dir."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    if not hasattr(_emul_lib, 'lib'):
+        d = tempfile.mkdtemp(prefix='mbx_emul_')
+        so = os.path.join(d, 'glp_host.so')
+        src = os.path.join(os.path.dirname(__file__), 'emul', 'gleet_policy_host.cpp')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', src, '-o', so], check=True)
+        L = C.CDLL(so)
+        fp = C.POINTER(C.c_float)
+        L.glp_host_forward.restype = C.c_int
+        L.glp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
+        _emul_lib.lib = L
+    return _emul_lib.lib
+
+
+def _emul_forward(w, x, noise=None):
+    import ctypes as C
+    L = _emul_lib()
+    fp = C.POINTER(C.c_float)
+    x = np.ascontiguousarray(x, dtype=np.float32); w = np.ascontiguousarray(w, dtype=np.float32)
+    B, NP, _ = x.shape
+    act = np.empty((B, NP), np.float32); mu = np.empty_like(act); sg = np.empty_like(act); lg = np.empty((B, NP, 16), np.float32)
+    nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32)
+    rc = L.glp_host_forward(x.ctypes.data_as(fp), w.ctypes.data_as(fp), None if nz is None else nz.ctypes.data_as(fp), act.ctypes.data_as(fp),
+                            mu.ctypes.data_as(fp), sg.ctypes.data_as(fp), lg.ctypes.data_as(fp), B, NP)
+    assert rc == 0
+    return act, mu, sg, lg
+
+
+def test_fused_gleet_policy_arithmetic_on_the_host_matches_the_reference():
+    """The per-particle device functions of the fused GLEET policy kernel (csrc/mbx_gleet_policy.cuh) compiled for the host, driven in the
+    kernel's phase order, with the weights packed by GLEET_Actor.pack(): against forwards of the unmodified reference (both checkpoints,
+    random / ragged / reference-produced states) and against the torch module under action noise."""
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    sub = lambda pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    assert _emul_lib().glp_host_weight_count() == 5432
+    g = np.random.RandomState(2)
+    for grp in ('gleet', 'gleet0'):
+        actor = ma.load_reference_weights(ma.GLEET_Actor(), sub(grp + '/'))
+        w = actor.pack().numpy()
+        assert w.shape == (5432,) and w.dtype == np.float32
+        for name in ('a', 'b', 'r'):
+            x = G[f'{grp}_kat/{name}/x']
+            noise = g.randn(*x.shape[:2]).astype(np.float32)
+            act, mu, sg, lg = _emul_forward(w, x, noise)
+            np.testing.assert_allclose(lg, G[f'{grp}_kat/{name}/logits'], rtol=2e-4, atol=3e-5)
+            np.testing.assert_allclose(mu, G[f'{grp}_kat/{name}/mu'][..., 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sg, G[f'{grp}_kat/{name}/sigma'][..., 0], rtol=1e-4, atol=1e-5)
+            want = actor(torch.as_tensor(x), noise=torch.as_tensor(noise)).numpy()
+            np.testing.assert_allclose(act, want, rtol=1e-4, atol=2e-5)
+            assert act.min() >= 0 and act.max() <= 1
+            np.testing.assert_allclose(_emul_forward(w, x)[0], np.clip(mu, 0, 1), rtol=0, atol=0)        # null noise -> the mean action
+    # edge swarm sizes (1 particle: the unbiased variance has 15 degrees of freedom; 128 = the kernel's maximum)
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet0/'))
+    for NP in (1, 2, 37, 128):
+        x = g.rand(2, NP, 27).astype(np.float32)
+        act, mu, sg, lg = _emul_forward(actor.pack().numpy(), x)
+        m2, s2, l2 = actor.distribution(torch.as_tensor(x))
+        np.testing.assert_allclose(lg, l2.detach().numpy(), rtol=2e-4, atol=3e-5)
+        np.testing.assert_allclose(mu, m2.detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sg, s2.detach().numpy(), rtol=1e-4, atol=1e-5)
 
 
 # ----------------------------------------------------------------------------------------- sharding / gather (gloo, world 2)

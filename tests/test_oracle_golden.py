@@ -442,12 +442,13 @@ def test_gleet_and_rl_pso_policy_restatements_match_reference():
     import torch
     from oracle import agents as oag, rollout as orr
     G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
-    w = oag.load_weights(G, 'gleet')
-    for name in ('a', 'b'):
-        mu, sigma, logits = oag.gleet_distribution(w, G[f'gleet_kat/{name}/x'])
-        np.testing.assert_allclose(logits.numpy(), G[f'gleet_kat/{name}/logits'], rtol=2e-4, atol=2e-5)
-        np.testing.assert_allclose(mu.numpy(), G[f'gleet_kat/{name}/mu'][..., 0], rtol=1e-4, atol=1e-5)
-        np.testing.assert_allclose(sigma.numpy(), G[f'gleet_kat/{name}/sigma'][..., 0], rtol=1e-4, atol=1e-5)
+    for grp in ('gleet0', 'gleet'):
+        w = oag.load_weights(G, grp)
+        for name in ('a', 'b', 'r'):
+            mu, sigma, logits = oag.gleet_distribution(w, G[f'{grp}_kat/{name}/x'])
+            np.testing.assert_allclose(logits.numpy(), G[f'{grp}_kat/{name}/logits'], rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(mu.numpy(), G[f'{grp}_kat/{name}/mu'][..., 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sigma.numpy(), G[f'{grp}_kat/{name}/sigma'][..., 0], rtol=1e-4, atol=1e-5)
     a = oag.gleet_act(w, G['gleet_kat/a/x'][0])
     assert a.shape == (100,) and a.dtype == np.float32 and a.min() >= 0 and a.max() <= 1
     w2 = oag.load_weights(G, 'rl_pso')
