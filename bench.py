@@ -52,7 +52,7 @@ def parse():
                          'gleet = the GLEET backbone (SURVEY 8f N1), policy chosen by --gleet-policy')
     ap.add_argument('--gleet-policy', default='actor', choices=['actor', 'fused', 'stand-in'],
                     help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor, torch); "
-                         'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); "
+                         'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); '
                          'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
