@@ -169,7 +169,7 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
     assert a.shape == (9, 1)
 
 
-def _emul_lib(tmp_path_factory=None):
+def _emul_lib():
     """g++ build of tests/emul/gleet_policy_host.cpp (the device header compiled for the host); cached per session in a temp dir."""
     import ctypes as C
     import subprocess
@@ -546,3 +546,38 @@ def test_qlpso_qtable_policy_on_cpu():
         ref[s][act] += 0.7 * (r + 0.8 * ref[nx].max() - ref[s][act])
     q.td_update(torch.tensor([0, 3, 0]), torch.tensor([1, 2, 1]), torch.tensor([2., -2., 1.]), torch.tensor([3, 0, 0]), alpha=0.7)
     np.testing.assert_allclose(q.q_table.numpy(), ref, rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------- bench.py contract (CPU side)
+@pytest.mark.parametrize('workload', ['rlepso', 'gleet'])
+def test_bench_reference_arm_prints_one_contract_line(workload):
+    """`bench.py --impl reference` = the oracle port on the host cores, a bounded sample: ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-gens', '2',
+                        '--workload', workload], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['metric'] == 'candidate evals/sec on BBOB dim=30 pop=100' and d['value'] > 0 and d['gpu_launches'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config']
+
+
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm exits non-zero with a message instead of measuring something else."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '1'], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode != 0 and not any(ln.startswith('{') for ln in r.stdout.splitlines())
+    assert 'CUDA' in (r.stderr + r.stdout)
