@@ -34,6 +34,14 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     cfg = _lib.MbxRunConfig(kind=0, NP=3, dim=10, maxFEs=100, n_logpoint=50, log_interval=2, use_tape=0, seed=1)
     rc = lib.mbx_rlepso_init(None, None, None, ctypes.byref(cfg), None, None, None, 1, None)
     assert rc == -1 and b'NP' in lib.mbx_last_error()
+    n = lib.mbx_gleet_policy_weight_count()
+    assert n == 5432
+    assert lib.mbx_gleet_policy(None, None, n, None, None, None, None, None, 1, 129, None) == -1 and b'NP' in lib.mbx_last_error()
+    assert lib.mbx_gleet_policy(None, None, n - 1, None, None, None, None, None, 1, 100, None) == -1 and b'packed weights' in lib.mbx_last_error()
+    assert lib.mbx_gleet_policy(None, None, n, None, None, None, None, None, 1, 100, None) == -1 and b'null' in lib.mbx_last_error()
+    assert lib.mbx_gleet_policy(ctypes.c_void_p(256), ctypes.c_void_p(260), n, None, ctypes.c_void_p(256), None, None, None, 1, 100, None) == -1 \
+        and b'aligned' in lib.mbx_last_error()
+    assert lib.mbx_gleet_policy(None, None, n, None, None, None, None, None, 0, 100, None) == 0          # empty batch: nothing to do
 
 
 @pytest.mark.parametrize('dim', [10])
