@@ -54,6 +54,9 @@ def parse():
                     help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor, torch); "
                          'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); '
                          'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
+    ap.add_argument('--fused-policy', action='store_true',
+                    help='deddqn: the Q-network + argmax as ONE kernel per step (agent.DE_DDQN_FusedNet -> mbx_deddqn_policy); '
+                         'gleet: same as --gleet-policy fused')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -268,7 +271,12 @@ def main():
     tr, te = mp.BBOB_Dataset.get_datasets(W['suit'], DIM, 5, difficulty='difficult' if W['subset'] == 'difficult-test' else 'easy')
     problems = te.data if W['subset'] == 'difficult-test' else tr.data + te.data
     pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
+    if args.fused_policy and args.workload == 'gleet':
+        args.gleet_policy = 'fused'
     net, wsrc = build_policy(args.workload, dev, NP, args.gleet_policy)
+    if args.fused_policy and args.workload == 'deddqn':
+        from metabox_b200 import agent as magent
+        net, wsrc = magent.DE_DDQN_FusedNet(net), wsrc + ', fused Q-network kernel (mbx_deddqn_policy)'
     inst, run = msweep.lane_table(len(problems), args.runs)
     if args.lane_order == 'run-major':                        # every contiguous stripe / rank sees the same mix of functions
         inst = np.ascontiguousarray(inst.reshape(len(problems), args.runs).T.reshape(-1))

@@ -348,6 +348,18 @@ int mbx_gleet_policy(const float* d_state, const float* d_weights, int n_weights
                      float* d_mu, float* d_sigma, float* d_logits, int B, int NP, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DE-DDQN Q-network, greedy rollout action -- replaces `__get_action(state, epsilon_greedy=False)` (agent/de_ddqn_agent.py:59-68) on
+ * the MLP 99 -> 100 -> 100 -> 100 -> 100 -> 4 (:21-25) for B lanes at once; called once per function evaluation from
+ * `rollout_episode` (:108-117).
+ *   d_state   [B,99] f32   the features mbx_deddqn_init / mbx_deddqn_step write (NaN / inf entries count as 0)
+ *   d_weights [mbx_deddqn_policy_weight_count()] f32, 16-byte aligned, packed as documented in
+ *             metabox_b200/csrc/mbx_deddqn_policy.cuh (agent.py DE_DDQN_Net.pack()); read on every launch
+ *   outputs:  d_action [B] i32 = argmax_a Q (first maximum) ; optional d_q [B,4] f32                                  */
+int mbx_deddqn_policy_weight_count(void);
+int mbx_deddqn_policy(const float* d_state, const float* d_weights, int n_weights, int32_t* d_action, float* d_q, int B,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Random_search -- replaces Random_search.run_episode (optimizer/random_search.py:17-59): the whole
  * episode (maxFEs/NP iterations) in one launch per lane.  d_tape_u (optional) [B, n_iter, NP, D] f64.
  *   outputs: curve [B, MBX_CURVE_LEN] f32, curve_len [B] i32, fes [B] i32                           */

@@ -141,6 +141,55 @@ class DE_DDQN_Net(MLP):
     def act(self, state):
         return torch.argmax(self.forward(state), dim=-1)
 
+    @torch.no_grad()
+    def pack(self, out=None):
+        """All parameters as ONE float32 vector in the layout `mbx_deddqn_policy` reads (csrc/mbx_deddqn_policy.cuh): the four hidden
+        layers as W^T [in][100] | bias, the output layer as W [4][100] | bias."""
+        lin = [m for m in self.net if isinstance(m, nn.Linear)]
+        parts = [t for l in lin[:-1] for t in (l.weight.t(), l.bias)] + [lin[-1].weight, lin[-1].bias]
+        flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for t in parts])
+        if out is None:
+            return flat.contiguous()
+        out.copy_(flat)
+        return out
+
+
+class DE_DDQN_FusedNet:
+    """`DE_DDQN_Net`'s greedy action as ONE CUDA kernel per environment step (C ABI `mbx_deddqn_policy`, csrc/mbx_deddqn_policy.cu) instead
+    of ~12 torch launches: `policy(state [B,99]) -> action [B] int32`; `sweep.DE_DDQN_Sweep` uses it when handed one.  `refresh()` re-packs
+    the weights in place after an optimiser step on `net` (graphs that captured the launch see the new values)."""
+    fused_action = True
+
+    def __init__(self, net: 'DE_DDQN_Net'):
+        from . import _lib
+        self.net = net
+        self.packed = net.pack()
+        n = _lib.lib().mbx_deddqn_policy_weight_count()
+        if self.packed.numel() != n:
+            raise _lib.MbxError(f'DE_DDQN_Net.pack() produced {self.packed.numel()} weights, libmbx.so expects {n}')
+        if not self.packed.is_cuda:
+            raise _lib.MbxError('DE_DDQN_FusedNet needs the network on a CUDA device (there is no CPU path)')
+
+    def refresh(self):
+        self.net.pack(out=self.packed)
+        return self
+
+    @torch.no_grad()
+    def __call__(self, state, q=False):
+        """-> action [B] int32; with `q=True` -> (action, Q [B,4])."""
+        from . import _lib
+        if state.dim() != 2 or state.shape[1] != 99 or state.dtype != torch.float32 or state.device != self.packed.device:
+            raise ValueError(f'state must be float32 [B, 99] on {self.packed.device}: got {state.dtype} {tuple(state.shape)} on {state.device}')
+        state = state.contiguous()
+        B = state.shape[0]
+        action = torch.empty(B, dtype=torch.int32, device=state.device)
+        qv = torch.empty(B, 4, dtype=torch.float32, device=state.device) if q else None
+        with torch.cuda.device(state.device):
+            rc = _lib.lib().mbx_deddqn_policy(_lib.ptr(state), _lib.ptr(self.packed), self.packed.numel(), _lib.ptr(action), _lib.ptr(qv), B,
+                                              _lib.stream_ptr())
+        _lib.check(rc, 'mbx_deddqn_policy')
+        return (action, qv) if q else action
+
 
 # ------------------------------------------------------------------------------------------ LDE
 class LDE_PolicyNet(nn.Module):
@@ -338,6 +387,7 @@ class GLEET_FusedActor:
     weights are a device buffer the kernel reads on every launch: after an optimiser step on `actor`, call `refresh()` (an in-place
     copy, so CUDA graphs that captured the launch see the new weights)."""
     takes_noise = True
+    fused_action = True
 
     def __init__(self, actor: 'GLEET_Actor'):
         from . import _lib

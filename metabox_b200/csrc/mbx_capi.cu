@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include "mbx_deddqn_policy.cuh"
 #include "mbx_gleet_policy.cuh"
 #include "mbx_launch.h"
 
@@ -169,6 +170,17 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
     return mbx_launch_landscape(d_sample, d_cost, d_ref, B, S, D, d_out, (cudaStream_t)stream);
 }
 
+
+int mbx_deddqn_policy_weight_count(void) { return ddq::N_WEIGHTS; }
+
+int mbx_deddqn_policy(const float* d_state, const float* d_weights, int n_weights, int32_t* d_action, float* d_q, int B,
+                      void* stream) {
+    MBX_REQUIRE(B >= 0, "mbx_deddqn_policy: bad shape B=%d", B);
+    MBX_REQUIRE(n_weights == ddq::N_WEIGHTS, "mbx_deddqn_policy: %d packed weights, expected %d", n_weights, ddq::N_WEIGHTS);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_state && d_weights && d_action, "mbx_deddqn_policy: null pointer");
+    return mbx_launch_deddqn_policy(d_state, d_weights, d_action, d_q, B, (cudaStream_t)stream);
+}
 
 int mbx_gleet_policy_weight_count(void) { return glp::N_WEIGHTS; }
 

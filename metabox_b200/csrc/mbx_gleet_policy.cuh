@@ -14,15 +14,13 @@
 //   O_DEC    block like O_ENC
 //   O_MU / O_SIGMA   head: L0W [32][16] | L0B [32] | L1W [8][32] | L1B [8] | L2W [8] | L2B [1] (+3 pad)
 #pragma once
-#include <math.h>
-
-#if defined(__CUDACC__)
-#define GLP_HD __host__ __device__ __forceinline__
-#else
-#define GLP_HD inline
-#endif
+#include "mbx_hostdev.cuh"
+#define GLP_HD MBX_HD
 
 namespace glp {
+using mbxhd::F4;
+using mbxhd::ld4;
+using mbxhd::st4;
 constexpr int E = 16, ND = 9, NF = 27, NH = 4, HK = 4;
 constexpr int BLK_WQ = 0, BLK_WK = 256, BLK_WV = 512, BLK_WO = 768, BLK_F1W = 1024, BLK_F1B = 1280, BLK_F2W = 1296, BLK_F2B = 1552,
               BLK_SIZE = 1568;
@@ -31,23 +29,6 @@ constexpr int O_EMB = 0, O_ENC = 144, O_DEMB = O_ENC + BLK_SIZE, O_DEC = O_DEMB 
               O_SIGMA = O_MU + HD_SIZE, N_WEIGHTS = O_SIGMA + HD_SIZE;
 constexpr float MAX_SIGMA = 0.7f, MIN_SIGMA = 0.01f, LEAKY = 0.01f, NORM_EPS = 1e-05f;
 constexpr float QSCALE = 0.5f * 1.4426950408889634f;          // 1/sqrt(key_dim) * log2(e): softmax through exp2f
-
-struct F4 { float x, y, z, w; };
-GLP_HD F4 ld4(const float* p) {
-#if defined(__CUDA_ARCH__)
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    return F4{v.x, v.y, v.z, v.w};
-#else
-    return F4{p[0], p[1], p[2], p[3]};
-#endif
-}
-GLP_HD void st4(float* p, float a, float b, float c, float d) {
-#if defined(__CUDA_ARCH__)
-    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
-#else
-    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
-#endif
-}
 
 // y[o] (+)= sum_i x[i] * W[i][o]      W in-major [NI][NO]
 template <int NI, int NO, bool ACC>

@@ -48,6 +48,7 @@ class _Sweep:
         self.time_kernels = time_kernels
         self.kernel_events = []
         self.launches = 0
+        self.kernels_per_step = 1           # kernels of libmbx.so per env step (2 when the policy is one of the fused kernels too)
         self.finite_reward = False          # RLEPSO: reward is +1 / -1, never NaN / inf
         self.ret = torch.zeros(engine.B, dtype=torch.float32, device=engine.device)
         self._graph = None
@@ -121,7 +122,7 @@ class _Sweep:
                 self._graph.replay()
             else:
                 self._step()
-            self.launches += per
+            self.launches += per * self.kernels_per_step
             self.steps += per
 
     def _result(self):
@@ -202,8 +203,11 @@ class DE_DDQN_Sweep(_Sweep):
         eng = DE_DDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
         super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
         self.net = net
+        self.kernels_per_step = 2 if getattr(net, 'fused_action', False) else 1
 
     def _policy(self, feat):
+        if getattr(self.net, 'fused_action', False):            # agent.DE_DDQN_FusedNet: sanitising, 5 layers and argmax in one kernel
+            return self.net(feat)
         q = self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0))
         return torch.argmax(q, dim=-1).to(torch.int32)
 
@@ -217,6 +221,7 @@ class GLEET_Sweep(_Sweep):
         eng = GLEET_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
         super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
         self.policy = policy
+        self.kernels_per_step = 2 if getattr(policy, 'fused_action', False) else 1
 
     def _policy(self, feat):
         if getattr(self.policy, 'takes_noise', False):          # agent.GLEET_Actor: noise from the sweep's own generator (graph-safe)

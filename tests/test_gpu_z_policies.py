@@ -188,3 +188,51 @@ def test_gleet_sweep_with_the_fused_policy_kernel():
     r = rows(sweep.GLEET_Sweep(pack, inst, fused, 3000, 50, seed=9, graph=True, poll=8))
     assert np.all((r[:, 51] >= 3000) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] <= 3100)
     assert np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused Q-network kernel (mbx_deddqn_policy)
+def test_fused_deddqn_policy_kernel_vs_reference_q_values_and_torch_net():
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    net = ma.load_reference_weights(ma.DE_DDQN_Net(), {k[len('deddqn/'):]: G[k] for k in G.files if k.startswith('deddqn/')}).cuda().eval()
+    fused = ma.DE_DDQN_FusedNet(net)
+    act, q = fused(torch.as_tensor(G['deddqn_kat/x']).cuda(), q=True)
+    np.testing.assert_allclose(q.cpu().numpy(), G['deddqn_kat/q'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(act.cpu().numpy(), np.argmax(G['deddqn_kat/q'], axis=1))
+    g = torch.Generator(device='cpu').manual_seed(3)
+    for B in (1, 7, 8, 9, 771, 4608):
+        x = (torch.rand(B, 99, generator=g) * 2 - 0.5)
+        if B > 8:
+            x[3, 17] = float('nan'); x[5, 0] = float('inf'); x[B - 1, 98] = float('-inf')
+        x = x.cuda()
+        act, q = fused(x, q=True)
+        with torch.no_grad():
+            want = net(torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0))
+        np.testing.assert_allclose(q.cpu().numpy(), want.cpu().numpy(), rtol=2e-4, atol=2e-5, err_msg=f'B {B}')
+        top2 = torch.topk(want, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4                                      # lanes without a near-tie between the two best actions
+        assert torch.equal(act[clear].long(), torch.argmax(want, dim=1)[clear]) and act.dtype == torch.int32
+        assert torch.equal(fused(x), act)
+    assert fused(torch.zeros(0, 99).cuda()).shape == (0,)
+    with pytest.raises(ValueError):
+        fused(torch.zeros(4, 98).cuda())
+
+
+def test_deddqn_sweep_with_the_fused_q_network():
+    """Complete DE-DDQN rollouts, fused step + fused Q-network: graph replay == eager launches, and the same rows as the sweep driven by the
+    torch network wherever no lane ever met a near-tie (the two Q implementations differ in summation order only)."""
+    from metabox_b200 import agent as ma, sweep
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    net = ma.load_reference_weights(ma.DE_DDQN_Net(), {k[len('deddqn/'):]: G[k] for k in G.files if k.startswith('deddqn/')}).cuda().eval()
+    fused = ma.DE_DDQN_FusedNet(net)
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    ra = rows(sweep.DE_DDQN_Sweep(pack, inst, fused, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    rb = rows(sweep.DE_DDQN_Sweep(pack, inst, fused, 460, 50, seed=5, graph=False, poll=50))
+    np.testing.assert_array_equal(ra, rb)
+    assert np.all(ra[:, 51] == 460) and np.all(np.diff(ra[:, :51], axis=1) <= 0) and np.isfinite(ra).all()
+    rt = rows(sweep.DE_DDQN_Sweep(pack, inst, net, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    same = np.all(ra == rt, axis=1)
+    assert same.mean() >= 0.5, f'only {same.sum()} of {len(same)} lanes agree with the torch-driven sweep'

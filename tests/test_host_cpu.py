@@ -42,6 +42,11 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.mbx_gleet_policy(ctypes.c_void_p(256), ctypes.c_void_p(260), n, None, ctypes.c_void_p(256), None, None, None, 1, 100, None) == -1 \
         and b'aligned' in lib.mbx_last_error()
     assert lib.mbx_gleet_policy(None, None, n, None, None, None, None, None, 0, 100, None) == 0          # empty batch: nothing to do
+    m = lib.mbx_deddqn_policy_weight_count()
+    assert m == 40704
+    assert lib.mbx_deddqn_policy(None, None, m + 1, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
+    assert lib.mbx_deddqn_policy(None, None, m, None, None, 1, None) == -1 and b'null' in lib.mbx_last_error()
+    assert lib.mbx_deddqn_policy(None, None, m, None, None, 0, None) == 0
 
 
 @pytest.mark.parametrize('dim', [10])
@@ -177,22 +182,27 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
     assert a.shape == (9, 1)
 
 
-def _emul_lib():
-    """g++ build of tests/emul/gleet_policy_host.cpp (the device header compiled for the host); cached per session in a temp dir."""
+def _emul_lib(name='gleet_policy'):
+    """g++ build of tests/emul/<name>_host.cpp (the device header compiled for the host); built once per session in a temp dir."""
     import ctypes as C
     import subprocess
     import tempfile
-    if not hasattr(_emul_lib, 'lib'):
+    cache = _emul_lib.__dict__.setdefault('cache', {})
+    if name not in cache:
         d = tempfile.mkdtemp(prefix='mbx_emul_')
-        so = os.path.join(d, 'glp_host.so')
-        src = os.path.join(os.path.dirname(__file__), 'emul', 'gleet_policy_host.cpp')
+        so = os.path.join(d, name + '_host.so')
+        src = os.path.join(os.path.dirname(__file__), 'emul', name + '_host.cpp')
         subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', src, '-o', so], check=True)
         L = C.CDLL(so)
         fp = C.POINTER(C.c_float)
-        L.glp_host_forward.restype = C.c_int
-        L.glp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
-        _emul_lib.lib = L
-    return _emul_lib.lib
+        if name == 'gleet_policy':
+            L.glp_host_forward.restype = C.c_int
+            L.glp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
+        else:
+            L.ddq_host_forward.restype = C.c_int
+            L.ddq_host_forward.argtypes = [fp, fp, C.POINTER(C.c_int32), fp, C.c_int]
+        cache[name] = L
+    return cache[name]
 
 
 def _emul_forward(w, x, noise=None):
@@ -243,6 +253,39 @@ def test_fused_gleet_policy_arithmetic_on_the_host_matches_the_reference():
         np.testing.assert_allclose(lg, l2.detach().numpy(), rtol=2e-4, atol=3e-5)
         np.testing.assert_allclose(mu, m2.detach().numpy(), rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(sg, s2.detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_deddqn_policy_arithmetic_on_the_host_matches_the_reference():
+    """The per-neuron device functions of the fused DE-DDQN Q-network kernel (csrc/mbx_deddqn_policy.cuh) compiled for the host, driven in
+    the kernel's order with the weights packed by DE_DDQN_Net.pack(): Q-values of the unmodified reference on the shipped pickle
+    (agents.npz), greedy actions equal to torch.argmax, ragged tile (B not a multiple of 8), NaN / inf features count as 0."""
+    import ctypes as C
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    net = ma.load_reference_weights(ma.DE_DDQN_Net(), {k[len('deddqn/'):]: G[k] for k in G.files if k.startswith('deddqn/')})
+    w = np.ascontiguousarray(net.pack().numpy())
+    L = _emul_lib('deddqn_policy')
+    assert L.ddq_host_weight_count() == w.size == 99 * 100 + 100 + 3 * (100 * 100 + 100) + 4 * 100 + 4
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+    def run(x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        act = np.empty(len(x), np.int32); q = np.empty((len(x), 4), np.float32)
+        assert L.ddq_host_forward(x.ctypes.data_as(fp), w.ctypes.data_as(fp), act.ctypes.data_as(ip), q.ctypes.data_as(fp), len(x)) == 0
+        return act, q
+
+    act, q = run(G['deddqn_kat/x'])                                    # 16 states
+    np.testing.assert_allclose(q, G['deddqn_kat/q'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(act, np.argmax(G['deddqn_kat/q'], axis=1))
+    g = np.random.RandomState(7)
+    x = (g.rand(21, 99) * 2 - 0.5).astype(np.float32)                 # 21 lanes: two full tiles + 5
+    x[3, 17] = np.nan; x[9, 0] = np.inf; x[20, 98] = -np.inf
+    act, q = run(x)
+    want = net(torch.nan_to_num(torch.as_tensor(x), nan=0.0, posinf=0.0, neginf=0.0)).detach().numpy()
+    np.testing.assert_allclose(q, want, rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(act, np.argmax(want, axis=1))
+    assert run(x[:1])[0][0] == act[0] and len(run(x[:0])[0]) == 0
 
 
 # ----------------------------------------------------------------------------------------- sharding / gather (gloo, world 2)
