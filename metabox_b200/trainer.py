@@ -1,5 +1,5 @@
-"""Sharded training rollouts for the LDE agent (REINFORCE) and the RLEPSO agent (PPO) (BASELINE config C4
-"LDE train rollout ... sharded").  The RLEPSO part is at the end of the file.
+"""Sharded training rollouts for the LDE agent (REINFORCE) and the RLEPSO / GLEET agents (PPO) (BASELINE config C4
+"LDE train rollout ... sharded").  The PPO part is at the end of the file.
 
 Reference: `LDE_Agent.train_episode` (`src/agent/lde_agent.py:85-145`): per problem, TRAJECTORY_NUM = 20 trajectories of
 TRAJECTORY_LENGTH = 50 environment steps are collected with the current policy (`sampler`, no gradient), then ONE batched
@@ -23,7 +23,7 @@ import torch
 
 from . import sweep as ms
 from .agent import LDE_PolicyNet, RLEPSO_Actor, RLEPSO_Critic
-from .optimizer import LDE_Engine, RLEPSO_Engine
+from .optimizer import GLEET_Engine, LDE_Engine, RLEPSO_Engine
 
 TRAJECTORY_NUM, TRAJECTORY_LENGTH, GAMMA, LR_MODEL = 20, 50, 0.99, 0.005      # lde_agent.py:36-42
 
@@ -173,61 +173,52 @@ def ppo_losses(actor, critic, states, actions, old_logp, rewards, weight, next_s
     return reinforce, baseline, value.detach(), int(live.sum().item())
 
 
-class RLEPSO_Trainer:
-    """`RLEPSO_Trainer(config, train_problems).train_episodes(problem_ids)` -- `RLEPSO_Agent.train_episode`
-    (rlepso_agent.py:113-292) for many problems at once: every problem is a lane of `RLEPSO_Engine`, all lanes advance in
-    lockstep in segments of n_step = 10 generations (policy sampling + fused step kernel on the GPU, nothing leaves the
-    device), and after each segment K_epochs = 3 clipped-PPO updates of actor and critic (two Adam optimizers, lr 1e-5)
-    are made from the mean of the per-lane losses.  With torch.distributed initialised the problems are sharded over the
-    ranks and the actor + critic gradients travel in ONE all-reduce per update (the same collective carries the number of
-    lanes still running, so every rank leaves the loop in the same segment).  One problem on one rank is the reference's
-    update rule.  config fields: dim, maxFEs, n_logpoint, log_interval, optional max_learning_step."""
+class _PPOTrainer:
+    """The segment loop shared by the PPO agents (RLEPSO, GLEET -- the reference's two `train_episode`s are the same algorithm):
+    every problem is a lane of a batched engine, all lanes advance in lockstep in segments of `n_step` generations (policy
+    sampling + fused step kernel on the GPU, nothing leaves the device), and after each segment `k_epochs` clipped-PPO updates
+    are made from the mean of the per-lane losses.  With torch.distributed initialised the problems are sharded over the ranks
+    and ALL gradients travel in ONE all-reduce per update (the same collective carries the number of lanes still running, so
+    every rank leaves the loop in the same segment).  One problem on one rank is the reference's update rule.
+    Subclasses provide: `_engine`, `_state`, `_sample`, `_heads`, `_params`, `_zero_grad`, `_backward`, `_apply`."""
+    n_step, k_epochs, eps_clip, gamma = N_STEP, K_EPOCHS, EPS_CLIP, PPO_GAMMA
 
-    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None):
+    def _setup(self, config, problems, seed, device):
         from .problem import InstancePack
         self.config, self.seed = config, int(seed)
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.problems = list(problems)
         self.pack = InstancePack(self.problems, self.device)
-        self.actor = (actor if actor is not None else RLEPSO_Actor()).to(self.device)
-        self.critic = (critic if critic is not None else RLEPSO_Critic()).to(self.device)
-        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=PPO_LR)
-        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=PPO_LR)
         self.learning_time = 0
         self.episodes = 0
 
-    def _params(self):
-        return list(self.actor.parameters()) + list(self.critic.parameters())
-
     @torch.no_grad()
-    def collect_segment(self, eng, n_step=N_STEP):
-        """n_step generations of all lanes with the current policy -> states [T,L,1], actions [T,L,35], logp, rewards, weight."""
+    def collect_segment(self, eng, n_step=None):
+        """n_step generations of all lanes with the current policy -> states [T,L,...], actions [T,L,...], logp, rewards, weight [T,L]."""
         S, A, LP, R, W = [], [], [], [], []
-        for _ in range(n_step):
+        for _ in range(n_step or self.n_step):
             alive = (eng.done == 0).to(torch.float32)
-            x = eng.feature.reshape(eng.B, 1).clone()
-            a = self.actor(x)
-            S.append(x); A.append(a); LP.append(self.actor.log_prob(x, a)); W.append(alive)
+            x = self._state(eng)
+            a, lp = self._sample(x)
+            S.append(x); A.append(a); LP.append(lp); W.append(alive)
             _, reward, _ = eng.update(a)
-            R.append(reward.clone() * alive)
+            R.append(torch.nan_to_num(reward.clone().to(torch.float32), nan=0.0, posinf=0.0, neginf=0.0) * alive)
         st = lambda xs: torch.stack(xs, dim=0)
-        return dict(states=st(S), actions=st(A), logp=st(LP), rewards=st(R), weight=st(W),
-                    next_state=eng.feature.reshape(eng.B, 1).clone())
+        return dict(states=st(S), actions=st(A), logp=st(LP), rewards=st(R), weight=st(W), next_state=self._state(eng))
 
     def train_episodes(self, problem_ids):
-        """Full episodes of `problem_ids` (sharded over the ranks).  -> info dict like train_episode's (:284-292) with
-        per-problem lists plus 'segments' and the last losses."""
+        """Full episodes of `problem_ids` (sharded over the ranks).  -> info dict like train_episode's with per-problem lists
+        plus 'segments' and the last losses."""
         import torch.distributed as dist
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         lo, hi = ms.shard_range(len(problem_ids), rank, world)
         mine = np.asarray(list(problem_ids[lo:hi]), dtype=np.int32)
-        cfg = self.config
-        max_ls = getattr(cfg, 'max_learning_step', None)
-        eng = RLEPSO_Engine(self.pack, mine, cfg.maxFEs, cfg.n_logpoint, getattr(cfg, 'log_interval', None),
-                            seed=self.seed + 104729 * self.episodes, lane_base=lo)
+        max_ls = getattr(self.config, 'max_learning_step', None)
+        eng = self._engine(mine, lo)
         if len(mine):
             eng.init_population()
         ret = torch.zeros(len(mine), device=self.device)
+        actor, critic = self._heads()
         segments, last, stop = 0, (0.0, 0.0), False
         running = 1.0
         while running > 0 and not stop:
@@ -235,24 +226,21 @@ class RLEPSO_Trainer:
             if seg is not None:
                 ret += seg['rewards'].sum(0)
             old_value = None
-            for _k in range(K_EPOCHS):
-                self.optimizer_actor.zero_grad(set_to_none=True)
-                self.optimizer_critic.zero_grad(set_to_none=True)
+            for _k in range(self.k_epochs):
+                self._zero_grad()
                 n_local, alive_after = 0, 0.0
                 if seg is not None:
-                    rl, bl, val, n_local = ppo_losses(self.actor, self.critic, seg['states'], seg['actions'], seg['logp'],
-                                                      seg['rewards'], seg['weight'], seg['next_state'], old_value)
+                    rl, bl, val, n_local = ppo_losses(actor, critic, seg['states'], seg['actions'], seg['logp'], seg['rewards'],
+                                                      seg['weight'], seg['next_state'], old_value, self.eps_clip, self.gamma)
                     if old_value is None:
                         old_value = val
                     if n_local:
-                        bl.backward()                                        # :257-258 (two separate backward passes)
-                        rl.backward()
+                        self._backward(rl, bl)
                         last = (float(rl.item()) / n_local, float(bl.item()) / n_local)
                     alive_after = float((eng.done == 0).sum().item())
                 total, (running,) = allreduce_gradients(self._params(), n_local, extra=[alive_after])
                 if total > 0:
-                    self.optimizer_actor.step()
-                    self.optimizer_critic.step()
+                    self._apply()
                     self.learning_time += 1
                 if max_ls is not None and self.learning_time >= max_ls:
                     stop = True
@@ -263,3 +251,117 @@ class RLEPSO_Trainer:
         return {'normalizer': [c[0] for c in curves], 'gbest': [c[-1] for c in curves], 'return': ret.tolist(),
                 'learn_steps': self.learning_time, 'segments': segments, 'reinforce_loss': last[0], 'baseline_loss': last[1],
                 'done': bool(max_ls is not None and self.learning_time >= max_ls)}
+
+
+class RLEPSO_Trainer(_PPOTrainer):
+    """`RLEPSO_Trainer(config, train_problems).train_episodes(problem_ids)` -- `RLEPSO_Agent.train_episode`
+    (rlepso_agent.py:113-292) for many problems at once (see `_PPOTrainer`): segments of n_step = 10 generations, K_epochs = 3
+    clipped-PPO updates of actor and critic (two Adam optimizers, lr 1e-5, two separate backward passes, :257-258).
+    config fields: dim, maxFEs, n_logpoint, log_interval, optional max_learning_step."""
+
+    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None):
+        self._setup(config, problems, seed, device)
+        self.actor = (actor if actor is not None else RLEPSO_Actor()).to(self.device)
+        self.critic = (critic if critic is not None else RLEPSO_Critic()).to(self.device)
+        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=PPO_LR)
+        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=PPO_LR)
+
+    def _params(self):
+        return list(self.actor.parameters()) + list(self.critic.parameters())
+
+    def _heads(self):
+        return self.actor, self.critic
+
+    def _engine(self, mine, lo):
+        cfg = self.config
+        return RLEPSO_Engine(self.pack, mine, cfg.maxFEs, cfg.n_logpoint, getattr(cfg, 'log_interval', None),
+                             seed=self.seed + 104729 * self.episodes, lane_base=lo)
+
+    def _state(self, eng):
+        return eng.feature.reshape(eng.B, 1).clone()
+
+    def _sample(self, x):
+        a = self.actor(x)
+        return a, self.actor.log_prob(x, a)
+
+    def _zero_grad(self):
+        self.optimizer_actor.zero_grad(set_to_none=True)
+        self.optimizer_critic.zero_grad(set_to_none=True)
+
+    def _backward(self, rl, bl):
+        bl.backward()
+        rl.backward()
+
+    def _apply(self):
+        self.optimizer_actor.step()
+        self.optimizer_critic.step()
+
+
+# ------------------------------------------------------------------------------------------------------------- GLEET (PPO)
+GLEET_LR, GLEET_MAX_GRAD_NORM = 1e-4, 0.1                                            # gleet_agent.py:50-52
+
+
+class _GleetActorHead:
+    """`ppo_losses` view of the GLEET actor: states [T,L,NP,27], actions [T,L,NP] -> joint log-probability [T,L]."""
+
+    def __init__(self, actor):
+        self.actor = actor
+
+    def log_prob(self, states, actions):
+        lead = states.shape[:-2]
+        return self.actor.log_prob(states.reshape(-1, *states.shape[-2:]), actions.reshape(-1, actions.shape[-1])).reshape(lead)
+
+
+class _GleetCriticHead:
+    """The GLEET critic reads the ACTOR's decoder output (gleet_agent.py:147-150, 236): value(states [...,NP,27]) -> [...]; the baseline loss
+    therefore also trains the actor's attention stack, exactly like the reference."""
+
+    def __init__(self, actor, critic):
+        self.actor, self.critic = actor, critic
+
+    def __call__(self, states):
+        lead = states.shape[:-2]
+        return self.critic(self.actor.logits(states.reshape(-1, *states.shape[-2:]))).reshape(lead)
+
+
+class GLEET_Trainer(_PPOTrainer):
+    """`GLEET_Agent.train_episode` (gleet_agent.py:111-290) for many problems at once (see `_PPOTrainer`): segments of n_step = 10
+    generations, K_epochs = 3 clipped-PPO epochs (eps 0.1, gamma 0.999, value clipping from the second epoch on), ONE Adam optimizer over
+    actor + critic (lr 1e-4; the reference builds an ExponentialLR scheduler but never steps it), loss = baseline + reinforce in one
+    backward pass, gradient-norm clipping at 0.1 per parameter group (actor, critic) after the all-reduce (`clip_grad_norms`, :472-487)."""
+
+    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None):
+        from .agent import GLEET_Actor, GLEET_Critic
+        self._setup(config, problems, seed, device)
+        self.actor = (actor if actor is not None else GLEET_Actor()).to(self.device)
+        self.critic = (critic if critic is not None else GLEET_Critic()).to(self.device)
+        self.optimizer = torch.optim.Adam([{'params': self.actor.parameters(), 'lr': GLEET_LR}, {'params': self.critic.parameters(), 'lr': GLEET_LR}])
+
+    def _params(self):
+        return list(self.actor.parameters()) + list(self.critic.parameters())
+
+    def _heads(self):
+        return _GleetActorHead(self.actor), _GleetCriticHead(self.actor, self.critic)
+
+    def _engine(self, mine, lo):
+        cfg = self.config
+        return GLEET_Engine(self.pack, mine, cfg.maxFEs, cfg.n_logpoint, getattr(cfg, 'log_interval', None),
+                            seed=self.seed + 104729 * self.episodes, lane_base=lo)
+
+    def _state(self, eng):
+        return eng.feature.clone()
+
+    def _sample(self, x):
+        a = self.actor(x)
+        return a, self.actor.log_prob(x, a)
+
+    def _zero_grad(self):
+        self.optimizer.zero_grad(set_to_none=True)
+
+    def _backward(self, rl, bl):
+        (bl + rl).backward()
+
+    def _apply(self):
+        for group in self.optimizer.param_groups:
+            torch.nn.utils.clip_grad_norm_(group['params'], GLEET_MAX_GRAD_NORM, norm_type=2)
+        self.optimizer.step()

@@ -236,3 +236,30 @@ def test_deddqn_sweep_with_the_fused_q_network():
     rt = rows(sweep.DE_DDQN_Sweep(pack, inst, net, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
     same = np.all(ra == rt, axis=1)
     assert same.mean() >= 0.5, f'only {same.sum()} of {len(same)} lanes agree with the torch-driven sweep'
+
+
+# ------------------------------------------------------------------------------------------------ GLEET PPO training on the lane machinery
+def test_gleet_trainer_collects_on_the_gpu_and_updates():
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, problem as mp, trainer as mt
+    from metabox_b200.optimizer import GLEET_Engine
+    cfg = argparse.Namespace(dim=10, maxFEs=2500, n_logpoint=50, log_interval=50)
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', 10, 5)
+    W, _ = _weights('gleet0')
+    Wc, _ = _weights('gleet0_critic')
+    actor, critic = ma.load_reference_weights(ma.GLEET_Actor(), W), ma.load_reference_weights(ma.GLEET_Critic(), Wc)
+    T = mt.GLEET_Trainer(cfg, tr.data, actor=actor, critic=critic, seed=5)
+    p0 = [p.detach().clone() for p in T._params()]
+    info = T.train_episodes([0, 1, 2, 3])
+    assert info['segments'] == 3 and info['learn_steps'] == 9 and not info['done']          # 25 generations -> 3 segments x 3 epochs
+    assert len(info['gbest']) == 4 and all(g <= n for g, n in zip(info['gbest'], info['normalizer']))
+    assert all(np.isfinite(r) and r >= 0 for r in info['return']) and np.isfinite(info['reinforce_loss']) and np.isfinite(info['baseline_loss'])
+    moved = max(float((a - b.detach()).abs().max()) for a, b in zip(p0, T._params()))
+    assert 1e-6 < moved < 1e-2 and all(torch.isfinite(p).all() for p in T._params())       # Adam, lr 1e-4, 9 clipped steps
+    eng = GLEET_Engine(T.pack, np.arange(3, dtype=np.int32), 2500, 50, 50, seed=1)
+    eng.init_population()
+    seg = T.collect_segment(eng)
+    assert seg['states'].shape == (10, 3, 100, 27) and seg['actions'].shape == (10, 3, 100) and seg['logp'].shape == (10, 3)
+    assert torch.all(seg['weight'] == 1) and torch.all(seg['rewards'] >= 0) and seg['next_state'].shape == (3, 100, 27)
+    assert torch.all((seg['actions'] >= 0) & (seg['actions'] <= 1))

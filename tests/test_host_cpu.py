@@ -576,6 +576,128 @@ def test_rlepso_ppo_loop_world2_gloo_ranks_stay_in_step():
     np.testing.assert_array_equal(w0, w1)                                # the same all-reduced gradients -> the same weights
 
 
+def _reference_gleet_ppo_epoch(actor, critic, states, actions, old_logp, rewards, next_state, old_value, gamma=0.999, eps_clip=0.1):
+    """Literal per-episode restatement of gleet_agent.py:196-262 (one lane, python loops over the segment): the critic reads the actor's
+    decoder output, the log-probability is the sum over the swarm, loss = baseline_loss + reinforce_loss."""
+    import torch
+    logprobs, bl_val = [], []
+    for tt in range(states.shape[0]):
+        mu, sigma, to_critic = actor.distribution(states[tt][None])
+        logprobs.append(torch.sum(torch.distributions.Normal(mu, sigma).log_prob(actions[tt][None]), dim=1))
+        bl_val.append(critic(to_critic).squeeze())
+    logprobs, bl_val = torch.stack(logprobs).view(-1), torch.stack(bl_val).view(-1)
+    R = critic(actor.logits(next_state[None])).detach().squeeze()
+    Reward = []
+    for r in list(rewards)[::-1]:
+        R = R * gamma + r
+        Reward.append(R)
+    Reward = torch.stack(Reward[::-1], 0).view(-1)
+    ratios = torch.exp(logprobs - old_logp.detach())
+    advantages = Reward - bl_val.detach()
+    reinforce_loss = -torch.min(ratios * advantages, torch.clamp(ratios, 1 - eps_clip, 1 + eps_clip) * advantages).mean()
+    if old_value is None:
+        baseline_loss = ((bl_val - Reward) ** 2).mean()
+    else:
+        vpredclipped = old_value + torch.clamp(bl_val - old_value, -eps_clip, eps_clip)
+        baseline_loss = torch.max((bl_val - Reward) ** 2, (vpredclipped - Reward) ** 2).mean()
+    return reinforce_loss, baseline_loss
+
+
+def test_gleet_ppo_losses_match_the_reference_formulas():
+    """GLEET's PPO epoch through the shared `ppo_losses` (actor / critic adapters of trainer.py) against the literal restatement, lane by
+    lane: losses and the gradients of ALL parameters (the baseline loss reaches the actor's attention stack through the critic's input)."""
+    import torch
+    from metabox_b200 import agent as ma, trainer as mt
+    torch.manual_seed(3)
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    sub = lambda pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet0/'))
+    critic = ma.load_reference_weights(ma.GLEET_Critic(), sub('gleet0_critic/'))
+    T, L, NP = 4, 3, 12
+    states, actions = torch.rand(T, L, NP, 27), torch.rand(T, L, NP)
+    rewards, nxt = torch.rand(T, L) * 0.2, torch.rand(L, NP, 27)
+    ah, ch = mt._GleetActorHead(actor), mt._GleetCriticHead(actor, critic)
+    with torch.no_grad():
+        old_logp = ah.log_prob(states, actions) + 0.05 * torch.randn(T, L)
+    weight = torch.ones(T, L)
+    weight[2:, 1] = 0                                                                 # lane 1 finished after 2 generations
+    for old_value in (None, torch.rand(T, L)):
+        rl, bl, val, n = mt.ppo_losses(ah, ch, states, actions, old_logp, rewards * weight, weight, nxt, old_value)
+        want_r, want_b = 0., 0.
+        for b in range(L):
+            tt = 2 if b == 1 else T
+            r, v = _reference_gleet_ppo_epoch(actor, critic, states[:tt, b], actions[:tt, b], old_logp[:tt, b], rewards[:tt, b], nxt[b],
+                                              None if old_value is None else old_value[:tt, b])
+            want_r, want_b = want_r + r, want_b + v
+        assert n == L and val.shape == (T, L)
+        np.testing.assert_allclose(float(rl.detach()), float(want_r.detach()), rtol=1e-4)
+        np.testing.assert_allclose(float(bl.detach()), float(want_b.detach()), rtol=1e-4)
+        ps = list(actor.parameters()) + list(critic.parameters())
+        g1 = torch.autograd.grad(rl + bl, ps, retain_graph=True, allow_unused=True)
+        g2 = torch.autograd.grad(want_r + want_b, ps, allow_unused=True)
+        assert all(a is not None for a in g1)                                         # every parameter of actor AND critic is trained
+        for a, b in zip(g1, g2):
+            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-3, atol=2e-5)
+
+
+class _FakeGleetEngine:
+    """CPU stand-in with the engine surface GLEET_Trainer uses: lane k finishes after 7 + 6 k generations; float rewards."""
+
+    def __init__(self, pack, lane_inst, maxFEs, n_logpoint=50, log_interval=None, seed=0, lane_base=0, NP=6):
+        import torch
+        self.B, self.NP = len(lane_inst), NP
+        self.life = torch.tensor([7 + 6 * (lane_base + k) for k in range(self.B)], dtype=torch.int64)
+        self.gen = torch.zeros(self.B, dtype=torch.int64)
+        self.g = torch.Generator().manual_seed(seed + lane_base)
+        self.feature = torch.rand(self.B, NP, 27, generator=self.g)
+        self.done = torch.zeros(self.B, dtype=torch.uint8)
+
+    def init_population(self):
+        return self.feature
+
+    def update(self, action):
+        import torch
+        assert action.shape == (self.B, self.NP) and float(action.min()) >= 0 and float(action.max()) <= 1
+        alive = self.done == 0
+        self.gen += alive.long()
+        r = action.mean(1) * 0.1 * alive
+        self.done = (self.gen >= self.life).to(torch.uint8)
+        self.feature = torch.rand(self.B, self.NP, 27, generator=self.g)
+        return self.feature, r, self.done
+
+    def cost_curves(self, pad=False):
+        return [[10.0, 1.0] for _ in range(self.B)]
+
+
+def test_gleet_ppo_loop_on_cpu_with_a_fake_engine():
+    """Host logic of GLEET_Trainer: segments of 10 generations x 3 epochs until the longest lane is done, one Adam optimizer, gradient
+    norms clipped to 0.1 per parameter group before every step, parameters move, max_learning_step stops the loop."""
+    import torch
+    from metabox_b200 import problem as mp, trainer as mt
+    old = (mp.InstancePack, mt.GLEET_Engine)
+    try:
+        mp.InstancePack = lambda problems, device=None: None
+        mt.GLEET_Engine = _FakeGleetEngine
+        torch.manual_seed(0)
+        cfg = argparse.Namespace(dim=10, maxFEs=4000, n_logpoint=50, log_interval=80)
+        T = mt.GLEET_Trainer(cfg, [None] * 3, seed=1, device='cpu')
+        before = torch.cat([p.detach().reshape(-1).clone() for p in T._params()])
+        norms = []
+        step = T.optimizer.step
+        T.optimizer.step = lambda: (norms.append([float(torch.norm(torch.stack([p.grad.norm() for p in g['params']]))) for g in T.optimizer.param_groups]), step())[1]
+        info = T.train_episodes([0, 1, 2])                                    # lanes live 7, 13, 19 generations -> 2 segments
+        assert info['segments'] == 2 and info['learn_steps'] == 6 and len(info['gbest']) == 3 and len(norms) == 6
+        assert all(n <= 0.1 + 1e-6 for pair in norms for n in pair)
+        after = torch.cat([p.detach().reshape(-1) for p in T._params()])
+        assert float((after - before).abs().max()) > 0 and torch.isfinite(after).all()
+        assert all(r > 0 for r in info['return'])
+        cfg.max_learning_step = 8
+        info = T.train_episodes([0, 1, 2])
+        assert info['done'] and info['learn_steps'] == 8
+    finally:
+        mp.InstancePack, mt.GLEET_Engine = old
+
+
 def test_qlpso_qtable_policy_on_cpu():
     """Tabular QLPSO policy (qlpso_agent.py:33-36, 47-48): softmax sampling by inverse CDF, TD rule."""
     import torch
