@@ -461,3 +461,47 @@ def test_gleet_and_rl_pso_policy_restatements_match_reference():
     assert r['gens'] == 4 and r['fes'] == 500 and np.isfinite(r['cost']).all()
     r2 = orr.gleet_rollout((tr + te)[0], 10, 20000, w, run_seed=3, max_gens=4)
     assert r2['cost'] == r['cost']                                           # seeded -> repeatable
+
+
+# ------------------------------------------------------------------------------------------ DEDQN
+def test_dedqn_steps_match_reference():
+    """130 consecutive single-individual steps of the real DEDQN_Optimizer per case (float32 storage contract, np.random re-seeded before
+    every step) vs the oracle carrying its OWN state and replaying the same draws: replaced rows / gbest bit-exact, the 4 landscape
+    features, the survival-based reward, fes accounting (200 charged evaluations per step) and the cost-curve protocol past maxFEs."""
+    from oracle import dedqn as od
+    G = load('dedqn.npz')
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = od.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, state = od.init_population(cfg, ev, optimum, lb, ub, od.NumpyTape(cfg.NP, dim, nc))
+        np.testing.assert_array_equal(S.pop, G[f'{key}/s0/pop'], err_msg=f'{key} init pop')
+        np.testing.assert_allclose(S.cost, G[f'{key}/s0/cost'], rtol=1e-6, atol=1e-10)
+        np.testing.assert_array_equal(S.best(), G[f'{key}/s0/gbest'])
+        np.testing.assert_allclose(state, G[f'{key}/s0/state'], rtol=1e-6, atol=1e-9)
+        assert S.fes == int(G[f'{key}/s0/fes']) == 2 * cfg.NP
+        S.cost = G[f'{key}/s0/cost'].copy(); S.gbest_cost = np.float32(G[f'{key}/s0/gbest_cost'])       # carry the reference's float32 costs
+        seen_done = False
+        for t in range(1, int(G['n_steps']) + 1):
+            np.random.seed(int(G[f'{key}/seed'][t - 1]))
+            j = S.pointer
+            S, state, reward, done = od.update(cfg, S, int(G[f'{key}/action'][t - 1]), ev, optimum, lb, ub, od.NumpyTape(cfg.NP, dim, nc))
+            tag = f'{key} step {t}'
+            np.testing.assert_array_equal(S.pop[j], G[f'{key}/row'][t - 1], err_msg=tag)
+            np.testing.assert_allclose(S.cost[j], G[f'{key}/row_cost'][t - 1], rtol=1e-6, atol=1e-10, err_msg=tag)
+            assert S.survival[j] == G[f'{key}/row_survival'][t - 1], tag
+            np.testing.assert_array_equal(S.best(), G[f'{key}/gbest'][t - 1], err_msg=tag)
+            np.testing.assert_allclose(float(S.gbest_cost), float(G[f'{key}/gbest_cost'][t - 1]), rtol=1e-6, atol=1e-10, err_msg=tag)
+            np.testing.assert_allclose(state, G[f'{key}/state'][t - 1], rtol=2e-5, atol=1e-8, err_msg=tag)
+            np.testing.assert_allclose(reward, G[f'{key}/reward'][t - 1], rtol=1e-12, err_msg=tag)
+            assert done == bool(G[f'{key}/done'][t - 1]) and S.fes == int(G[f'{key}/fes'][t - 1]) == 200 + 200 * t, tag
+            assert S.log_index == int(G[f'{key}/log_index'][t - 1]) and len(S.curve) == int(G[f'{key}/curve_len'][t - 1]), tag
+            np.testing.assert_allclose(float(S.curve[-1]), float(G[f'{key}/curve_last'][t - 1]), rtol=1e-6, atol=1e-10, err_msg=tag)
+            S.cost[j] = G[f'{key}/row_cost'][t - 1]; S.gbest_cost = np.float32(G[f'{key}/gbest_cost'][t - 1])   # last-bit teacher forcing of costs
+            seen_done |= done
+        np.testing.assert_array_equal(S.pop, G[f'{key}/final_pop'], err_msg=f'{key} final pop')
+        np.testing.assert_array_equal(S.survival, G[f'{key}/final_survival'])
+        assert seen_done == (key == 'f1_d10')
+    with pytest.raises(ValueError):
+        od.update(cfg, S, 3, ev, optimum, lb, ub, od.NumpyTape(cfg.NP, dim, nc))
