@@ -191,6 +191,17 @@ class DE_DDQN_FusedNet:
         return (action, qv) if q else action
 
 
+class DEDQN_Net(MLP):
+    """Q-network of DEDQN_Agent: 4 -> 10 -> 10 -> 3 (dedqn_agent.py:13-15); greedy rollout action = argmax Q (:44-53, :87-96)."""
+
+    def __init__(self):
+        super().__init__(_mlp_cfg([4, 10, 10, 3]))
+
+    @torch.no_grad()
+    def act(self, state):
+        return torch.argmax(self.forward(state), dim=-1)
+
+
 # ------------------------------------------------------------------------------------------ LDE
 class LDE_PolicyNet(nn.Module):
     """LSTM(NP+10 -> 50) + Linear mu/sigma heads -> 2*NP (lde_agent.py:8-29)."""

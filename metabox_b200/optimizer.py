@@ -842,3 +842,7 @@ class QLPSO_Optimizer(Learnable_Optimizer):
         state, reward, done = self._engine.update(a.to(self._engine.device))
         self._sync()
         return int(state[0].item()), int(reward[0].item()), bool(done[0].item())
+
+
+# ======================================================================================== DEDQN (composed step, see dedqn.py)
+from .dedqn import DEDQN_Engine, DEDQN_Optimizer  # noqa: E402,F401

@@ -370,6 +370,24 @@ class InstancePack:
             _lib.check(rc, 'mbx_eval')
             return out.cpu().numpy()
 
+    def eval_device(self, lane_inst, x, subtract_optimum=False, seed=0, gen=0):
+        """Device-resident twin of `eval_lanes`: lane_inst int32 [B] and x float32/float64 [B, NP, D] are tensors on the pack's device,
+        the result [B, NP] (same dtype as x) stays there; launched on the current stream, no synchronisation."""
+        import torch
+        if x.device != self.device or lane_inst.device != self.device or lane_inst.dtype != torch.int32:
+            raise ValueError('eval_device: lane_inst (int32) and x must live on the pack\'s device')
+        if x.dtype not in (torch.float32, torch.float64) or x.dim() != 3 or x.shape[2] != self.dim or lane_inst.shape != x.shape[:1]:
+            raise ValueError(f'eval_device: x must be float32/float64 [B, NP, {self.dim}] with lane_inst [B]: got {x.dtype} {tuple(x.shape)}')
+        x = x.contiguous()
+        B, NP, D = x.shape
+        out = torch.empty((B, NP), dtype=x.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_eval(self.kind, _lib.ptr(self.headers), _lib.ptr(self.consts), _lib.ptr(lane_inst), _lib.ptr(x),
+                                     int(x.dtype == torch.float64), _lib.ptr(out), B, NP, D, int(subtract_optimum), seed, gen, None,
+                                     _lib.stream_ptr())
+        _lib.check(rc, 'mbx_eval')
+        return out
+
     def eval_host(self, index, x, seed=0, gen=0):
         return self.eval_lanes([index], x[None], seed=seed, gen=gen)[0]
 

@@ -212,6 +212,22 @@ class DE_DDQN_Sweep(_Sweep):
         return torch.argmax(q, dim=-1).to(torch.int32)
 
 
+class DEDQN_Sweep(_Sweep):
+    """DEDQN_Agent.rollout_episode (dedqn_agent.py:87-96): greedy argmax of the 4 -> 10 -> 10 -> 3 Q-network on the landscape features;
+    every step charges 2 * NP evaluations, so a run is (maxFEs - 2 NP) / (2 NP) steps.  The engine is a composition of library kernels and
+    torch ops with a python-side pointer, so it runs eagerly (no graph capture)."""
+
+    def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=16, time_kernels=False, graph=False):
+        from .dedqn import DEDQN_Engine
+        eng = DEDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, int(math.ceil(maxFEs / (2 * eng.NP))) + 1, poll, False, 1, time_kernels)
+        self.net = net
+        self.kernels_per_step = 3                         # mbx_eval (trial), mbx_eval (population), mbx_landscape_features
+
+    def _policy(self, feat):
+        return torch.argmax(self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0)), dim=-1)
+
+
 class GLEET_Sweep(_Sweep):
     """GLEET_Agent.rollout_episode (gleet_agent.py:293-303): `policy(state [B,NP,27]) -> action [B,NP]` in [0,1] (the
     reference's attention actor, or any torch callable, runs on the same stream between the fused steps)."""

@@ -9,6 +9,7 @@ gleet_kat/*  the UNMODIFIED reference actor evaluated on seeded [B, NP, 27] stat
 gleet0/*, gleet0_kat/*   the same for checkpoint 0 (the freshly initialised actor, whose mu / sigma heads are not saturated -- the trained
              checkpoint answers mu ~ 1, sigma ~ 0.7 almost everywhere, which pins the attention stack but hardly the heads); case 'r' of
              both KAT groups uses states the reference GLEET_Optimizer itself produced (tests/golden/gleet.npz)
+dedqn/*, dedqn_kat/*   Q-network of the shipped `DEDQN_Agent` (src/agent/dedqn_agent.py:13-25) + Q-values on states of reference runs
 rl_pso/*     state_dict of `RL_PSO_Agent`'s PolicyNetwork (src/agent/rl_pso_agent.py:9-45) from `agent_model/test/bbob_easy`
 rl_pso_kat/* mu / sigma for seeded [B, 2*dim] states (dim 10: the shipped weights are dimension-specific), plus the
              reference's out-of-range action transformation evaluated on hand-built samples
@@ -85,6 +86,14 @@ def main():
         for k, v in dict(x=x, mu=mu, sigma=sigma, eps=eps, action=action).items():
             out['rl_pso_kat/' + k] = v.numpy()
         out['rl_pso_kat/max_sigma'] = np.float64(net._PolicyNetwork__max_sigma); out['rl_pso_kat/min_sigma'] = np.float64(net._PolicyNetwork__min_sigma)
+        # ------------------------------------------------------------------ DEDQN (dedqn_agent.py:13-25: MLP 4 -> 10 -> 10 -> 3)
+        ag = _load('test/bbob_easy/DEDQN_Agent.pkl')
+        dqn = ag._DEDQN_Agent__dqn.cpu()
+        for k, v in dqn.state_dict().items():
+            out['dedqn/' + k] = v.numpy()
+        GD = np.load(os.path.join(HERE, 'dedqn.npz'))
+        x = torch.as_tensor(np.concatenate([GD[f'{c}/state'][::13] for c in GD['cases']]).astype(np.float32))     # states of reference runs
+        out['dedqn_kat/x'] = x.numpy(); out['dedqn_kat/q'] = dqn(x).numpy()
     np.savez_compressed(os.path.join(HERE, 'agents2.npz'), **out)
     print('rl_pso mu', mu.min().item(), mu.max().item(), 'sigma', sigma.min().item(), sigma.max().item(), 'filtered samples:', int(filt.sum()), 'of', filt.numel())
 

@@ -265,3 +265,83 @@ def test_gleet_trainer_collects_on_the_gpu_and_updates():
     assert seg['states'].shape == (10, 3, 100, 27) and seg['actions'].shape == (10, 3, 100) and seg['logp'].shape == (10, 3)
     assert torch.all(seg['weight'] == 1) and torch.all(seg['rewards'] >= 0) and seg['next_state'].shape == (3, 100, 27)
     assert torch.all((seg['actions'] >= 0) & (seg['actions'] <= 1))
+
+
+# ------------------------------------------------------------------------------------------------ DEDQN backbone (composed step, metabox_b200/dedqn.py)
+def test_dedqn_engine_on_the_device_vs_oracle():
+    """The composed DEDQN step with the real kernels (mbx_eval, mbx_landscape_features): every step the oracle replays the engine's own
+    draws from the engine's previous state -- replaced rows bit-exact, costs to float32 rounding, landscape features of the engine's own
+    (walk, cost) pair against the oracle's functions."""
+    import torch
+    from metabox_b200 import dedqn as md, problem as mp
+    from oracle import bbob as ob, dedqn as od, landscape as ola
+    dim, maxFEs, fids = 10, 20000, [1, 3, 9, 17, 21, 24]
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', dim, 5)
+    probs = {p.fid: p for p in tr.data + te.data}
+    otr, ote = ob.make_suite('bbob', dim, 5.0)
+    oin = {i.fid: i for i in otr + ote}
+    pack = mp.InstancePack([probs[f] for f in fids])
+    eng = md.DEDQN_Engine(pack, list(range(len(fids))), maxFEs, 50, seed=12)
+    cfg = od.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    assert eng.feature.shape == (len(fids), 4) and torch.all(eng.fes == 200)
+    g = np.random.RandomState(1)
+    for t in range(1, 31):
+        action = g.randint(0, 3, size=len(fids))
+        prev = [eng.read_state(b) for b in range(len(fids))]
+        p = eng.pointer
+        feat, reward, done = eng.update(torch.as_tensor(action).cuda(), check_action=True)
+        tp = {k: v.cpu().numpy() for k, v in eng.last_tape.items()}
+        smp, cst = eng.last_sample.cpu().numpy(), eng.last_cost.cpu().numpy()
+        for b, f in enumerate(fids):
+            I = oin[f]
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            q = prev[b]
+            S = od.State(pop=q['pop'], cost=q['cost'], survival=q['survival'], gbest_row=int(q['gbest_row']), gbest=q['gbest'],
+                         gbest_cost=np.float32(q['gbest_cost']), pointer=p, fes=int(q['fes']), log_index=int(q['log_index']),
+                         curve=list(q['curve'][:int(q['curve_len'])]))
+            rec = {'r': tp['r'][b], 'jrand': tp['jrand'][b], 'cr_u': tp['cr_u'][b], 'walk_u': tp['walk_u'][b]}
+            N, state, r, d = od.update(cfg, S, int(action[b]), ev, I.optimum, -5., 5., od.ArrayTape(rec))
+            st = eng.read_state(b)
+            tag = f'step {t} lane {b} (fid {f})'
+            np.testing.assert_array_equal(st['pop'], N.pop, err_msg=tag)
+            np.testing.assert_allclose(st['cost'], N.cost, rtol=1e-6, atol=1e-10, err_msg=tag)
+            np.testing.assert_array_equal(st['survival'], N.survival, err_msg=tag)
+            assert int(st['gbest_row']) == N.gbest_row and int(st['fes']) == N.fes and int(st['log_index']) == N.log_index, tag
+            np.testing.assert_allclose(cst[b], N.cost.astype(np.float64), rtol=1e-6, atol=1e-10, err_msg=tag)      # the re-evaluated population
+            own = np.array([ola.cal_fdc(smp[b], cst[b]), ola.cal_rie(cst[b]), ola.cal_acf(cst[b]), ola.cal_nop(smp[b], cst[b])])
+            np.testing.assert_allclose(st['feature64'], own, rtol=1e-9, atol=1e-12, err_msg=tag)
+            np.testing.assert_allclose(st['feature64'], state, rtol=1e-3, atol=1e-6, err_msg=tag)
+            np.testing.assert_allclose(float(eng.reward64[b]), r, rtol=1e-12, err_msg=tag)
+    with pytest.raises(ValueError):
+        eng.update(torch.as_tensor([0, 1, 2, 3, 0, 1]).cuda(), check_action=True)
+
+
+def test_dedqn_sweep_tester_and_dropin():
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, environment as me, optimizer as mo, problem as mp, sweep
+    W, _ = _weights('dedqn')
+    net = ma.load_reference_weights(ma.DEDQN_Net(), W).cuda().eval()
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    sw = sweep.DEDQN_Sweep(pack, inst, net, 3000, 50, seed=4)
+    r1 = sweep.gather_results(sw.run(), 1).cpu().numpy()
+    r2 = sweep.gather_results(sweep.DEDQN_Sweep(pack, inst, net, 3000, 50, seed=4).run(), 1).cpu().numpy()
+    np.testing.assert_array_equal(r1, r2)                                                  # same seed -> same rows
+    assert np.all((r1[:, 51] == 3000) | (r1[:, 50] <= 1e-8)) and np.all(np.diff(r1[:, :51], axis=1) <= 0) and np.isfinite(r1).all()
+    assert np.all(r1[:, 52] > 0) and sw.launches >= 3 * 14
+    # drop-in: PBO_Env + DEDQN_Optimizer with the reference's signatures
+    cfg = argparse.Namespace(dim=10, maxFEs=3000, n_logpoint=50, log_interval=60)
+    env = me.PBO_Env(probs[0], mo.DEDQN_Optimizer(cfg))
+    np.random.seed(0)
+    state = env.reset()
+    assert state.shape == (4,) and state.dtype == np.float64 and env.optimizer.fes == 200 and len(env.optimizer.cost) == 1
+    done, n = False, 0
+    while not done:
+        state, reward, done = env.step(int(np.random.randint(0, 3)))
+        assert isinstance(reward, float) and 0 < reward <= 1 and state.shape == (4,)
+        n += 1
+    assert n == 14 and env.optimizer.fes == 3000 and len(env.optimizer.cost) == 16           # ONE log point per step (:183-185) + the final one
+    with pytest.raises(ValueError):
+        env.step(3)

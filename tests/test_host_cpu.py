@@ -180,6 +180,10 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
     a = net(x, noise=torch.as_tensor(G['rl_pso_kat/eps']))
     np.testing.assert_allclose(a.numpy(), G['rl_pso_kat/action'], rtol=1e-5, atol=1e-6)          # incl. 3 out-of-range samples
     assert a.shape == (9, 1)
+    dq = ma.load_reference_weights(ma.DEDQN_Net(), sub('dedqn/'))                      # Q-network of the shipped DEDQN agent, states of reference runs
+    q = dq(torch.as_tensor(G['dedqn_kat/x']))
+    np.testing.assert_allclose(q.detach().numpy(), G['dedqn_kat/q'], rtol=1e-5, atol=1e-6)
+    assert torch.equal(dq.act(torch.as_tensor(G['dedqn_kat/x'])), torch.as_tensor(np.argmax(G['dedqn_kat/q'], axis=1)))
 
 
 def _emul_lib(name='gleet_policy'):
@@ -754,3 +758,114 @@ def test_bench_product_arm_refuses_to_run_without_a_gpu():
                        timeout=600, cwd=root)
     assert r.returncode != 0 and not any(ln.startswith('{') for ln in r.stdout.splitlines())
     assert 'CUDA' in (r.stderr + r.stdout)
+
+
+# ----------------------------------------------------------------------------------------- DEDQN engine: host logic with injected kernels
+def _dedqn_cpu_engine(fids, dim, maxFEs, seed=3):
+    """DEDQN_Engine on CPU tensors: the two CUDA kernels it composes (mbx_eval, mbx_landscape_features) are replaced by the oracle's
+    functions, everything else -- the batched single-row DE arithmetic, selection, survival, accounting, curve protocol -- is the product
+    code.  (Only tests can inject kernels; the product constructor needs a CUDA InstancePack.)"""
+    import torch
+    from metabox_b200 import dedqn as md
+    from oracle import bbob as ob, landscape as ola
+    tr, te = ob.make_suite('bbob', dim, 5.0, 'easy')
+    insts = [[i for i in tr + te if i.fid == f][0] for f in fids]
+
+    def ev(x, gen):
+        x = x.numpy().astype(np.float64)
+        return torch.as_tensor(np.stack([(ob.func_true(I, x[b]) - I.optimum).astype(np.float32) for b, I in enumerate(insts)]))
+
+    def feats(sample, cost):
+        s, c = sample.numpy(), cost.numpy()
+        return torch.as_tensor(np.array([[ola.cal_fdc(s[b], c[b]), ola.cal_rie(c[b]), ola.cal_acf(c[b]), ola.cal_nop(s[b], c[b])] for b in range(len(s))]))
+
+    eng = md.DEDQN_Engine(None, list(range(len(fids))), maxFEs, 50, seed=seed, _kernels=dict(dim=dim, lb=-5., ub=5., has_opt=True, eval=ev, features=feats))
+    return eng, insts
+
+
+def test_dedqn_engine_host_logic_vs_oracle_with_injected_kernels():
+    """Every step the engine draws its own tape on (CPU) tensors; the oracle replays exactly those draws from the engine's previous
+    state: population / costs / survival / gbest bit-exact, features and reward to rounding, accounting and curve equal, lanes freeze
+    when done."""
+    import torch
+    from oracle import bbob as ob, dedqn as od
+    fids, dim, maxFEs = [1, 8, 15, 21], 10, 4400                  # 21 steps after init
+    eng, insts = _dedqn_cpu_engine(fids, dim, maxFEs)
+    cfg = od.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    t0 = {k: v.numpy() for k, v in eng.last_tape.items()}
+    S = []
+    for b, I in enumerate(insts):
+        ev = lambda x, draws, I=I: ob.func_true(I, x)
+        s, state = od.init_population(cfg, ev, I.optimum, -5., 5., od.ArrayTape({'init_u': t0['init_u'][b], 'walk_u': t0['walk_u'][b]}))
+        st = eng.read_state(b)
+        np.testing.assert_array_equal(st['pop'], s.pop); np.testing.assert_array_equal(st['cost'], s.cost)
+        assert int(st['gbest_row']) == s.gbest_row and int(st['fes']) == s.fes == 200
+        np.testing.assert_allclose(st['feature64'], state, rtol=1e-9, atol=1e-12)
+        S.append(s)
+    g = np.random.RandomState(0)
+    for t in range(1, 24):
+        action = g.randint(0, 3, size=len(fids))
+        was_done = eng.done.numpy().copy()
+        before = [eng.read_state(b) for b in range(len(fids))]
+        feat, reward, done = eng.update(torch.as_tensor(action), check_action=True)
+        tp = {k: v.numpy() for k, v in eng.last_tape.items()}
+        for b, I in enumerate(insts):
+            st = eng.read_state(b)
+            if was_done[b]:
+                for k in ('pop', 'cost', 'survival', 'fes', 'curve', 'curve_len', 'feature64'):
+                    np.testing.assert_array_equal(st[k], before[b][k], err_msg=f'finished lane {b} changed {k}')
+                assert float(reward[b]) == 0.0
+                continue
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            rec = {'r': tp['r'][b], 'jrand': tp['jrand'][b], 'cr_u': tp['cr_u'][b], 'walk_u': tp['walk_u'][b]}
+            s, state, r, d = od.update(cfg, S[b], int(action[b]), ev, I.optimum, -5., 5., od.ArrayTape(rec))
+            tag = f'step {t} lane {b}'
+            np.testing.assert_array_equal(st['pop'], s.pop, err_msg=tag); np.testing.assert_array_equal(st['cost'], s.cost, err_msg=tag)
+            np.testing.assert_array_equal(st['survival'], s.survival, err_msg=tag)
+            assert int(st['gbest_row']) == s.gbest_row and float(st['gbest_cost']) == float(s.gbest_cost), tag
+            if s.gbest_row < 0:
+                np.testing.assert_array_equal(st['gbest'], s.gbest, err_msg=tag)
+            np.testing.assert_allclose(st['feature64'], state, rtol=1e-9, atol=1e-12, err_msg=tag)
+            np.testing.assert_allclose(float(eng.reward64[b]), r, rtol=1e-13, err_msg=tag)
+            assert int(st['fes']) == s.fes and int(st['log_index']) == s.log_index and bool(st['done']) == d, tag
+            np.testing.assert_array_equal(st['curve'][:int(st['curve_len'])], np.array(s.curve, dtype=np.float32), err_msg=tag)
+            S[b] = s
+    assert bool((eng.done != 0).all()) and all(len(c) == 51 for c in eng.cost_curves())
+    assert int(eng.fes.max()) == 4400
+    with pytest.raises(ValueError):
+        eng.update(torch.as_tensor([0, 1, 2, 3]), check_action=True)
+    with pytest.raises(ValueError):
+        eng.update(torch.as_tensor([0, 1]))
+
+
+def test_dedqn_engine_replays_the_reference_tape():
+    """Golden steps of the unmodified reference (tests/golden/dedqn.npz, one noise-free BBOB case) through the ENGINE's host logic: the
+    reference's own draws are recovered by re-seeding np.random (NumpyTape) and handed to the engine as a tape."""
+    import torch
+    from oracle import bbob as ob, dedqn as od
+    G = np.load(os.path.join(GOLDEN, 'dedqn.npz'))
+    key, dim = 'f15_d10', 10
+    eng, insts = _dedqn_cpu_engine([15], dim, int(G[f'{key}/maxFEs']))
+    nt = od.NumpyTape(100, dim)
+    np.random.seed(int(G[f'{key}/seed0']))
+    nt.init_u(); nt.walk_u()
+    eng.init_population(tape={'init_u': nt.rec['init_u'][None], 'walk_u': nt.rec['walk_u'][None]})
+    np.testing.assert_array_equal(eng.pop[0].numpy(), G[f'{key}/s0/pop'])
+    np.testing.assert_allclose(eng.feature64[0].numpy(), G[f'{key}/s0/state'], rtol=1e-6, atol=1e-9)
+    for t in range(1, 61):
+        a = int(G[f'{key}/action'][t - 1])
+        np.random.seed(int(G[f'{key}/seed'][t - 1]))
+        j = eng.pointer
+        nt = od.NumpyTape(100, dim)
+        nt.r(od.N_COLS[a], j); nt.crossover(); nt.walk_u()
+        tape = {'r': nt.rec['r'][None], 'jrand': np.array([nt.rec['jrand']]), 'cr_u': nt.rec['cr_u'][None], 'walk_u': nt.rec['walk_u'][None]}
+        feat, reward, done = eng.update(torch.as_tensor([a]), tape=tape)
+        tag = f'step {t}'
+        np.testing.assert_array_equal(eng.pop[0, j].numpy(), G[f'{key}/row'][t - 1], err_msg=tag)
+        np.testing.assert_allclose(float(eng.cost[0, j]), float(G[f'{key}/row_cost'][t - 1]), rtol=1e-6, err_msg=tag)
+        assert float(eng.survival[0, j]) == float(G[f'{key}/row_survival'][t - 1]), tag
+        np.testing.assert_allclose(eng.feature64[0].numpy(), G[f'{key}/state'][t - 1], rtol=2e-5, atol=1e-8, err_msg=tag)
+        np.testing.assert_allclose(float(eng.reward64[0]), float(G[f'{key}/reward'][t - 1]), rtol=1e-12, err_msg=tag)
+        assert int(eng.fes[0]) == int(G[f'{key}/fes'][t - 1]) and int(eng.log_index[0]) == int(G[f'{key}/log_index'][t - 1]), tag
+        assert int(eng.curve_len[0]) == int(G[f'{key}/curve_len'][t - 1]), tag
