@@ -55,7 +55,8 @@ def parse():
                          'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); '
                          'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
     ap.add_argument('--fused-policy', action='store_true',
-                    help='deddqn: the Q-network + argmax as ONE kernel per step (agent.DE_DDQN_FusedNet -> mbx_deddqn_policy); '
+                    help='rlepso: the actor as ONE kernel per generation (agent.RLEPSO_FusedActor -> mbx_rlepso_policy); '
+                         'deddqn: the Q-network + argmax as ONE kernel per step (agent.DE_DDQN_FusedNet -> mbx_deddqn_policy); '
                          'gleet: same as --gleet-policy fused')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
@@ -277,6 +278,9 @@ def main():
     if args.fused_policy and args.workload == 'deddqn':
         from metabox_b200 import agent as magent
         net, wsrc = magent.DE_DDQN_FusedNet(net), wsrc + ', fused Q-network kernel (mbx_deddqn_policy)'
+    if args.fused_policy and args.workload == 'rlepso':
+        from metabox_b200 import agent as magent
+        net, wsrc = magent.RLEPSO_FusedActor(net), wsrc + ', fused actor kernel (mbx_rlepso_policy)'
     inst, run = msweep.lane_table(len(problems), args.runs)
     if args.lane_order == 'run-major':                        # every contiguous stripe / rank sees the same mix of functions
         inst = np.ascontiguousarray(inst.reshape(len(problems), args.runs).T.reshape(-1))

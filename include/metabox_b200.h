@@ -348,6 +348,18 @@ int mbx_gleet_policy(const float* d_state, const float* d_weights, int n_weights
                      float* d_mu, float* d_sigma, float* d_logits, int B, int NP, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * RLEPSO actor, rollout forward -- replaces `Actor.forward` (agent/rlepso_agent.py:22-47; two MLPs 1 -> 64 -> 32 -> 35), called once per
+ * generation from `rollout_episode` (:294-303), for B lanes at once.
+ *   d_state   [B] (or [B,1]) f32 = fes / maxFEs, the feature mbx_rlepso_init / mbx_rlepso_step write
+ *   d_weights [mbx_rlepso_policy_weight_count()] f32, packed as documented in metabox_b200/csrc/mbx_rlepso_policy.cuh
+ *             (agent.py RLEPSO_Actor.pack()); read on every launch
+ *   d_noise   [B,35] f32 standard-normal draws, or null (action = clamp(mu, 0, 1))
+ *   outputs:  d_action [B,35] f32 = clamp(mu + sigma * noise, 0, 1) ; optional d_mu, d_sigma [B,35]                              */
+int mbx_rlepso_policy_weight_count(void);
+int mbx_rlepso_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                      float* d_mu, float* d_sigma, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DE-DDQN Q-network, greedy rollout action -- replaces `__get_action(state, epsilon_greedy=False)` (agent/de_ddqn_agent.py:59-68) on
  * the MLP 99 -> 100 -> 100 -> 100 -> 100 -> 4 (:21-25) for B lanes at once; called once per function evaluation from
  * `rollout_episode` (:108-117).

@@ -131,6 +131,8 @@ SIGNATURES = {
     'mbx_qlpso_step': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxQlpsoState), C.POINTER(MbxQlpsoTape), _P,
                                  _P, _P, C.c_int, _P]),
     'mbx_landscape_features': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    'mbx_rlepso_policy_weight_count': (C.c_int, []),
+    'mbx_rlepso_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     'mbx_deddqn_policy_weight_count': (C.c_int, []),
     'mbx_deddqn_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     'mbx_gleet_policy_weight_count': (C.c_int, []),

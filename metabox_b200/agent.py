@@ -97,6 +97,62 @@ class RLEPSO_Actor(nn.Module):
         return torch.clamp(mu + sigma * eps, min=0, max=1)
 
 
+    @torch.no_grad()
+    def pack(self, out=None):
+        """All parameters as ONE float32 vector in the layout `mbx_rlepso_policy` reads (csrc/mbx_rlepso_policy.cuh): per network (mu, sigma)
+        L0 w [64] | b [64] | L1 W^T [64][32] | b [32] | L2 W^T [32][35] | b [35]."""
+        parts = []
+        for net in (self.mu_net, self.sigma_net):
+            l0, l1, l2 = [m for m in net.net if isinstance(m, nn.Linear)]
+            parts += [l0.weight[:, 0], l0.bias, l1.weight.t(), l1.bias, l2.weight.t(), l2.bias]
+        flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for t in parts])
+        if out is None:
+            return flat.contiguous()
+        out.copy_(flat)
+        return out
+
+
+class RLEPSO_FusedActor:
+    """`RLEPSO_Actor`'s rollout forward as ONE CUDA kernel per generation (C ABI `mbx_rlepso_policy`, csrc/mbx_rlepso_policy.cu) instead of
+    ~20 torch launches; same call convention (`policy(state [B,1], noise=None) -> action [B,35]`, `takes_noise`, `action_dim`), so it
+    plugs into `sweep.RLEPSO_Sweep`.  `refresh()` re-packs the weights in place after an optimiser step on `actor`."""
+    takes_noise = True
+    fused_action = True
+    action_dim = 35
+
+    def __init__(self, actor: 'RLEPSO_Actor'):
+        from . import _lib
+        self.actor = actor
+        self.packed = actor.pack()
+        n = _lib.lib().mbx_rlepso_policy_weight_count()
+        if self.packed.numel() != n:
+            raise _lib.MbxError(f'RLEPSO_Actor.pack() produced {self.packed.numel()} weights, libmbx.so expects {n}')
+        if not self.packed.is_cuda:
+            raise _lib.MbxError('RLEPSO_FusedActor needs the actor on a CUDA device (there is no CPU path)')
+
+    def refresh(self):
+        self.actor.pack(out=self.packed)
+        return self
+
+    @torch.no_grad()
+    def __call__(self, x, noise=None, outputs=False):
+        """-> action [B,35]; with `outputs=True` -> (action, mu [B,35], sigma [B,35])."""
+        from . import _lib
+        if x.dtype != torch.float32 or x.device != self.packed.device or x.numel() != x.shape[0]:
+            raise ValueError(f'state must be float32 [B] or [B, 1] on {self.packed.device}: got {x.dtype} {tuple(x.shape)} on {x.device}')
+        x = x.contiguous()
+        B = x.shape[0]
+        if noise is not None:
+            noise = noise.to(torch.float32).reshape(B, 35).contiguous()
+        action = torch.empty(B, 35, dtype=torch.float32, device=x.device)
+        mu, sigma = (torch.empty_like(action), torch.empty_like(action)) if outputs else (None, None)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().mbx_rlepso_policy(_lib.ptr(x), _lib.ptr(self.packed), self.packed.numel(), _lib.ptr(noise), _lib.ptr(action),
+                                              _lib.ptr(mu), _lib.ptr(sigma), B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rlepso_policy')
+        return (action, mu, sigma) if outputs else action
+
+
 class RLEPSO_Critic(nn.Module):
     """Value head 1 -> 16 -> 8 -> 1 (rlepso_agent.py:49-61); forward(x [..., 1]) -> value [...]."""
 

@@ -5,6 +5,7 @@
 #include "mbx_deddqn_policy.cuh"
 #include "mbx_gleet_policy.cuh"
 #include "mbx_launch.h"
+#include "mbx_rlepso_policy.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -170,6 +171,17 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
     return mbx_launch_landscape(d_sample, d_cost, d_ref, B, S, D, d_out, (cudaStream_t)stream);
 }
 
+
+int mbx_rlepso_policy_weight_count(void) { return rlp::N_WEIGHTS; }
+
+int mbx_rlepso_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                      float* d_mu, float* d_sigma, int B, void* stream) {
+    MBX_REQUIRE(B >= 0, "mbx_rlepso_policy: bad shape B=%d", B);
+    MBX_REQUIRE(n_weights == rlp::N_WEIGHTS, "mbx_rlepso_policy: %d packed weights, expected %d", n_weights, rlp::N_WEIGHTS);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_state && d_weights && d_action, "mbx_rlepso_policy: null pointer");
+    return mbx_launch_rlepso_policy(d_state, d_weights, d_noise, d_action, d_mu, d_sigma, B, (cudaStream_t)stream);
+}
 
 int mbx_deddqn_policy_weight_count(void) { return ddq::N_WEIGHTS; }
 

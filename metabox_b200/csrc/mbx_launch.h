@@ -61,3 +61,5 @@ int mbx_launch_rl_pso_step(int kind, const MbxInstance* inst, const double* cons
 int mbx_launch_gleet_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
                             float* logits, int B, int NP, cudaStream_t st);
 int mbx_launch_deddqn_policy(const float* state, const float* weights, int32_t* action, float* q, int B, cudaStream_t st);
+int mbx_launch_rlepso_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
+                             int B, cudaStream_t st);

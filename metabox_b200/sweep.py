@@ -165,6 +165,7 @@ class RLEPSO_Sweep(_Sweep):
         super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
         self.actor = actor
         self.finite_reward = True
+        self.kernels_per_step = 2 if getattr(actor, 'fused_action', False) else 1
 
     def _policy(self, feat):
         if getattr(self.actor, 'takes_noise', False):

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from metabox_b200 import agent as ma   # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--only', default='both', choices=['both', 'gleet', 'deddqn'])
+ap.add_argument('--only', default='both', choices=['both', 'gleet', 'deddqn', 'rlepso'])
 ap.add_argument('--reps', type=int, default=20)
 a = ap.parse_args()
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
@@ -54,3 +54,12 @@ if a.only in ('both', 'deddqn'):
         t_torch, t_fused = timed(ref, a.reps), timed(lambda: fused(x), a.reps)
         agree = float((ref() == fused(x)).float().mean())
         print(f'deddqn policy B={B:5d}:        torch module {t_torch:8.3f} ms   fused kernel {t_fused:8.3f} ms   x{t_torch / t_fused:6.1f}   actions equal {agree:.4f}')
+if a.only in ('both', 'rlepso'):
+    G = np.load(os.path.join(GOLD, 'agents.npz'))
+    actor = ma.load_reference_weights(ma.RLEPSO_Actor(), {k[7:]: G[k] for k in G.files if k.startswith('rlepso/')}).cuda().eval()
+    fused = ma.RLEPSO_FusedActor(actor)
+    for B in (2048, 6144):
+        x = torch.rand(B, 1, device='cuda'); nz = torch.randn(B, 35, device='cuda')
+        t_torch, t_fused = timed(lambda: actor(x, noise=nz), a.reps), timed(lambda: fused(x, noise=nz), a.reps)
+        err = float((actor(x, noise=nz) - fused(x, noise=nz)).abs().max())
+        print(f'rlepso policy B={B:5d}:        torch module {t_torch:8.3f} ms   fused kernel {t_fused:8.3f} ms   x{t_torch / t_fused:6.1f}   max |diff| {err:.2e}')

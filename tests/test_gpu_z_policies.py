@@ -345,3 +345,33 @@ def test_dedqn_sweep_tester_and_dropin():
     assert n == 14 and env.optimizer.fes == 3000 and len(env.optimizer.cost) == 16           # ONE log point per step (:183-185) + the final one
     with pytest.raises(ValueError):
         env.step(3)
+
+
+# ------------------------------------------------------------------------------------------------ fused RLEPSO actor kernel (mbx_rlepso_policy)
+def test_fused_rlepso_policy_kernel_and_sweep():
+    import torch
+    from metabox_b200 import agent as ma, sweep
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    actor = ma.load_reference_weights(ma.RLEPSO_Actor(), {k[len('rlepso/'):]: G[k] for k in G.files if k.startswith('rlepso/')}).cuda().eval()
+    fused = ma.RLEPSO_FusedActor(actor)
+    act, mu, sigma = fused(torch.as_tensor(G['rlepso_kat/x']).cuda(), outputs=True)
+    np.testing.assert_allclose(mu.cpu().numpy(), G['rlepso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sigma.cpu().numpy(), G['rlepso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    g = torch.Generator(device='cpu').manual_seed(2)
+    for B in (1, 3, 4, 5, 6144):                                                           # ragged last CTA (4 lanes per CTA)
+        x = torch.rand(B, 1, generator=g).cuda(); nz = torch.randn(B, 35, generator=g).cuda()
+        np.testing.assert_allclose(fused(x, noise=nz).cpu().numpy(), actor(x, noise=nz).cpu().numpy(), rtol=2e-5, atol=3e-6, err_msg=f'B {B}')
+        assert torch.equal(fused(x.reshape(-1)), torch.clamp(fused(x, outputs=True)[1], 0, 1))
+    assert fused(torch.zeros(0, 1).cuda()).shape == (0, 35)
+    with pytest.raises(ValueError):
+        fused(torch.zeros(4, 2).cuda())
+    # complete sweeps: graph replay == eager launches with the mean action, sampled sweep sane
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    mean = lambda st: fused(st)
+    ra = rows(sweep.RLEPSO_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=True, poll=8))
+    rb = rows(sweep.RLEPSO_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=False, poll=8))
+    np.testing.assert_array_equal(ra, rb)
+    r = rows(sweep.RLEPSO_Sweep(pack, inst, fused, 3000, 50, seed=9, graph=True, poll=8))
+    assert np.all((r[:, 51] >= 3000) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] < 3200) and np.all(np.abs(r[:, 52]) <= 31)

@@ -42,6 +42,11 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.mbx_gleet_policy(ctypes.c_void_p(256), ctypes.c_void_p(260), n, None, ctypes.c_void_p(256), None, None, None, 1, 100, None) == -1 \
         and b'aligned' in lib.mbx_last_error()
     assert lib.mbx_gleet_policy(None, None, n, None, None, None, None, None, 0, 100, None) == 0          # empty batch: nothing to do
+    k = lib.mbx_rlepso_policy_weight_count()
+    assert k == 6726
+    assert lib.mbx_rlepso_policy(None, None, k - 2, None, None, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
+    assert lib.mbx_rlepso_policy(None, None, k, None, None, None, None, 1, None) == -1 and b'null' in lib.mbx_last_error()
+    assert lib.mbx_rlepso_policy(None, None, k, None, None, None, None, 0, None) == 0
     m = lib.mbx_deddqn_policy_weight_count()
     assert m == 40704
     assert lib.mbx_deddqn_policy(None, None, m + 1, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
@@ -202,6 +207,9 @@ def _emul_lib(name='gleet_policy'):
         if name == 'gleet_policy':
             L.glp_host_forward.restype = C.c_int
             L.glp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
+        elif name == 'rlepso_policy':
+            L.rlp_host_forward.restype = C.c_int
+            L.rlp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, C.c_int]
         else:
             L.ddq_host_forward.restype = C.c_int
             L.ddq_host_forward.argtypes = [fp, fp, C.POINTER(C.c_int32), fp, C.c_int]
@@ -257,6 +265,42 @@ def test_fused_gleet_policy_arithmetic_on_the_host_matches_the_reference():
         np.testing.assert_allclose(lg, l2.detach().numpy(), rtol=2e-4, atol=3e-5)
         np.testing.assert_allclose(mu, m2.detach().numpy(), rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(sg, s2.detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_rlepso_policy_arithmetic_on_the_host_matches_the_reference():
+    """The per-neuron device functions of the fused RLEPSO actor kernel (csrc/mbx_rlepso_policy.cuh) compiled for the host with the weights
+    packed by RLEPSO_Actor.pack(): (mu, sigma) of the unmodified reference on the shipped pickle (agents.npz) and the torch module's
+    sampled actions under the same noise."""
+    import ctypes as C
+    import torch
+    from metabox_b200 import agent as ma
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    actor = ma.load_reference_weights(ma.RLEPSO_Actor(), {k[len('rlepso/'):]: G[k] for k in G.files if k.startswith('rlepso/')})
+    w = np.ascontiguousarray(actor.pack().numpy())
+    L = _emul_lib('rlepso_policy')
+    assert L.rlp_host_weight_count() == w.size == 2 * (64 + 64 + 64 * 32 + 32 + 32 * 35 + 35)
+    fp = C.POINTER(C.c_float)
+
+    def run(x, noise=None):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        act = np.empty((len(x), 35), np.float32); mu = np.empty_like(act); sg = np.empty_like(act)
+        nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32)
+        assert L.rlp_host_forward(x.ctypes.data_as(fp), w.ctypes.data_as(fp), None if nz is None else nz.ctypes.data_as(fp),
+                                  act.ctypes.data_as(fp), mu.ctypes.data_as(fp), sg.ctypes.data_as(fp), len(x)) == 0
+        return act, mu, sg
+
+    act, mu, sg = run(G['rlepso_kat/x'])
+    np.testing.assert_allclose(mu, G['rlepso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sg, G['rlepso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(act, np.clip(mu, 0, 1))
+    g = np.random.RandomState(4)
+    x = g.rand(37, 1).astype(np.float32); noise = g.randn(37, 35).astype(np.float32)
+    act, mu, sg = run(x, noise)
+    want = actor(torch.as_tensor(x), noise=torch.as_tensor(noise)).numpy()
+    np.testing.assert_allclose(act, want, rtol=1e-5, atol=2e-6)
+    act, _, _ = run(x, 50 * noise)                                                  # wild draws: the clamp to [0, 1] is part of the action
+    np.testing.assert_allclose(act, actor(torch.as_tensor(x), noise=torch.as_tensor(50 * noise)).numpy(), rtol=1e-5, atol=2e-6)
+    assert act.min() == 0 and act.max() == 1
 
 
 def test_fused_deddqn_policy_arithmetic_on_the_host_matches_the_reference():
