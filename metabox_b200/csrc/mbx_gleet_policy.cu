@@ -47,7 +47,7 @@ __device__ __forceinline__ void glp_block(const float* Wb, const float* qsrc, fl
     for (int c = 0; c < glp::E; ++c) h[c] = x[c];
 }
 
-__global__ void __launch_bounds__(GLP_NT, 3)
+__global__ void __launch_bounds__(GLP_NT, 4)
 gleet_policy_kernel(const float* __restrict__ state, const float* __restrict__ weights, const float* __restrict__ noise,
                     float* __restrict__ action, float* __restrict__ mu_out, float* __restrict__ sigma_out,
                     float* __restrict__ logits_out, int NP) {

@@ -90,6 +90,18 @@ GLP_HD void project(const float* Wb, const float* qsrc, const float* kvsrc, floa
     for (int c = 0; c < E; c += 4) st4(Vrow + c, t[c], t[c + 1], t[c + 2], t[c + 3]);
 }
 
+// 2^x for the softmax weights, x <= 0.  Device: one MUFU.EX2 (ex2.approx.ftz: 2 ulp, results below 2^-126 flush to zero -- such a
+// weight is < 1e-38 of the row's largest one); exp2f without fast-math wraps the same instruction in a range fix-up (4 issue slots).
+GLP_HD float exp2_neg(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+
 GLP_HD float score(const float* qs, const F4& k) { return fmaf(qs[3], k.w, fmaf(qs[2], k.z, fmaf(qs[1], k.y, qs[0] * k.x))); }
 
 // softmax(q K^T / sqrt(4)) V for the four heads of one query; two passes over the NP keys (exact maximum first), then the output
@@ -107,7 +119,7 @@ GLP_HD void attend(const float* Wb, const float* K, const float* V, int NP, cons
     for (int j = 0; j < NP; ++j) {
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-            const float p = exp2f(score(qs + HK * h, ld4(K + j * E + HK * h)) - m[h]);
+            const float p = exp2_neg(score(qs + HK * h, ld4(K + j * E + HK * h)) - m[h]);
             const F4 v = ld4(V + j * E + HK * h);
             l[h] += p;
             acc[HK * h + 0] = fmaf(p, v.x, acc[HK * h + 0]);
