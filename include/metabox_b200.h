@@ -360,6 +360,22 @@ int mbx_rlepso_policy(const float* d_state, const float* d_weights, int n_weight
                       float* d_mu, float* d_sigma, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * RL_PSO policy network, rollout forward -- replaces `PolicyNetwork.forward` (agent/rl_pso_agent.py:22-45; two MLPs 2*dim -> 32 -> 8 -> 1),
+ * called once per function evaluation from `rollout_episode` (:116-124), for B lanes at once.
+ *   d_state   [B, n_in] f32, n_in = 2*dim <= 64: the state mbx_rl_pso_init / mbx_rl_pso_step write
+ *   d_weights [mbx_rl_pso_policy_weight_count(n_in)] f32, packed as documented in metabox_b200/csrc/mbx_pso_policies.cuh
+ *   d_noise   [B] f32 standard-normal draws, or null (eps = 0)
+ *   outputs:  d_action [B] f32 (incl. the reference's transformation of samples outside (0, 1), :33-34) ; optional d_mu, d_sigma [B] */
+int mbx_rl_pso_policy_weight_count(int n_in);
+int mbx_rl_pso_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                      float* d_mu, float* d_sigma, int B, int n_in, void* stream);
+
+/* QLPSO tabular policy -- replaces `__get_action` (agent/qlpso_agent.py:33-36): action ~ softmax(Q[state]).
+ *   d_q_state [B] i32 in 0..3 (what mbx_qlpso_init / mbx_qlpso_step write) ; d_q_table [4,4] f64 ; d_u [B] f32 uniforms in [0, 1)
+ *   output:   d_action [B] i32 in 0..3 = the first k with u < cumulative softmax probability (inverse-CDF sampling)               */
+int mbx_qlpso_policy(const int32_t* d_q_state, const double* d_q_table, const float* d_u, int32_t* d_action, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DE-DDQN Q-network, greedy rollout action -- replaces `__get_action(state, epsilon_greedy=False)` (agent/de_ddqn_agent.py:59-68) on
  * the MLP 99 -> 100 -> 100 -> 100 -> 100 -> 4 (:21-25) for B lanes at once; called once per function evaluation from
  * `rollout_episode` (:108-117).

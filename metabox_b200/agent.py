@@ -530,3 +530,85 @@ class RL_PSO_PolicyNet(nn.Module):
         mu, sigma = self.distribution(x)
         a = mu + sigma * (torch.randn_like(mu) if noise is None else noise)
         return torch.where(torch.abs(a - 0.5) >= 0.5, (a + 3 * sigma - mu) * (1. / 6 * sigma), a)
+
+    @torch.no_grad()
+    def pack(self, out=None):
+        """All parameters as ONE float32 vector in the layout `mbx_rl_pso_policy` reads (csrc/mbx_pso_policies.cuh): per network (mu, sigma)
+        L0 W^T [2*dim][32] | b [32] | L1 W [8][32] | b [8] | L2 w [8] | b [1]."""
+        parts = []
+        for net in (self.mu_net, self.sigma_net):
+            l0, l1, l2 = [m for m in net.net if isinstance(m, nn.Linear)]
+            parts += [l0.weight.t(), l0.bias, l1.weight, l1.bias, l2.weight, l2.bias]
+        flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for t in parts])
+        if out is None:
+            return flat.contiguous()
+        out.copy_(flat)
+        return out
+
+
+class RL_PSO_FusedPolicy:
+    """`RL_PSO_PolicyNet`'s rollout forward as ONE CUDA kernel per environment step (C ABI `mbx_rl_pso_policy`, csrc/mbx_pso_policies.cu):
+    `policy(state [B, 2*dim], noise=None) -> action [B, 1]`, `takes_noise`; plugs into `sweep.RL_PSO_Sweep`.  `refresh()` re-packs."""
+    takes_noise = True
+    fused_action = True
+
+    def __init__(self, net: 'RL_PSO_PolicyNet'):
+        from . import _lib
+        self.net, self.n_in = net, 2 * net.dim
+        self.packed = net.pack()
+        n = _lib.lib().mbx_rl_pso_policy_weight_count(self.n_in)
+        if self.packed.numel() != n:
+            raise _lib.MbxError(f'RL_PSO_PolicyNet.pack() produced {self.packed.numel()} weights, libmbx.so expects {n}')
+        if not self.packed.is_cuda:
+            raise _lib.MbxError('RL_PSO_FusedPolicy needs the network on a CUDA device (there is no CPU path)')
+
+    def refresh(self):
+        self.net.pack(out=self.packed)
+        return self
+
+    @torch.no_grad()
+    def __call__(self, x, noise=None, outputs=False):
+        from . import _lib
+        if x.dim() != 2 or x.shape[1] != self.n_in or x.dtype != torch.float32 or x.device != self.packed.device:
+            raise ValueError(f'state must be float32 [B, {self.n_in}] on {self.packed.device}: got {x.dtype} {tuple(x.shape)} on {x.device}')
+        x = x.contiguous()
+        B = x.shape[0]
+        if noise is not None:
+            noise = noise.to(torch.float32).reshape(B).contiguous()
+        action = torch.empty(B, 1, dtype=torch.float32, device=x.device)
+        mu, sigma = (torch.empty_like(action), torch.empty_like(action)) if outputs else (None, None)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().mbx_rl_pso_policy(_lib.ptr(x), _lib.ptr(self.packed), self.packed.numel(), _lib.ptr(noise), _lib.ptr(action),
+                                              _lib.ptr(mu), _lib.ptr(sigma), B, self.n_in, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_rl_pso_policy')
+        return (action, mu, sigma) if outputs else action
+
+
+class QLPSO_FusedQTable:
+    """`QLPSO_QTable`'s sampling as ONE CUDA kernel per environment step (C ABI `mbx_qlpso_policy`): `policy(q_state [B] int32, u=None) ->
+    action [B] int32`, `takes_uniform`; plugs into `sweep.QLPSO_Sweep`.  The kernel reads the module's live float64 Q-table buffer, so
+    `td_update` needs no refresh."""
+    takes_uniform = True
+    fused_action = True
+
+    def __init__(self, qtable: 'QLPSO_QTable'):
+        from . import _lib
+        _lib.lib()
+        if not qtable.q_table.is_cuda or tuple(qtable.q_table.shape) != (4, 4):
+            raise _lib.MbxError('QLPSO_FusedQTable needs a [4, 4] Q-table on a CUDA device (there is no CPU path)')
+        self.qtable = qtable
+
+    @torch.no_grad()
+    def __call__(self, state, u=None):
+        from . import _lib
+        q = self.qtable.q_table
+        if state.dim() != 1 or state.device != q.device:
+            raise ValueError(f'q_state must be [B] on {q.device}: got {tuple(state.shape)} on {state.device}')
+        state = state.to(torch.int32).contiguous()
+        B = state.shape[0]
+        u = torch.rand(B, device=q.device, dtype=torch.float32) if u is None else u.to(torch.float32).reshape(B).contiguous()
+        action = torch.empty(B, dtype=torch.int32, device=q.device)
+        with torch.cuda.device(q.device):
+            rc = _lib.lib().mbx_qlpso_policy(_lib.ptr(state), _lib.ptr(q), _lib.ptr(u), _lib.ptr(action), B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_qlpso_policy')
+        return action

@@ -5,6 +5,7 @@
 #include "mbx_deddqn_policy.cuh"
 #include "mbx_gleet_policy.cuh"
 #include "mbx_launch.h"
+#include "mbx_pso_policies.cuh"
 #include "mbx_rlepso_policy.cuh"
 
 static thread_local char g_err[512] = "";
@@ -181,6 +182,25 @@ int mbx_rlepso_policy(const float* d_state, const float* d_weights, int n_weight
     if (B == 0) return MBX_OK;
     MBX_REQUIRE(d_state && d_weights && d_action, "mbx_rlepso_policy: null pointer");
     return mbx_launch_rlepso_policy(d_state, d_weights, d_noise, d_action, d_mu, d_sigma, B, (cudaStream_t)stream);
+}
+
+int mbx_rl_pso_policy_weight_count(int n_in) { return rpp::n_weights(n_in); }
+
+int mbx_rl_pso_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,
+                      float* d_mu, float* d_sigma, int B, int n_in, void* stream) {
+    MBX_REQUIRE(B >= 0 && n_in >= 1 && n_in <= 64, "mbx_rl_pso_policy: bad shape B=%d n_in=%d (1 <= n_in = 2*dim <= 64)", B, n_in);
+    MBX_REQUIRE(n_weights == rpp::n_weights(n_in), "mbx_rl_pso_policy: %d packed weights, expected %d for n_in=%d", n_weights,
+                rpp::n_weights(n_in), n_in);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_state && d_weights && d_action, "mbx_rl_pso_policy: null pointer");
+    return mbx_launch_rl_pso_policy(d_state, d_weights, d_noise, d_action, d_mu, d_sigma, B, n_in, (cudaStream_t)stream);
+}
+
+int mbx_qlpso_policy(const int32_t* d_q_state, const double* d_q_table, const float* d_u, int32_t* d_action, int B, void* stream) {
+    MBX_REQUIRE(B >= 0, "mbx_qlpso_policy: bad shape B=%d", B);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_q_state && d_q_table && d_u && d_action, "mbx_qlpso_policy: null pointer");
+    return mbx_launch_qlpso_policy(d_q_state, d_q_table, d_u, d_action, B, (cudaStream_t)stream);
 }
 
 int mbx_deddqn_policy_weight_count(void) { return ddq::N_WEIGHTS; }

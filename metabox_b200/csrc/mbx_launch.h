@@ -63,3 +63,6 @@ int mbx_launch_gleet_policy(const float* state, const float* weights, const floa
 int mbx_launch_deddqn_policy(const float* state, const float* weights, int32_t* action, float* q, int B, cudaStream_t st);
 int mbx_launch_rlepso_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
                              int B, cudaStream_t st);
+int mbx_launch_rl_pso_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
+                             int B, int n_in, cudaStream_t st);
+int mbx_launch_qlpso_policy(const int32_t* q_state, const double* q_table, const float* u, int32_t* action, int B, cudaStream_t st);

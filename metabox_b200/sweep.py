@@ -254,9 +254,10 @@ class RL_PSO_Sweep(_Sweep):
         eng = RL_PSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
         super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
         self.policy = policy
+        self.kernels_per_step = 2 if getattr(policy, 'fused_action', False) else 1
 
     def _policy(self, feat):
-        if getattr(self.policy, 'takes_noise', False):          # agent.RL_PSO_PolicyNet
+        if getattr(self.policy, 'takes_noise', False):          # agent.RL_PSO_PolicyNet / RL_PSO_FusedPolicy
             return self.policy(feat, noise=self._randn(feat.shape[0], 1)).reshape(-1)
         return self.policy(feat).reshape(-1)
 
@@ -272,6 +273,7 @@ class QLPSO_Sweep(_Sweep):
         super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
         self.policy = policy
         self.finite_reward = True                    # rewards are 2 / 1 / 0 / -2
+        self.kernels_per_step = 2 if getattr(policy, 'fused_action', False) else 1
 
     def _policy(self, feat):
         if getattr(self.policy, 'takes_uniform', False):

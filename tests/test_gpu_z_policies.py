@@ -375,3 +375,41 @@ def test_fused_rlepso_policy_kernel_and_sweep():
     np.testing.assert_array_equal(ra, rb)
     r = rows(sweep.RLEPSO_Sweep(pack, inst, fused, 3000, 50, seed=9, graph=True, poll=8))
     assert np.all((r[:, 51] >= 3000) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] < 3200) and np.all(np.abs(r[:, 52]) <= 31)
+
+
+# ------------------------------------------------------------------------------------------------ fused RL_PSO / QLPSO policy kernels
+def test_fused_rl_pso_and_qlpso_policy_kernels_and_sweeps():
+    import torch
+    from metabox_b200 import agent as ma, sweep
+    W, G = _weights('rl_pso')
+    net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), W).cuda().eval()
+    fused = ma.RL_PSO_FusedPolicy(net)
+    act, mu, sigma = fused(torch.as_tensor(G['rl_pso_kat/x']).cuda(), noise=torch.as_tensor(G['rl_pso_kat/eps']).cuda(), outputs=True)
+    np.testing.assert_allclose(mu.cpu().numpy(), G['rl_pso_kat/mu'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sigma.cpu().numpy(), G['rl_pso_kat/sigma'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(act.cpu().numpy(), G['rl_pso_kat/action'], rtol=1e-5, atol=2e-6)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    for dim, B in ((10, 1), (12, 5), (30, 6144)):
+        torch.manual_seed(dim)
+        n2 = ma.RL_PSO_PolicyNet(dim).cuda().eval()
+        f2 = ma.RL_PSO_FusedPolicy(n2)
+        x = (torch.rand(B, 2 * dim, generator=g) * 2 - 0.5).cuda(); nz = (3 * torch.randn(B, 1, generator=g)).cuda()
+        np.testing.assert_allclose(f2(x, noise=nz).cpu().numpy(), n2(x, noise=nz).cpu().numpy(), rtol=2e-5, atol=3e-6, err_msg=f'dim {dim}')
+    qt = ma.QLPSO_QTable(np.array([[0., 1., 2., 3.], [0., 0., 0., 0.], [5., 0., 0., 0.], [-1., -1., 4., -1.]])).cuda()
+    fq = ma.QLPSO_FusedQTable(qt)
+    state = torch.randint(0, 4, (5000,), generator=g, dtype=torch.int32).cuda(); u = torch.rand(5000, generator=g).cuda()
+    assert torch.equal(fq(state, u=u), qt(state, u=u)) and fq(state).dtype == torch.int32
+    # complete sweeps with both policies fused (one library kernel for the policy + one for the step per environment step)
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    for make in (lambda graph: sweep.RL_PSO_Sweep(pack, inst, lambda st: fused(st), 460, 50, seed=5, graph=graph, steps_per_graph=7, poll=70),
+                 lambda graph: sweep.QLPSO_Sweep(pack, inst, lambda st: fq(st, u=torch.full((st.shape[0],), 0.37, device=st.device)), 460, 50,
+                                                 seed=5, graph=graph, steps_per_graph=7, poll=70)):
+        ra, rb = rows(make(True)), rows(make(False))
+        np.testing.assert_array_equal(ra, rb)                                              # deterministic policies: graph == eager
+        assert np.all((ra[:, 51] == 460) | (ra[:, 50] <= 1e-8)) and np.all(np.diff(ra[:, :51], axis=1) <= 0) and np.isfinite(ra).all()
+    r = rows(sweep.RL_PSO_Sweep(pack, inst, fused, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    assert np.isfinite(r).all() and np.all(np.diff(r[:, :51], axis=1) <= 0)
+    r = rows(sweep.QLPSO_Sweep(pack, inst, fq, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
+    assert np.isfinite(r).all() and np.all(np.diff(r[:, :51], axis=1) <= 0)

@@ -47,6 +47,11 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.mbx_rlepso_policy(None, None, k - 2, None, None, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
     assert lib.mbx_rlepso_policy(None, None, k, None, None, None, None, 1, None) == -1 and b'null' in lib.mbx_last_error()
     assert lib.mbx_rlepso_policy(None, None, k, None, None, None, None, 0, None) == 0
+    assert lib.mbx_rl_pso_policy_weight_count(20) == 2 * (20 * 32 + 32 + 8 * 32 + 8 + 8 + 1)
+    assert lib.mbx_rl_pso_policy(None, None, 10, None, None, None, None, 1, 20, None) == -1 and b'packed weights' in lib.mbx_last_error()
+    assert lib.mbx_rl_pso_policy(None, None, 10, None, None, None, None, 1, 65, None) == -1 and b'n_in' in lib.mbx_last_error()
+    assert lib.mbx_qlpso_policy(None, None, None, None, 1, None) == -1 and b'null' in lib.mbx_last_error()
+    assert lib.mbx_qlpso_policy(None, None, None, None, 0, None) == 0
     m = lib.mbx_deddqn_policy_weight_count()
     assert m == 40704
     assert lib.mbx_deddqn_policy(None, None, m + 1, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
@@ -207,6 +212,11 @@ def _emul_lib(name='gleet_policy'):
         if name == 'gleet_policy':
             L.glp_host_forward.restype = C.c_int
             L.glp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
+        elif name == 'pso_policies':
+            L.rpp_host_forward.restype = C.c_int
+            L.rpp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, C.c_int, C.c_int]
+            L.qlp_host_forward.restype = C.c_int
+            L.qlp_host_forward.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_double), fp, C.POINTER(C.c_int32), C.c_int]
         elif name == 'rlepso_policy':
             L.rlp_host_forward.restype = C.c_int
             L.rlp_host_forward.argtypes = [fp, fp, fp, fp, fp, fp, C.c_int]
@@ -301,6 +311,51 @@ def test_fused_rlepso_policy_arithmetic_on_the_host_matches_the_reference():
     act, _, _ = run(x, 50 * noise)                                                  # wild draws: the clamp to [0, 1] is part of the action
     np.testing.assert_allclose(act, actor(torch.as_tensor(x), noise=torch.as_tensor(50 * noise)).numpy(), rtol=1e-5, atol=2e-6)
     assert act.min() == 0 and act.max() == 1
+
+
+def test_fused_rl_pso_and_qlpso_policy_arithmetic_on_the_host_matches_the_reference():
+    """Device functions of the RL_PSO policy-network kernel and the QLPSO table-sampling kernel (csrc/mbx_pso_policies.cuh) compiled for the
+    host: RL_PSO against the unmodified reference's (mu, sigma) and its out-of-range transformation (agents2.npz), other input widths
+    against the torch module; QLPSO against QLPSO_QTable.forward for every state and a sweep of uniforms."""
+    import ctypes as C
+    import torch
+    from metabox_b200 import agent as ma
+    L = _emul_lib('pso_policies')
+    fp = C.POINTER(C.c_float)
+    G = np.load(os.path.join(GOLDEN, 'agents2.npz'))
+    net = ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), {k[len('rl_pso/'):]: G[k] for k in G.files if k.startswith('rl_pso/')})
+
+    def run(net, x, noise=None):
+        w = np.ascontiguousarray(net.pack().numpy())
+        assert L.rpp_host_weight_count(2 * net.dim) == w.size
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        act = np.empty(len(x), np.float32); mu = np.empty_like(act); sg = np.empty_like(act)
+        nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32).reshape(-1)
+        assert L.rpp_host_forward(x.ctypes.data_as(fp), w.ctypes.data_as(fp), None if nz is None else nz.ctypes.data_as(fp),
+                                  act.ctypes.data_as(fp), mu.ctypes.data_as(fp), sg.ctypes.data_as(fp), len(x), x.shape[1]) == 0
+        return act, mu, sg
+
+    act, mu, sg = run(net, G['rl_pso_kat/x'], G['rl_pso_kat/eps'])
+    np.testing.assert_allclose(mu, G['rl_pso_kat/mu'][:, 0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sg, G['rl_pso_kat/sigma'][:, 0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(act, G['rl_pso_kat/action'][:, 0], rtol=1e-5, atol=2e-6)        # 4 of the 9 samples take the transformation
+    g = np.random.RandomState(6)
+    for dim in (12, 30):
+        torch.manual_seed(dim)
+        n2 = ma.RL_PSO_PolicyNet(dim)
+        x = (g.rand(11, 2 * dim) * 2 - 0.5).astype(np.float32); nz = (3 * g.randn(11, 1)).astype(np.float32)
+        act, _, _ = run(n2, x, nz)
+        np.testing.assert_allclose(act, n2(torch.as_tensor(x), noise=torch.as_tensor(nz)).numpy()[:, 0], rtol=1e-5, atol=2e-6)
+    qt = np.array([[0., 1., 2., 3.], [0., 0., 0., 0.], [5., 0., 0., 0.], [-1., -1., 4., -1.]])
+    q = ma.QLPSO_QTable(qt)
+    n = 4000
+    state = np.ascontiguousarray(g.randint(0, 4, size=n), dtype=np.int32)
+    u = np.ascontiguousarray(g.rand(n), dtype=np.float32); u[:4] = 0.0; u[4:8] = np.float32(1 - 2 ** -24)
+    act = np.empty(n, np.int32)
+    assert L.qlp_host_forward(state.ctypes.data_as(C.POINTER(C.c_int32)), qt.ctypes.data_as(C.POINTER(C.c_double)), u.ctypes.data_as(fp),
+                              act.ctypes.data_as(C.POINTER(C.c_int32)), n) == 0
+    np.testing.assert_array_equal(act, q(torch.as_tensor(state), u=torch.as_tensor(u)).numpy())
+    assert set(act.tolist()) == {0, 1, 2, 3}
 
 
 def test_fused_deddqn_policy_arithmetic_on_the_host_matches_the_reference():
