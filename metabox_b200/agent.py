@@ -612,3 +612,14 @@ class QLPSO_FusedQTable:
             rc = _lib.lib().mbx_qlpso_policy(_lib.ptr(state), _lib.ptr(q), _lib.ptr(u), _lib.ptr(action), B, _lib.stream_ptr())
         _lib.check(rc, 'mbx_qlpso_policy')
         return action
+
+
+def fuse(policy):
+    """The single-kernel twin of a rollout policy when the library has one (RLEPSO actor, DE-DDQN Q-network, GLEET actor, RL_PSO policy
+    network, QLPSO Q-table), else the policy itself.  The module must already live on its CUDA device."""
+    table = ((RLEPSO_Actor, RLEPSO_FusedActor), (DE_DDQN_Net, DE_DDQN_FusedNet), (GLEET_Actor, GLEET_FusedActor),
+             (RL_PSO_PolicyNet, RL_PSO_FusedPolicy), (QLPSO_QTable, QLPSO_FusedQTable))
+    for cls, wrapper in table:
+        if isinstance(policy, cls):
+            return wrapper(policy)
+    return policy

@@ -116,7 +116,8 @@ class Tester:
     """`Tester(config, policies).test()` -- config fields used: problem, difficulty, dim, maxFEs, n_logpoint,
     log_interval, upperbound, test_log_dir, agent_for_cp (names out of RLEPSO_Agent / LDE_Agent / DE_DDQN_Agent / GLEET_Agent /
     RL_PSO_Agent / QLPSO_Agent),
-    t_optimizer_for_cp (only 'Random_search' has a B200 path).  `policies`: {agent name: torch module on the GPU}."""
+    t_optimizer_for_cp (only 'Random_search' has a B200 path).  `policies`: {agent name: torch module on the GPU}.
+    `config.fused_policies = True` swaps every policy that has a single-kernel twin in the library for it (`agent.fuse`)."""
 
     def __init__(self, config, policies, device=None, data_folder=None):
         import torch
@@ -125,6 +126,9 @@ class Tester:
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.train_set, self.test_set = construct_problem_set(config, data_folder)
         self.policies = dict(policies)
+        if getattr(config, 'fused_policies', False):
+            from .agent import fuse
+            self.policies = {k: fuse(v) for k, v in self.policies.items()}
         for name in getattr(config, 'agent_for_cp', list(self.policies)):
             if name not in AGENT_ALGO:
                 raise ValueError(f'{name}: no B200 backbone (supported: {sorted(AGENT_ALGO)})')

@@ -413,3 +413,30 @@ def test_fused_rl_pso_and_qlpso_policy_kernels_and_sweeps():
     assert np.isfinite(r).all() and np.all(np.diff(r[:, :51], axis=1) <= 0)
     r = rows(sweep.QLPSO_Sweep(pack, inst, fq, 460, 50, seed=5, graph=True, steps_per_graph=7, poll=70))
     assert np.isfinite(r).all() and np.all(np.diff(r[:, :51], axis=1) <= 0)
+
+
+def test_tester_with_fused_policies(tmp_path):
+    """`config.fused_policies = True`: the Tester swaps every policy for its single-kernel twin and writes the reference's layouts."""
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, tester as mt
+    G1 = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    sub = lambda G, pre: {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    W2, G2 = _weights('gleet')
+    pol = {'RLEPSO_Agent': ma.load_reference_weights(ma.RLEPSO_Actor(), sub(G1, 'rlepso/')).cuda().eval(),
+           'DE_DDQN_Agent': ma.load_reference_weights(ma.DE_DDQN_Net(), sub(G1, 'deddqn/')).cuda().eval(),
+           'GLEET_Agent': ma.load_reference_weights(ma.GLEET_Actor(), W2).cuda().eval(),
+           'RL_PSO_Agent': ma.load_reference_weights(ma.RL_PSO_PolicyNet(10), sub(G2, 'rl_pso/')).cuda().eval(),
+           'QLPSO_Agent': ma.QLPSO_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda(),
+           'DEDQN_Agent': ma.load_reference_weights(ma.DEDQN_Net(), sub(G2, 'dedqn/')).cuda().eval()}
+    cfg = argparse.Namespace(problem='bbob', difficulty='easy', dim=10, maxFEs=600, n_logpoint=50, log_interval=12, upperbound=5,
+                             test_log_dir=str(tmp_path / 'test') + '/', agent_for_cp=list(pol), t_optimizer_for_cp=[], fused_policies=True)
+    T = mt.Tester(cfg, pol)
+    assert [type(T.policies[k]).__name__ for k in pol] == ['RLEPSO_FusedActor', 'DE_DDQN_FusedNet', 'GLEET_FusedActor', 'RL_PSO_FusedPolicy',
+                                                          'QLPSO_FusedQTable', 'DEDQN_Net']
+    R = T.test(n_runs=2, random_search_baseline=False)['test']
+    for p in R['cost']:
+        assert set(R['cost'][p]) == set(pol)
+        for a in R['cost'][p]:
+            assert len(R['cost'][p][a]) == 2 and all(len(c) == 51 for c in R['cost'][p][a])
+            assert all(f >= 600 or c[-1] <= 1e-8 for f, c in zip(R['fes'][p][a], R['cost'][p][a]))
