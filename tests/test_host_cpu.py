@@ -801,6 +801,46 @@ def test_gleet_ppo_loop_on_cpu_with_a_fake_engine():
         mp.InstancePack, mt.GLEET_Engine = old
 
 
+def _gleet_ppo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from metabox_b200 import problem as mp, trainer as mt
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        mp.InstancePack = lambda problems, device=None: None            # no GPU in this test: host logic only
+        mt.GLEET_Engine = _FakeGleetEngine
+        torch.manual_seed(0)                                             # identical initial weights on every rank
+        cfg = argparse.Namespace(dim=10, maxFEs=4000, n_logpoint=50, log_interval=80)
+        T = mt.GLEET_Trainer(cfg, [None] * 5, seed=1, device='cpu')
+        info = T.train_episodes([0, 1, 2, 3, 4])                         # rank 0: lanes 0-2 (<= 19 gens), rank 1: lanes 3, 4 (<= 31 gens)
+        flat = torch.cat([p.detach().reshape(-1) for p in T._params()])
+        q.put((rank, info['segments'], info['learn_steps'], len(info['gbest']), flat.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gleet_ppo_loop_world2_gloo_ranks_stay_in_step():
+    """GLEET_Trainer under gloo, world 2: ranks whose lanes finish in different segments make the same number of collectives; the clipped,
+    all-reduced gradients give identical weights on both ranks."""
+    import socket
+    import torch.multiprocessing as tmp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = tmp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gleet_ppo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, seg0, ls0, n0, w0), (r1, seg1, ls1, n1, w1) = got
+    assert seg0 == seg1 == 4 and ls0 == ls1 == 12                        # longest lane: 7 + 6*4 = 31 generations = 4 segments x 3 epochs
+    assert (n0, n1) == (3, 2)
+    np.testing.assert_array_equal(w0, w1)
+
+
 def test_qlpso_qtable_policy_on_cpu():
     """Tabular QLPSO policy (qlpso_agent.py:33-36, 47-48): softmax sampling by inverse CDF, TD rule."""
     import torch
