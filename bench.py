@@ -423,7 +423,8 @@ def main():
             # the oracle port, timed in a fresh process (no CUDA context, so its fork pool is safe)
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
-                                    '--warmup', '1', '--cpu-gens', str(args.cpu_gens), '--workload', args.workload],
+                                    '--warmup', '1', '--cpu-gens', str(args.cpu_gens), '--workload', args.workload,
+                                    '--gleet-policy', 'stand-in' if args.gleet_policy == 'stand-in' else 'actor'],
                                    capture_output=True, text=True,
                                    timeout=600, env={**os.environ, 'RANK': '0', 'WORLD_SIZE': '1', 'CUDA_VISIBLE_DEVICES': ''})
                 out['cpu_baseline'] = json.loads(r.stdout.strip().splitlines()[-1])['cpu_baseline']
