@@ -9,3 +9,4 @@ timeout 200 python scripts/policy_timing.py > gpurun_out/r2a_policy_timing.txt 2
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gleet_policy -s 3 -c 1 -o gpurun_out/r2a_ncu_gleet_policy -f python scripts/policy_timing.py --only gleet --reps 4 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:deddqn_policy -s 3 -c 1 -o gpurun_out/r2a_ncu_deddqn_policy -f python scripts/policy_timing.py --only deddqn --reps 4 > /dev/null 2>&1
 ls -la gpurun_out | tail -8
+timeout 600 python scripts/train_timing.py > gpurun_out/r2a_train_timing.txt 2>&1; cat gpurun_out/r2a_train_timing.txt
