@@ -58,6 +58,9 @@ def parse():
                     help='rlepso: the actor as ONE kernel per generation (agent.RLEPSO_FusedActor -> mbx_rlepso_policy); '
                          'deddqn: the Q-network + argmax as ONE kernel per step (agent.DE_DDQN_FusedNet -> mbx_deddqn_policy); '
                          'gleet: same as --gleet-policy fused')
+    ap.add_argument('--steps-per-graph', type=int, default=None,
+                    help='environment steps captured per CUDA graph (default: 1 for the population backbones, 10 for deddqn); more steps = fewer '
+                         'graph launches, finished lanes idle through the surplus steps')
     ap.add_argument('--runs', type=int, default=None, help='runs per function per GPU (default 256)')
     ap.add_argument('--cpu-gens', type=int, default=None, help='generations (deddqn: steps) per lane in one CPU sample step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -303,7 +306,8 @@ def main():
         return res, rows
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
-    sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph)
+    gkw = {} if args.steps_per_graph is None else {'steps_per_graph': args.steps_per_graph}
+    sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph, **gkw)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -404,7 +408,7 @@ def main():
             'config': {'workload': f'{W["desc"]} x {args.runs} runs/GPU, dim {DIM}, pop {NP}, maxFEs {MAXFES}, '
                                    'one step = one complete sweep (init + all generations + all-gather)',
                        'lanes_per_gpu': n_local, 'lane_order': args.lane_order, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
-                       'launch': 'eager' if args.no_graph else f'policy forward + fused step replayed from one CUDA graph per step; {args.stripes} lane stripe(s) on separate streams',
+                       'launch': 'eager' if args.no_graph else f'policy forward + fused step replayed from one CUDA graph per {args.steps_per_graph or (10 if args.workload == "deddqn" else 1)} step(s); {args.stripes} lane stripe(s) on separate streams',
                        'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
                        'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

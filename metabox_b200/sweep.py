@@ -159,10 +159,10 @@ class RLEPSO_Sweep(_Sweep):
     """RLEPSO_Agent.rollout_episode (rlepso_agent.py:294-303) for all lanes of one rank."""
 
     def __init__(self, pack, lane_inst, actor, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False,
-                 graph=True):
+                 graph=True, steps_per_graph=1):
         eng = RLEPSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
         # every generation charges >= NP evaluations, so ceil(maxFEs/NP) generations always suffice
-        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, steps_per_graph, time_kernels)
         self.actor = actor
         self.finite_reward = True
         self.kernels_per_step = 2 if getattr(actor, 'fused_action', False) else 1
@@ -177,9 +177,9 @@ class LDE_Sweep(_Sweep):
     """LDE_Agent.rollout_episode (lde_agent.py:147-163): LSTM state (h, c) per lane, zero at reset."""
 
     def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, NP=None, poll=64,
-                 time_kernels=False, graph=True):
+                 time_kernels=False, graph=True, steps_per_graph=1):
         eng = LDE_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base, NP=NP or net.NP)
-        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, steps_per_graph, time_kernels)
         self.net = net
         self.h = torch.zeros(eng.B, net.cell, device=eng.device)
         self.c = torch.zeros(eng.B, net.cell, device=eng.device)
@@ -234,9 +234,9 @@ class GLEET_Sweep(_Sweep):
     reference's attention actor, or any torch callable, runs on the same stream between the fused steps)."""
 
     def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False,
-                 graph=True):
+                 graph=True, steps_per_graph=1):
         eng = GLEET_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
-        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, 1, time_kernels)
+        super().__init__(eng, int(math.ceil(maxFEs / eng.NP)) + 1, poll, graph, steps_per_graph, time_kernels)
         self.policy = policy
         self.kernels_per_step = 2 if getattr(policy, 'fused_action', False) else 1
 

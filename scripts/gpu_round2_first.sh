@@ -6,6 +6,7 @@ timeout 200 python scripts/policy_timing.py > gpurun_out/r2a_policy_timing.txt 2
 ( timeout 300 python bench.py --workload gleet --gleet-policy fused --steps 3 --no-cpu-baseline ) > gpurun_out/r2a_bench_n1_gleet_fused.json 2> gpurun_out/r2a_gleet_fused.err; tail -1 gpurun_out/r2a_bench_n1_gleet_fused.json | cut -c1-200
 ( timeout 500 python bench.py --workload deddqn --fused-policy --steps 2 --no-cpu-baseline ) > gpurun_out/r2a_bench_n1_deddqn_fused.json 2> gpurun_out/r2a_deddqn_fused.err; tail -1 gpurun_out/r2a_bench_n1_deddqn_fused.json | cut -c1-200
 ( timeout 300 python bench.py --fused-policy --steps 3 --no-cpu-baseline ) > gpurun_out/r2a_bench_n1_rlepso_fused.json 2> gpurun_out/r2a_rlepso_fused.err; tail -1 gpurun_out/r2a_bench_n1_rlepso_fused.json | cut -c1-200
+( timeout 300 python bench.py --steps-per-graph 4 --steps 3 --no-cpu-baseline ) > gpurun_out/r2a_bench_n1_rlepso_spg4.json 2> gpurun_out/r2a_rlepso_spg4.err; tail -1 gpurun_out/r2a_bench_n1_rlepso_spg4.json | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gleet_policy -s 3 -c 1 -o gpurun_out/r2a_ncu_gleet_policy -f python scripts/policy_timing.py --only gleet --reps 4 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:deddqn_policy -s 3 -c 1 -o gpurun_out/r2a_ncu_deddqn_policy -f python scripts/policy_timing.py --only deddqn --reps 4 > /dev/null 2>&1
 ls -la gpurun_out | tail -8

@@ -454,3 +454,23 @@ def test_tester_with_fused_policies(tmp_path):
         for a in R['cost'][p]:
             assert len(R['cost'][p][a]) == 2 and all(len(c) == 51 for c in R['cost'][p][a])
             assert all(f >= 600 or c[-1] <= 1e-8 for f, c in zip(R['fes'][p][a], R['cost'][p][a]))
+
+
+@pending_first_device_run
+def test_population_sweeps_with_several_steps_per_graph():
+    """Graphs of 4 generations: finished lanes idle through surplus generations, the rows equal the one-generation-per-graph sweep."""
+    from metabox_b200 import agent as ma, sweep
+    G = np.load(os.path.join(GOLDEN, 'agents.npz'))
+    actor = ma.load_reference_weights(ma.RLEPSO_Actor(), {k[len('rlepso/'):]: G[k] for k in G.files if k.startswith('rlepso/')}).cuda().eval()
+    mean = _Mean(actor, lambda d: d[0])
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    rows = lambda sw: sweep.gather_results(sw.run(), 1).cpu().numpy()
+    r1 = rows(sweep.RLEPSO_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=True, poll=8))
+    r4 = rows(sweep.RLEPSO_Sweep(pack, inst, mean, 3000, 50, seed=9, graph=True, poll=8, steps_per_graph=4))
+    np.testing.assert_array_equal(r1, r4)
+    W, _ = _weights('gleet')
+    gm = _Mean(ma.load_reference_weights(ma.GLEET_Actor(), W).cuda().eval(), lambda d: d[0])
+    g1 = rows(sweep.GLEET_Sweep(pack, inst, gm, 3000, 50, seed=9, graph=True, poll=8))
+    g3 = rows(sweep.GLEET_Sweep(pack, inst, gm, 3000, 50, seed=9, graph=True, poll=9, steps_per_graph=3))
+    np.testing.assert_array_equal(g1, g3)
