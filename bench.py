@@ -30,13 +30,17 @@ DIM, MAXFES = 30, 60000
 # workload -> (suite, difficulty/subset, NP, algorithmic bytes per evaluation, description)
 WORKLOADS = {
     'rlepso': dict(suit='bbob', subset='all', NP=100, bytes_per_eval=24 * DIM + 24, kernel='rlepso_step_kernel<30,BBOB>',
-                   desc='RLEPSO rollouts, BBOB 24 fns'),
+                   desc='RLEPSO rollouts, BBOB 24 fns',
+                   bound_note='instruction issue (62 % of issue slots busy, DRAM 4.5 % in the ncu capture profiles/r1e_ncu_rlepso_step_d30.txt), not HBM'),
     'lde': dict(suit='bbob-noisy', subset='all', NP=100, bytes_per_eval=8 * DIM + 20.4, kernel='lde_step_kernel<30,BBOB>',
-                desc='LDE rollouts, BBOB-noisy 30 fns'),
+                desc='LDE rollouts, BBOB-noisy 30 fns',
+                bound_note='instruction issue (49 % of issue slots busy, FP64 pipe 16 %; profiles/r1e_ncu_lde_step_d30.txt), not HBM'),
     'deddqn': dict(suit='bbob', subset='difficult-test', NP=100, bytes_per_eval=32 * DIM + 404,
-                   kernel='deddqn_step_kernel<30,BBOB>', desc='DE-DDQN rollouts, BBOB difficult test set 18 fns'),
+                   kernel='deddqn_step_kernel<30,BBOB>', desc='DE-DDQN rollouts, BBOB difficult test set 18 fns',
+                   bound_note='latency of a chain of short dependent phases, one trial per lane per step (issue 34 % busy; profiles/r1g_ncu_deddqn.txt), not HBM'),
     'gleet': dict(suit='bbob', subset='all', NP=100, bytes_per_eval=24 * DIM + 204, kernel='gleet_step_kernel<30,BBOB>',
-                  desc='GLEET rollouts, BBOB 24 fns'),
+                  desc='GLEET rollouts, BBOB 24 fns',
+                  bound_note='instruction issue and long-scoreboard stalls in the feature tail (issue 32 % busy; profiles/r1g_ncu_gleet.txt), not HBM'),
 }
 METRIC = 'candidate evals/sec on BBOB dim=30 pop=100'
 
@@ -418,8 +422,7 @@ def main():
                          'timed': 'separate instrumented (eager, unstriped) sweep of the same workload right after the timed region; '
                                   'kernel_share_of_step = step-kernel time / duration of that sweep',
                          'note': f'algorithmic bytes = {W["bytes_per_eval"]} B/eval x evals charged by the step launches; see DESIGN.md section 4 '
-                                 'for what actually bounds the kernel (instruction issue: 62 % of issue slots busy, DRAM 4.5 % in the ncu capture '
-                                 'profiles/r1e_ncu_rlepso_step_d30.txt; not HBM)'},
+                                 'for what actually bounds the kernel: ' + W['bound_note']},
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches), 'clocks': clk,
         }
