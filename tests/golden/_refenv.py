@@ -32,10 +32,13 @@ class F32Problem:
     (or None when the wrapped problem has none) so the reference's `eval(x) - problem.optimum` and
     its `gbest <= 1e-8` termination test keep their meaning."""
 
-    def __init__(self, inner):
+    def __init__(self, inner, inplace=False):
+        """inplace=True additionally writes the rounded positions back into the caller's array, so that what the reference optimizer
+        STORES afterwards (trial vectors, walk samples) is the float32-representable point that was evaluated."""
         import numpy as np
         self._np = np
         self.inner = inner
+        self.inplace = inplace
         self.dim, self.lb, self.ub = inner.dim, inner.lb, inner.ub
         self.optimum = None if inner.optimum is None else 0.0
         self.T1 = 0
@@ -50,6 +53,8 @@ class F32Problem:
     def eval(self, x):
         np = self._np
         x32 = np.asarray(x, dtype=np.float64).astype(np.float32).astype(np.float64)
+        if self.inplace and isinstance(x, np.ndarray) and x.flags.writeable and x.dtype == np.float64:
+            x[...] = x32
         f = self.inner.eval(x32)
         if self.inner.optimum is not None:
             f = f - self.inner.optimum

@@ -505,3 +505,53 @@ def test_dedqn_steps_match_reference():
         assert seen_done == (key == 'f1_d10')
     with pytest.raises(ValueError):
         od.update(cfg, S, 3, ev, optimum, lb, ub, od.NumpyTape(cfg.NP, dim, nc))
+
+
+# ------------------------------------------------------------------------------------------ RL_HPSDE
+def test_rl_hpsde_generations_match_reference():
+    """Consecutive generations of the real RL_HPSDE_Optimizer per case (float32 storage contract, np.random re-seeded before every
+    generation) vs the oracle carrying its OWN state and replaying the same draws (incl. scipy's cauchy / levy samplers): sorted
+    population and costs, success-history memories, population-size schedule, landscape state, reward, accounting, curve protocol; one
+    case runs to the end of its budget."""
+    from oracle import rl_hpsde as oh
+    G = load('rl_hpsde.npz')
+    seen_states, seen_done, n_tie_swaps = set(), False, 0
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = oh.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, state = oh.init_population(cfg, ev, optimum, lb, ub, oh.NumpyTape(dim, nc))
+        np.testing.assert_array_equal(S.group, G[f'{key}/s0/group'], err_msg=f'{key} init group')
+        np.testing.assert_allclose(S.cost, G[f'{key}/s0/cost'], rtol=1e-6, atol=1e-10)
+        assert state == int(G[f'{key}/s0/state']) and S.fes == int(G[f'{key}/s0/fes']) == 18 * dim + 201
+        S.cost = G[f'{key}/s0/cost'].copy()
+        for t in range(1, int(G[f'{key}/n_steps']) + 1):
+            np.random.seed(int(G[f'{key}/seed'][t - 1]))
+            S, state, reward, done = oh.update(cfg, S, int(G[f'{key}/action'][t - 1]), ev, optimum, lb, ub, oh.NumpyTape(dim, nc))
+            tag = f'{key} generation {t}'
+            assert S.NP == int(G[f'{key}/NP'][t - 1]), tag
+            np.testing.assert_allclose(S.cost, G[f'{key}/cost/{t}'], rtol=1e-6, atol=1e-10, err_msg=tag)
+            ref_group = G[f'{key}/group/{t}']
+            if not np.array_equal(S.group, ref_group):                     # np.argsort (quicksort) vs the oracle's stable order of TIED costs
+                for lo in np.flatnonzero(np.r_[True, S.cost[1:] != S.cost[:-1]]):
+                    hi = lo + 1
+                    while hi < S.NP and S.cost[hi] == S.cost[lo]:
+                        hi += 1
+                    rows = lambda A: sorted(map(tuple, A[lo:hi].tolist()))
+                    assert rows(S.group) == rows(ref_group), tag
+                n_tie_swaps += 1
+                S.group = ref_group.copy()
+            np.testing.assert_allclose(S.MF, G[f'{key}/MF'][t - 1], rtol=1e-5, atol=1e-9, err_msg=tag)
+            np.testing.assert_allclose(S.MCr, G[f'{key}/MCr'][t - 1], rtol=1e-5, atol=1e-9, err_msg=tag)
+            assert S.k == int(G[f'{key}/k'][t - 1]) and state == int(G[f'{key}/state'][t - 1]), tag
+            np.testing.assert_allclose(reward, G[f'{key}/reward'][t - 1], rtol=1e-12, err_msg=tag)
+            assert done == bool(G[f'{key}/done'][t - 1]) and S.fes == int(G[f'{key}/fes'][t - 1]), tag
+            assert S.log_index == int(G[f'{key}/log_index'][t - 1]) and len(S.curve) == int(G[f'{key}/curve_len'][t - 1]), tag
+            np.testing.assert_allclose(float(S.curve[-1]), float(G[f'{key}/curve_last'][t - 1]), rtol=1e-6, atol=1e-10, err_msg=tag)
+            S.cost = G[f'{key}/cost/{t}'].copy(); S.gbest = np.float32(G[f'{key}/gbest'][t - 1])       # last-bit teacher forcing of the costs
+            S.MF, S.MCr = G[f'{key}/MF'][t - 1].copy(), G[f'{key}/MCr'][t - 1].copy()
+            seen_states.add(state); seen_done |= done
+    assert seen_done and seen_states == {0, 1, 2, 3} and n_tie_swaps >= 1          # tied costs do occur (plateaus, converged swarms)
+    with pytest.raises(ValueError):
+        oh.update(cfg, S, 4, ev, optimum, lb, ub, oh.NumpyTape(dim, nc))
