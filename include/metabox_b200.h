@@ -331,6 +331,16 @@ int mbx_landscape_features(const double* d_sample, const double* d_cost, const d
                            double* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Progressive random walk of RL_HPSDE's state computation -- replaces `__progressive_random_walk`
+ * (optimizer/rl_hpsde_optimizer.py:150-167) for B lanes at once; the walk's costs then go through mbx_eval and its statistics through
+ * mbx_landscape_features (columns dfdc_r, drie_r).
+ *   d_zone_u, d_r_u [B,D] f64 uniforms (start half / start offset) ; d_rD [B] i32 (the dimension that starts on a box face) ;
+ *   d_step_u [B,n_steps,D] f64 uniforms ; lb, ub: the box ; step_size: 10 in the reference
+ *   outputs: d_out [B,n_steps+1,D] f64 ; optional d_out32 (same shape, f32: the points as they are evaluated)                       */
+int mbx_progressive_walk(const double* d_zone_u, const double* d_r_u, const int32_t* d_rD, const double* d_step_u, double lb, double ub,
+                         double step_size, int B, int D, int n_steps, double* d_out, float* d_out32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * GLEET attention actor, rollout forward -- replaces `Actor.forward` (agent/gleet_agent.py:386-440, called once per
  * generation from `rollout_episode`, :293-303) on agent/networks.py:47-356 for B swarms at once: embedder, encoder block
  * (4-head self-attention over the swarm, whole-swarm normalisation, feed-forward), decoder block (the exploration /

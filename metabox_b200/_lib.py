@@ -133,6 +133,7 @@ SIGNATURES = {
     'mbx_landscape_features': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     'mbx_rlepso_policy_weight_count': (C.c_int, []),
     'mbx_rlepso_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
+    'mbx_progressive_walk': (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     'mbx_rl_pso_policy_weight_count': (C.c_int, [C.c_int]),
     'mbx_rl_pso_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     'mbx_qlpso_policy': (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),

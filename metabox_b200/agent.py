@@ -330,6 +330,9 @@ class QLPSO_QTable(nn.Module):
             q[s, a] += alpha * (r + gamma * q[n].max() - q[s, a])
 
 
+RL_HPSDE_QTable = QLPSO_QTable          # RL_HPSDE_Agent (rl_hpsde_agent.py:13,27-30,42-43) is the same tabular softmax policy over 4 states x 4 actions (gamma 0.5)
+
+
 # ------------------------------------------------------------------------------------------ GLEET
 class _SwarmNorm(nn.Module):
     """The reference's 'layer' normalisation (networks.py:68-72): every lane is standardised over ALL of its [NP, E] entries

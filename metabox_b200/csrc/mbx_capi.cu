@@ -184,6 +184,16 @@ int mbx_rlepso_policy(const float* d_state, const float* d_weights, int n_weight
     return mbx_launch_rlepso_policy(d_state, d_weights, d_noise, d_action, d_mu, d_sigma, B, (cudaStream_t)stream);
 }
 
+int mbx_progressive_walk(const double* d_zone_u, const double* d_r_u, const int32_t* d_rD, const double* d_step_u, double lb, double ub,
+                         double step_size, int B, int D, int n_steps, double* d_out, float* d_out32, void* stream) {
+    MBX_REQUIRE(B >= 0 && D >= 1 && n_steps >= 0 && ub > lb, "mbx_progressive_walk: bad arguments B=%d D=%d n_steps=%d lb=%g ub=%g", B, D,
+                n_steps, lb, ub);
+    if (B == 0) return MBX_OK;
+    MBX_REQUIRE(d_zone_u && d_r_u && d_rD && d_out && (d_step_u || n_steps == 0), "mbx_progressive_walk: null pointer");
+    return mbx_launch_progressive_walk(d_zone_u, d_r_u, d_rD, d_step_u, lb, ub, step_size, B, D, n_steps, d_out, d_out32,
+                                       (cudaStream_t)stream);
+}
+
 int mbx_rl_pso_policy_weight_count(int n_in) { return rpp::n_weights(n_in); }
 
 int mbx_rl_pso_policy(const float* d_state, const float* d_weights, int n_weights, const float* d_noise, float* d_action,

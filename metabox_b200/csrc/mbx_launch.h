@@ -66,3 +66,5 @@ int mbx_launch_rlepso_policy(const float* state, const float* weights, const flo
 int mbx_launch_rl_pso_policy(const float* state, const float* weights, const float* noise, float* action, float* mu, float* sigma,
                              int B, int n_in, cudaStream_t st);
 int mbx_launch_qlpso_policy(const int32_t* q_state, const double* q_table, const float* u, int32_t* action, int B, cudaStream_t st);
+int mbx_launch_progressive_walk(const double* zone_u, const double* r_u, const int32_t* rD, const double* step_u, double lb, double ub,
+                                double step_size, int B, int D, int n_steps, double* out, float* out32, cudaStream_t st);

@@ -229,6 +229,25 @@ class DEDQN_Sweep(_Sweep):
         return torch.argmax(self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0)), dim=-1)
 
 
+class RL_HPSDE_Sweep(_Sweep):
+    """RL_HPSDE_Agent.rollout_episode (rl_hpsde_agent.py:62-72): the action is sampled from softmax(Q[state]) of a 4 x 4 table
+    (`agent.RL_HPSDE_QTable`, or its single-kernel twin); every generation charges NP + 201 evaluations with NP shrinking from 18 dim to 4.
+    The engine is a composition of library kernels and torch ops with a host-side population-size schedule, so it runs eagerly."""
+
+    def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=8, time_kernels=False, graph=False):
+        from .rl_hpsde import NP_MIN, RW_STEPS, RL_HPSDE_Engine
+        eng = RL_HPSDE_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, int(math.ceil(maxFEs / (NP_MIN + RW_STEPS + 1))) + 1, poll, False, 1, time_kernels)
+        self.policy = policy
+        self.kernels_per_step = 4 + (1 if getattr(policy, 'fused_action', False) else 0)     # 2 x mbx_eval, walk, landscape features
+
+    def _policy(self, feat):
+        if getattr(self.policy, 'takes_uniform', False):
+            u = torch.rand(feat.shape[0], generator=self.gen, device=feat.device, dtype=torch.float32)
+            return self.policy(feat, u=u).reshape(-1)
+        return self.policy(feat).reshape(-1)
+
+
 class GLEET_Sweep(_Sweep):
     """GLEET_Agent.rollout_episode (gleet_agent.py:293-303): `policy(state [B,NP,27]) -> action [B,NP]` in [0,1] (the
     reference's attention actor, or any torch callable, runs on the same stream between the fused steps)."""

@@ -474,3 +474,84 @@ def test_population_sweeps_with_several_steps_per_graph():
     g1 = rows(sweep.GLEET_Sweep(pack, inst, gm, 3000, 50, seed=9, graph=True, poll=8))
     g3 = rows(sweep.GLEET_Sweep(pack, inst, gm, 3000, 50, seed=9, graph=True, poll=9, steps_per_graph=3))
     np.testing.assert_array_equal(g1, g3)
+
+
+# ------------------------------------------------------------------------------------------------ RL_HPSDE backbone (composed step, metabox_b200/rl_hpsde.py)
+@pending_first_device_run
+def test_rl_hpsde_engine_on_the_device_vs_oracle():
+    """The composed RL_HPSDE generation with the real kernels (mbx_eval, mbx_progressive_walk, mbx_landscape_features): every generation the
+    oracle replays the engine's own draws from the engine's previous state."""
+    import torch
+    from metabox_b200 import problem as mp, rl_hpsde as mh
+    from oracle import bbob as ob, landscape as ola, rl_hpsde as oh
+    dim, maxFEs, fids = 10, 20000, [1, 3, 9, 17, 21, 24]
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', dim, 5)
+    probs = {p.fid: p for p in tr.data + te.data}
+    otr, ote = ob.make_suite('bbob', dim, 5.0)
+    oin = {i.fid: i for i in otr + ote}
+    pack = mp.InstancePack([probs[f] for f in fids])
+    eng = mh.RL_HPSDE_Engine(pack, list(range(len(fids))), maxFEs, 50, seed=12)
+    cfg = oh.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    assert eng.feature.shape == (len(fids),) and torch.all(eng.fes == 180 + 201) and eng.NP == 180
+    # the walk kernel against the oracle's restatement, bit for bit
+    tp = {k: v.cpu().numpy() for k, v in eng.last_tape.items()}
+    for b in range(len(fids)):
+        want = oh.progressive_walk(-5., 5., tp['zone_u'][b], tp['r_u'][b], int(tp['rD'][b]), tp['step_u'][b])
+        np.testing.assert_array_equal(eng.last_sample[b].cpu().numpy(), want.astype(np.float32))
+    g = np.random.RandomState(1)
+    for t in range(1, 13):
+        action = g.randint(0, 4, size=len(fids))
+        prev = [eng.read_state(b) for b in range(len(fids))]
+        feat, reward, done = eng.update(torch.as_tensor(action).cuda(), check_action=True)
+        tp = {k: v.cpu().numpy() for k, v in eng.last_tape.items()}
+        smp, cst = eng.last_sample.cpu().numpy().astype(np.float64), eng.last_cost.cpu().numpy()
+        for b, f in enumerate(fids):
+            I = oin[f]
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            q = prev[b]
+            S = oh.State(group=q['group'], cost=q['cost'], MF=q['MF'], MCr=q['MCr'], k=int(q['k']), gbest=np.float32(q['gbest']), fes=int(q['fes']),
+                         log_index=int(q['log_index']), curve=list(q['curve'][:int(q['curve_len'])]))
+            N, state, r, d = oh.update(cfg, S, int(action[b]), ev, I.optimum, -5., 5., oh.ArrayTape({k: v[b] for k, v in tp.items()}))
+            st = eng.read_state(b)
+            tag = f'generation {t} lane {b} (fid {f})'
+            assert st['cost'].shape[0] == N.NP, tag
+            np.testing.assert_allclose(st['cost'], N.cost, rtol=1e-6, atol=1e-10, err_msg=tag)
+            if np.all(np.diff(N.cost) > 1e-5 * np.abs(N.cost[1:])):                            # no near-ties: the sorted order is unambiguous
+                np.testing.assert_array_equal(st['group'], N.group, err_msg=tag)
+            np.testing.assert_allclose(st['MF'], N.MF, rtol=1e-4, atol=1e-7, err_msg=tag)
+            np.testing.assert_allclose(st['MCr'], N.MCr, rtol=1e-4, atol=1e-7, err_msg=tag)
+            assert int(st['k']) == N.k and int(st['fes']) == N.fes and int(st['log_index']) == N.log_index, tag
+            own = (ola.dfdc_r(smp[b], cst[b], st['group'][0].astype(np.float64)), ola.drie_r(cst[b]))
+            np.testing.assert_allclose([float(st['dfdc']), float(st['drie'])], own, rtol=1e-9, atol=1e-12, err_msg=tag)
+            np.testing.assert_allclose(float(eng.reward64[b]), r, atol=2.0 / N.NP, err_msg=tag)   # a last-bit cost difference may flip one strict comparison
+    assert eng.NP < 180
+
+
+@pending_first_device_run
+def test_rl_hpsde_sweep_tester_and_dropin():
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, environment as me, optimizer as mo, sweep
+    qt = ma.RL_HPSDE_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda()
+    pack, probs = _pack()
+    inst, _ = sweep.lane_table(len(probs), 2)
+    r1 = sweep.gather_results(sweep.RL_HPSDE_Sweep(pack, inst, qt, 4000, 50, seed=4).run(), 1).cpu().numpy()
+    r2 = sweep.gather_results(sweep.RL_HPSDE_Sweep(pack, inst, ma.fuse(qt), 4000, 50, seed=4).run(), 1).cpu().numpy()
+    for r in (r1, r2):
+        assert np.all((r[:, 51] >= 4000) | (r[:, 50] <= 1e-8)) and np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()
+        assert np.all(r[:, 52] > 0)
+    np.testing.assert_array_equal(r1, r2)                       # same uniforms, same table: the fused sampler picks the same actions
+    cfg = argparse.Namespace(dim=10, maxFEs=4000, n_logpoint=50, log_interval=80)
+    env = me.PBO_Env(probs[0], mo.RL_HPSDE_Optimizer(cfg))
+    np.random.seed(0)
+    state = env.reset()
+    assert state in (0, 1, 2, 3) and env.optimizer.fes == 180 + 201
+    done, n = False, 0
+    while not done:
+        state, reward, done = env.step(int(np.random.randint(0, 4)))
+        assert isinstance(reward, float) and 0 <= reward <= 1 and state in (0, 1, 2, 3)
+        n += 1
+    assert 9 <= n <= 12 and env.optimizer.fes >= 4000
+    with pytest.raises(ValueError):
+        env.step(4)

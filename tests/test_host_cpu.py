@@ -52,6 +52,9 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.mbx_rl_pso_policy(None, None, 10, None, None, None, None, 1, 65, None) == -1 and b'n_in' in lib.mbx_last_error()
     assert lib.mbx_qlpso_policy(None, None, None, None, 1, None) == -1 and b'null' in lib.mbx_last_error()
     assert lib.mbx_qlpso_policy(None, None, None, None, 0, None) == 0
+    assert lib.mbx_progressive_walk(None, None, None, None, -5., 5., 10., 1, 10, 200, None, None, None) == -1 and b'null' in lib.mbx_last_error()
+    assert lib.mbx_progressive_walk(None, None, None, None, 5., -5., 10., 1, 10, 200, None, None, None) == -1 and b'bad arguments' in lib.mbx_last_error()
+    assert lib.mbx_progressive_walk(None, None, None, None, -5., 5., 10., 0, 10, 200, None, None, None) == 0
     m = lib.mbx_deddqn_policy_weight_count()
     assert m == 40704
     assert lib.mbx_deddqn_policy(None, None, m + 1, None, None, 1, None) == -1 and b'packed weights' in lib.mbx_last_error()
@@ -1008,3 +1011,141 @@ def test_dedqn_engine_replays_the_reference_tape():
         np.testing.assert_allclose(float(eng.reward64[0]), float(G[f'{key}/reward'][t - 1]), rtol=1e-12, err_msg=tag)
         assert int(eng.fes[0]) == int(G[f'{key}/fes'][t - 1]) and int(eng.log_index[0]) == int(G[f'{key}/log_index'][t - 1]), tag
         assert int(eng.curve_len[0]) == int(G[f'{key}/curve_len'][t - 1]), tag
+
+
+# ----------------------------------------------------------------------------------------- RL_HPSDE engine: host logic with injected kernels
+def _walk_emul():
+    import ctypes as C
+    import subprocess
+    import tempfile
+    if not hasattr(_walk_emul, 'lib'):
+        d = tempfile.mkdtemp(prefix='mbx_emul_')
+        so = os.path.join(d, 'walk_host.so')
+        subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', os.path.join(os.path.dirname(__file__), 'emul', 'walk_host.cpp'),
+                        '-o', so], check=True)
+        L = C.CDLL(so)
+        dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.pwalk_host.restype = C.c_int
+        L.pwalk_host.argtypes = [dp, dp, ip, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, fp]
+        _walk_emul.lib = L
+    return _walk_emul.lib
+
+
+def _walk_host(zone_u, r_u, rD, step_u, lb, ub):
+    """tests/emul/walk_host.cpp: the device header of mbx_progressive_walk compiled for the host -> (f64 walk, f32 walk)."""
+    import ctypes as C
+    L = _walk_emul()
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    z, r, s = (np.ascontiguousarray(a, dtype=np.float64) for a in (zone_u, r_u, step_u))
+    d = np.ascontiguousarray(rD, dtype=np.int32)
+    B, n, D = s.shape
+    out = np.empty((B, n + 1, D)); out32 = np.empty((B, n + 1, D), np.float32)
+    assert L.pwalk_host(z.ctypes.data_as(dp), r.ctypes.data_as(dp), d.ctypes.data_as(ip), s.ctypes.data_as(dp), lb, ub, 10.0, B, D, n,
+                        out.ctypes.data_as(dp), out32.ctypes.data_as(fp)) == 0
+    return out, out32
+
+
+def test_progressive_walk_device_header_on_the_host_equals_the_oracle():
+    """One coordinate function for kernel and host: against the oracle's restatement of the reference walk, bit for bit, for the BBOB box
+    (a step never crosses the box twice) and the protein box (narrower than a step: mirrored points stay outside, like the reference)."""
+    from oracle import rl_hpsde as oh
+    g = np.random.RandomState(3)
+    for lb, ub, D in ((-5.0, 5.0, 10), (-5.0, 5.0, 30), (-1.5, 1.5, 12)):
+        B = 5
+        zone_u, r_u, rD, step_u = g.rand(B, D), g.rand(B, D), g.randint(0, D, size=B), g.rand(B, 200, D)
+        out, out32 = _walk_host(zone_u, r_u, rD, step_u, lb, ub)
+        for b in range(B):
+            want = oh.progressive_walk(lb, ub, zone_u[b], r_u[b], int(rD[b]), step_u[b])
+            np.testing.assert_array_equal(out[b], want)
+            np.testing.assert_array_equal(out32[b], want.astype(np.float32))
+        assert (out[:, 0][np.arange(B), rD] == np.where(zone_u[np.arange(B), rD] < 0.5, lb, ub)).all()
+        assert ((out < lb) | (out > ub)).any() == (ub - lb < 10)
+
+
+def _hpsde_cpu_engine(fids, dim, maxFEs, seed=3):
+    """RL_HPSDE_Engine on CPU tensors: mbx_eval / mbx_landscape_features are replaced by the oracle's functions and mbx_progressive_walk
+    by the host build of its own device header; everything else is the product code."""
+    import torch
+    from metabox_b200 import rl_hpsde as mh
+    from oracle import bbob as ob, landscape as ola
+    tr, te = ob.make_suite('bbob', dim, 5.0, 'easy')
+    insts = [[i for i in tr + te if i.fid == f][0] for f in fids]
+
+    def ev(x, gen):
+        x = x.numpy().astype(np.float64)
+        return torch.as_tensor(np.stack([(ob.func_true(I, x[b]) - I.optimum).astype(np.float32) for b, I in enumerate(insts)]))
+
+    def feats(sample, cost, ref):
+        s, c, r = sample.numpy(), cost.numpy(), ref.numpy()
+        return torch.as_tensor(np.array([[ola.dfdc_r(s[b], c[b], r[b]), ola.drie_r(c[b])] for b in range(len(s))]))
+
+    def walk(zone_u, r_u, rD, step_u):
+        return torch.as_tensor(_walk_host(zone_u.numpy(), r_u.numpy(), rD.numpy(), step_u.numpy(), -5.0, 5.0)[1])
+
+    eng = mh.RL_HPSDE_Engine(None, list(range(len(fids))), maxFEs, 50, seed=seed,
+                             _kernels=dict(dim=dim, lb=-5., ub=5., has_opt=True, eval=ev, features=feats, walk=walk))
+    return eng, insts
+
+
+def test_rl_hpsde_engine_host_logic_vs_oracle_with_injected_kernels():
+    """Every generation the engine draws its own tape on (CPU) tensors; the oracle replays exactly those draws from the engine's previous
+    state: sorted population / costs bit-exact, memories and reward to rounding, population-size schedule, state, accounting and curve
+    equal; a full run to the end of the budget (NP 180 -> 4)."""
+    import torch
+    from oracle import bbob as ob, rl_hpsde as oh
+    fids, dim, maxFEs = [1, 8, 15, 21], 10, 20000
+    eng, insts = _hpsde_cpu_engine(fids, dim, maxFEs)
+    cfg = oh.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    t0 = {k: v.numpy() for k, v in eng.last_tape.items()}
+    S = []
+    for b, I in enumerate(insts):
+        ev = lambda x, draws, I=I: ob.func_true(I, x)
+        s, state = oh.init_population(cfg, ev, I.optimum, -5., 5., oh.ArrayTape({k: v[b] for k, v in t0.items()}))
+        st = eng.read_state(b)
+        np.testing.assert_array_equal(st['group'], s.group); np.testing.assert_array_equal(st['cost'], s.cost)
+        assert int(st['feature']) == state and int(st['fes']) == s.fes == 180 + 201
+        S.append(s)
+    g = np.random.RandomState(0)
+    gens = 0
+    while not bool((eng.done != 0).all()):
+        gens += 1
+        action = g.randint(0, 4, size=len(fids))
+        was_done = eng.done.numpy().copy()
+        feat, reward, done = eng.update(torch.as_tensor(action), check_action=True)
+        tp = {k: v.numpy() for k, v in eng.last_tape.items()}
+        for b, I in enumerate(insts):
+            if was_done[b]:
+                assert float(reward[b]) == 0.0
+                continue
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            s, state, r, d = oh.update(cfg, S[b], int(action[b]), ev, I.optimum, -5., 5., oh.ArrayTape({k: v[b] for k, v in tp.items()}))
+            st = eng.read_state(b)
+            tag = f'generation {gens} lane {b}'
+            assert st['cost'].shape[0] == s.NP, tag
+            np.testing.assert_array_equal(st['group'], s.group, err_msg=tag); np.testing.assert_array_equal(st['cost'], s.cost, err_msg=tag)
+            np.testing.assert_allclose(st['MF'], s.MF, rtol=1e-12, err_msg=tag); np.testing.assert_allclose(st['MCr'], s.MCr, rtol=1e-12, err_msg=tag)
+            assert int(st['k']) == s.k and int(st['feature']) == state and bool(st['done']) == d, tag
+            np.testing.assert_allclose(float(eng.reward64[b]), r, rtol=1e-13, err_msg=tag)
+            assert int(st['fes']) == s.fes and int(st['log_index']) == s.log_index, tag
+            np.testing.assert_array_equal(st['curve'][:int(st['curve_len'])], np.array(s.curve, dtype=np.float32), err_msg=tag)
+            S[b] = s
+    assert gens >= 55 and eng.NP <= 5 and all(len(c) == 51 for c in eng.cost_curves())
+    with pytest.raises(ValueError):
+        eng.update(torch.as_tensor([0, 1, 2, 4]), check_action=True)
+
+
+def test_rl_hpsde_distinct_index_sampler():
+    """Production replacement of `generate_random_int`'s rejection loop: triples mutually distinct, != the row index, every admissible value
+    equally likely (smallest population NP = 4: each row gets a permutation of the three other rows)."""
+    import torch
+    eng, _ = _hpsde_cpu_engine([1, 8], 10, 20000)
+    for N in (4, 7, 180):
+        r = torch.stack([eng._distinct(N) for _ in range(400 if N < 100 else 3)]).numpy()          # [reps, B, N, 3]
+        i = np.arange(N)[None, None, :, None]
+        assert r.min() >= 0 and r.max() < N and not (r == i).any()
+        assert not ((r[..., 0] == r[..., 1]) | (r[..., 0] == r[..., 2]) | (r[..., 1] == r[..., 2])).any()
+        if N == 7:
+            for col in range(3):                                                                   # row 2 never draws 2, the other 6 values ~ 1/6 each
+                cnt = np.bincount(r[:, :, 2, col].reshape(-1), minlength=N)
+                assert cnt[2] == 0 and np.all(np.abs(cnt[[0, 1, 3, 4, 5, 6]] / cnt.sum() - 1 / 6) < 0.06)
