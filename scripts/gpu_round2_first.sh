@@ -11,3 +11,4 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:glee
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:deddqn_policy -s 3 -c 1 -o gpurun_out/r2a_ncu_deddqn_policy -f python scripts/policy_timing.py --only deddqn --reps 4 > /dev/null 2>&1
 ls -la gpurun_out | tail -8
 timeout 600 python scripts/train_timing.py > gpurun_out/r2a_train_timing.txt 2>&1; cat gpurun_out/r2a_train_timing.txt
+timeout 600 python scripts/composed_timing.py > gpurun_out/r2a_composed_timing.txt 2>&1; cat gpurun_out/r2a_composed_timing.txt
