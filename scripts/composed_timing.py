@@ -25,7 +25,7 @@ inst, _ = sweep.lane_table(len(probs), a.runs)
 maxFEs = 2000 * a.dim
 G = np.load(os.path.join(GOLD, 'agents2.npz'))
 dq = ma.load_reference_weights(ma.DEDQN_Net(), {k[6:]: G[k] for k in G.files if k.startswith('dedqn/')}).cuda().eval()
-qt = ma.RL_HPSDE_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda()
+qt = ma.RL_HPSDE_QTable(G['rl_hpsde_q']).cuda()           # the shipped agent's Q-table
 for name, make in (('DEDQN', lambda: sweep.DEDQN_Sweep(pack, inst, dq, maxFEs, 50, seed=1)),
                    ('RL_HPSDE', lambda: sweep.RL_HPSDE_Sweep(pack, inst, ma.fuse(qt), maxFEs, 50, seed=1))):
     sw = make()

@@ -10,6 +10,7 @@ gleet0/*, gleet0_kat/*   the same for checkpoint 0 (the freshly initialised acto
              checkpoint answers mu ~ 1, sigma ~ 0.7 almost everywhere, which pins the attention stack but hardly the heads); case 'r' of
              both KAT groups uses states the reference GLEET_Optimizer itself produced (tests/golden/gleet.npz)
 dedqn/*, dedqn_kat/*   Q-network of the shipped `DEDQN_Agent` (src/agent/dedqn_agent.py:13-25) + Q-values on states of reference runs
+qlpso_q, rl_hpsde_q    the [4, 4] Q-tables of the shipped tabular agents
 rl_pso/*     state_dict of `RL_PSO_Agent`'s PolicyNetwork (src/agent/rl_pso_agent.py:9-45) from `agent_model/test/bbob_easy`
 rl_pso_kat/* mu / sigma for seeded [B, 2*dim] states (dim 10: the shipped weights are dimension-specific), plus the
              reference's out-of-range action transformation evaluated on hand-built samples
@@ -94,6 +95,9 @@ def main():
         GD = np.load(os.path.join(HERE, 'dedqn.npz'))
         x = torch.as_tensor(np.concatenate([GD[f'{c}/state'][::13] for c in GD['cases']]).astype(np.float32))     # states of reference runs
         out['dedqn_kat/x'] = x.numpy(); out['dedqn_kat/q'] = dqn(x).numpy()
+        # ------------------------------------------------------------------ tabular agents: the shipped Q-tables (qlpso_agent.py:17, rl_hpsde_agent.py:13)
+        out['qlpso_q'] = np.asarray(_load('test/bbob_easy/QLPSO_Agent.pkl')._QLPSO_Agent__q_table, dtype=np.float64)
+        out['rl_hpsde_q'] = np.asarray(_load('test/bbob_easy/RL_HPSDE_Agent.pkl')._RL_HPSDE_Agent__q_table, dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, 'agents2.npz'), **out)
     print('rl_pso mu', mu.min().item(), mu.max().item(), 'sigma', sigma.min().item(), sigma.max().item(), 'filtered samples:', int(filt.sum()), 'of', filt.numel())
 

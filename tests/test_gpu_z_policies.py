@@ -533,7 +533,7 @@ def test_rl_hpsde_sweep_tester_and_dropin():
     import argparse
     import torch
     from metabox_b200 import agent as ma, environment as me, optimizer as mo, sweep
-    qt = ma.RL_HPSDE_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda()
+    qt = ma.RL_HPSDE_QTable(_weights('rl_hpsde')[1]['rl_hpsde_q']).cuda()                  # the shipped agent's Q-table
     pack, probs = _pack()
     inst, _ = sweep.lane_table(len(probs), 2)
     r1 = sweep.gather_results(sweep.RL_HPSDE_Sweep(pack, inst, qt, 4000, 50, seed=4).run(), 1).cpu().numpy()

@@ -197,6 +197,11 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
     q = dq(torch.as_tensor(G['dedqn_kat/x']))
     np.testing.assert_allclose(q.detach().numpy(), G['dedqn_kat/q'], rtol=1e-5, atol=1e-6)
     assert torch.equal(dq.act(torch.as_tensor(G['dedqn_kat/x'])), torch.as_tensor(np.argmax(G['dedqn_kat/q'], axis=1)))
+    for key in ('qlpso_q', 'rl_hpsde_q'):                                              # the shipped tabular agents load into the table policy
+        qt = ma.QLPSO_QTable(G[key])
+        a = qt(torch.arange(4, dtype=torch.int32), u=torch.full((4,), 0.5))
+        want = [int(np.searchsorted(np.cumsum(np.exp(G[key][s]) / np.exp(G[key][s]).sum()), 0.5, side='right')) for s in range(4)]
+        assert a.tolist() == [min(w, 3) for w in want] and G[key].shape == (4, 4)
 
 
 def _emul_lib(name='gleet_policy'):
