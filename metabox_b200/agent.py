@@ -300,6 +300,26 @@ class LDE_PolicyNet(nn.Module):
         return torch.clip(mu + sigma * eps, 0, 1), h2, c2
 
 
+# ------------------------------------------------------------------------------------------ L2L
+class L2L_PolicyNet(nn.Module):
+    """nn.LSTM(dim + 2 -> 32, proj_size = dim) in float64 (l2l_agent.py:20-21); `step` is the cell written out (gate order i, f, g, o;
+    h' = W_hr (o * tanh(c'))) so that the 100-step episode is plain matmuls on the current stream."""
+
+    def __init__(self, dim, hidden=32):
+        super().__init__()
+        self.dim, self.hidden = int(dim), int(hidden)
+        self.net = nn.LSTM(input_size=self.dim + 2, hidden_size=self.hidden, proj_size=self.dim, dtype=torch.float64)
+
+    @torch.no_grad()
+    def step(self, x, h, c):
+        """x [B, dim+2], h [B, dim], c [B, 32] (float64) -> raw action = h' [B, dim], c'."""
+        L = self.net
+        gates = torch.addmm(L.bias_ih_l0 + L.bias_hh_l0, x, L.weight_ih_l0.t()) + h @ L.weight_hh_l0.t()
+        i, f, g, o = gates.chunk(4, dim=-1)
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        return (torch.sigmoid(o) * torch.tanh(c2)) @ L.weight_hr_l0.t(), c2
+
+
 # ------------------------------------------------------------------------------------------ QLPSO
 class QLPSO_QTable(nn.Module):
     """Tabular policy of QLPSO_Agent (qlpso_agent.py:17-37): a [4, 4] Q-table; the action is sampled from

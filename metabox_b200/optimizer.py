@@ -847,3 +847,4 @@ class QLPSO_Optimizer(Learnable_Optimizer):
 # ======================================================================================== DEDQN (composed step, see dedqn.py)
 from .dedqn import DEDQN_Engine, DEDQN_Optimizer  # noqa: E402,F401
 from .rl_hpsde import RL_HPSDE_Engine, RL_HPSDE_Optimizer  # noqa: E402,F401  (composed step, see rl_hpsde.py)
+from .l2l import L2L_Engine, L2L_Optimizer  # noqa: E402,F401

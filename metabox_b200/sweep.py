@@ -248,6 +248,32 @@ class RL_HPSDE_Sweep(_Sweep):
         return self.policy(feat).reshape(-1)
 
 
+class L2L_Sweep(_Sweep):
+    """L2L_Agent.rollout_episode (l2l_agent.py:97-134): 100 steps of LSTM proposal -> evaluation; the result rows carry every second
+    best-so-far value as the curve and `sum(y) / y[0]` as the return, like the reference's rollout."""
+
+    def __init__(self, pack, lane_inst, net, maxFEs=100, n_logpoint=50, seed=0, lane_base=0, poll=50, time_kernels=False, graph=False):
+        from .l2l import L2L_Engine, T_MAX
+        eng = L2L_Engine(pack, lane_inst, seed=seed, lane_base=lane_base)
+        super().__init__(eng, T_MAX, poll, False, 1, time_kernels)            # eager: the engine's step index is a host-side argument
+        self.net = net
+        self.h = torch.zeros(eng.B, net.dim, dtype=torch.float64, device=eng.device)
+        self.c = torch.zeros(eng.B, net.hidden, dtype=torch.float64, device=eng.device)
+
+    def _reset_policy(self):
+        self.h.zero_(); self.c.zero_()
+
+    def _policy(self, feat):
+        h, c = self.net.step(feat, self.h, self.c)
+        self.h.copy_(h); self.c.copy_(c)
+        return h
+
+    def _result(self):
+        res = super()._result()
+        res['ret'] = self.engine.episode_return().to(torch.float32)
+        return res
+
+
 class GLEET_Sweep(_Sweep):
     """GLEET_Agent.rollout_episode (gleet_agent.py:293-303): `policy(state [B,NP,27]) -> action [B,NP]` in [0,1] (the
     reference's attention actor, or any torch callable, runs on the same stream between the fused steps)."""

@@ -555,3 +555,39 @@ def test_rl_hpsde_sweep_tester_and_dropin():
     assert 9 <= n <= 12 and env.optimizer.fes >= 4000
     with pytest.raises(ValueError):
         env.step(4)
+
+
+# ------------------------------------------------------------------------------------------------ L2L (metabox_b200/l2l.py)
+@pending_first_device_run
+def test_l2l_sweep_and_dropin_replay_reference_episodes():
+    """Whole episodes of the unmodified reference L2L agent (tests/golden/l2l.npz, shipped weights) through the sweep on the device and through
+    the drop-in optimizer: every-second-best curve, fes and return."""
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, environment as me, optimizer as mo, problem as mp, sweep
+    G = np.load(os.path.join(GOLDEN, 'l2l.npz'))
+    fids = [int(f) for f in G['fids'] if f < 100]
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', 10, 5)
+    probs = {p.fid: p for p in tr.data + te.data}
+    pack = mp.InstancePack([probs[f] for f in fids])
+    net = ma.L2L_PolicyNet(10)
+    net.net.load_state_dict({k[4:]: torch.as_tensor(G[k]) for k in G.files if k.startswith('net/')})
+    net = net.cuda().eval()
+    rows = sweep.gather_results(sweep.L2L_Sweep(pack, np.arange(len(fids), dtype=np.int32), net).run(), 1).cpu().numpy()
+    for b, f in enumerate(fids):
+        want = list(G[f'f{f}/cost']) + [G[f'f{f}/cost'][-1]]                               # 50 points, padded to 51 like tester.py:204-205
+        np.testing.assert_allclose(rows[b, :51], want, rtol=2e-5, err_msg=f'f{f}')
+        assert rows[b, 51] == 100
+        np.testing.assert_allclose(rows[b, 52], float(G[f'f{f}/ret']), rtol=1e-4)
+    env = me.PBO_Env(probs[fids[0]], mo.L2L_Optimizer(argparse.Namespace(dim=10)))
+    env.reset()
+    h, c = torch.zeros(1, 10, dtype=torch.float64).cuda(), torch.zeros(1, 32, dtype=torch.float64).cuda()
+    x = torch.zeros(1, 12, dtype=torch.float64).cuda()
+    ys, done = [], False
+    while not done:
+        h, c = net.step(x, h, c)
+        y, r, done = env.step(h[0].cpu().numpy())
+        ys.append(float(y))
+        x = torch.cat((h, torch.tensor([[float(y), 1.0]], dtype=torch.float64).cuda()), dim=1)
+    np.testing.assert_allclose(ys, G[f'f{fids[0]}/y'], rtol=2e-5)
+    assert r == 0 and len(env.optimizer.cost) == 100

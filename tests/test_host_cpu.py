@@ -1154,3 +1154,46 @@ def test_rl_hpsde_distinct_index_sampler():
             for col in range(3):                                                                   # row 2 never draws 2, the other 6 values ~ 1/6 each
                 cnt = np.bincount(r[:, :, 2, col].reshape(-1), minlength=N)
                 assert cnt[2] == 0 and np.all(np.abs(cnt[[0, 1, 3, 4, 5, 6]] / cnt.sum() - 1 / 6) < 0.06)
+
+
+# ----------------------------------------------------------------------------------------- L2L: engine + policy host logic vs golden episodes
+def test_l2l_engine_and_policy_replay_reference_episodes():
+    """Product host logic (L2L_Engine with the evaluation kernel replaced by the oracle's function, agent.L2L_PolicyNet with the shipped
+    weights, the sweep's recurrence) through whole episodes of the unmodified reference (tests/golden/l2l.npz): costs, every-second-best
+    curve, fes, return."""
+    import torch
+    from metabox_b200 import agent as ma, l2l as ml
+    from oracle import bbob as ob
+    G = np.load(os.path.join(GOLDEN, 'l2l.npz'))
+    fids = [int(f) for f in G['fids'] if f < 100]
+    tr, te = ob.make_suite('bbob', 10, 5.0, 'easy')
+    insts = [[i for i in tr + te if i.fid == f][0] for f in fids]
+
+    def ev(x, gen):
+        x = x.numpy().astype(np.float64)
+        return torch.as_tensor(np.stack([(ob.func_true(I, x[b]) - I.optimum).astype(np.float32) for b, I in enumerate(insts)]))
+
+    net = ma.L2L_PolicyNet(10)
+    net.net.load_state_dict({k[4:]: torch.as_tensor(G[k]) for k in G.files if k.startswith('net/')})
+    eng = ml.L2L_Engine(None, list(range(len(fids))), _kernels=dict(dim=10, lb=-5., ub=5., has_opt=True, eval=ev))
+    feat = eng.init_population()
+    h, c = torch.zeros(len(fids), 10, dtype=torch.float64), torch.zeros(len(fids), 32, dtype=torch.float64)
+    ys = []
+    for t in range(100):
+        h, c = net.step(feat, h, c)
+        feat, y, done = eng.update(h)
+        ys.append(y.numpy().copy())
+    ys = np.array(ys)                                                  # [100, lanes]
+    assert bool((done != 0).all()) and torch.all(eng.fes == 100)
+    for b, f in enumerate(fids):
+        np.testing.assert_allclose(ys[:, b], G[f'f{f}/y'], rtol=2e-6, err_msg=f'f{f}')
+        np.testing.assert_allclose(eng.cost_curves(pad=False)[b], G[f'f{f}/cost'], rtol=2e-6)
+        np.testing.assert_allclose(float(eng.episode_return()[b]), float(G[f'f{f}/ret']), rtol=1e-6)
+    before = eng.fes.clone()
+    eng.update(h)                                                      # finished lanes are frozen
+    assert torch.equal(eng.fes, before)
+    # nn.LSTM itself (the reference's call) agrees with the written-out cell
+    out, (h2, c2) = net.net(feat[None, :1], (h[None, :1], c[None, :1]))
+    hs, cs = net.step(feat[:1], h[:1], c[:1])
+    np.testing.assert_allclose(out[0].detach().numpy(), hs.numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(c2[0].detach().numpy(), cs.numpy(), rtol=1e-12, atol=1e-14)

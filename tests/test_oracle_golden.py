@@ -555,3 +555,22 @@ def test_rl_hpsde_generations_match_reference():
     assert seen_done and seen_states == {0, 1, 2, 3} and n_tie_swaps >= 1          # tied costs do occur (plateaus, converged swarms)
     with pytest.raises(ValueError):
         oh.update(cfg, S, 4, ev, optimum, lb, ub, oh.NumpyTape(dim, nc))
+
+
+# ------------------------------------------------------------------------------------------ L2L
+def test_l2l_episodes_match_reference():
+    """Whole 100-step episodes of the real L2L agent + optimizer (shipped weights, dim 10; no random draws for noise-free functions) vs the
+    oracle's LSTM-with-projection restatement and update rule: every cost the episode saw, the returned curve, fes and return."""
+    from oracle import l2l as ol
+    G = load('l2l.npz')
+    import torch
+    w = {k[4:]: torch.as_tensor(G[k]) for k in G.files if k.startswith('net/')}
+    for fid in G['fids']:
+        if fid > 100:
+            continue                                                   # noisy: the reference's noise comes from np.random inside eval
+        I, ev, optimum, lb, ub, nc = _problem_for(str(fid), 10)
+        r = ol.rollout(w, 10, ev, optimum, lb, ub)
+        np.testing.assert_allclose(r['y'], G[f'f{fid}/y'], rtol=2e-6, err_msg=f'f{fid}')
+        np.testing.assert_allclose(r['cost'], G[f'f{fid}/cost'], rtol=2e-6)
+        assert r['fes'] == int(G[f'f{fid}/fes']) == 100 and len(r['cost']) == 50
+        np.testing.assert_allclose(r['ret'], float(G[f'f{fid}/ret']), rtol=1e-6)
