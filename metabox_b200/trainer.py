@@ -302,26 +302,36 @@ GLEET_LR, GLEET_MAX_GRAD_NORM = 1e-4, 0.1                                       
 
 
 class _GleetActorHead:
-    """`ppo_losses` view of the GLEET actor: states [T,L,NP,27], actions [T,L,NP] -> joint log-probability [T,L]."""
+    """`ppo_losses` view of the GLEET actor: states [T,L,NP,27], actions [T,L,NP] -> joint log-probability [T,L].  The decoder output of
+    the last `log_prob` call is kept (with its autograd graph) so that the critic head, which `ppo_losses` calls next on the SAME states,
+    does not run the attention stack a second time."""
 
     def __init__(self, actor):
         self.actor = actor
+        self.cached = (None, None)                      # (states tensor, decoder logits [T*L, NP, 16])
 
     def log_prob(self, states, actions):
         lead = states.shape[:-2]
-        return self.actor.log_prob(states.reshape(-1, *states.shape[-2:]), actions.reshape(-1, actions.shape[-1])).reshape(lead)
+        mu, sigma, lg = self.actor.distribution(states.reshape(-1, *states.shape[-2:]))
+        self.cached = (states, lg)
+        return torch.distributions.Normal(mu, sigma).log_prob(actions.reshape(-1, actions.shape[-1])).sum(-1).reshape(lead)
 
 
 class _GleetCriticHead:
     """The GLEET critic reads the ACTOR's decoder output (gleet_agent.py:147-150, 236): value(states [...,NP,27]) -> [...]; the baseline loss
     therefore also trains the actor's attention stack, exactly like the reference."""
 
-    def __init__(self, actor, critic):
-        self.actor, self.critic = actor, critic
+    def __init__(self, actor, critic, actor_head=None):
+        self.actor, self.critic, self.actor_head = actor, critic, actor_head
 
     def __call__(self, states):
         lead = states.shape[:-2]
-        return self.critic(self.actor.logits(states.reshape(-1, *states.shape[-2:]))).reshape(lead)
+        if self.actor_head is not None and self.actor_head.cached[0] is states:
+            lg = self.actor_head.cached[1]
+            self.actor_head.cached = (None, None)       # one use: the next epoch runs with updated weights
+        else:
+            lg = self.actor.logits(states.reshape(-1, *states.shape[-2:]))
+        return self.critic(lg).reshape(lead)
 
 
 class GLEET_Trainer(_PPOTrainer):
@@ -341,7 +351,8 @@ class GLEET_Trainer(_PPOTrainer):
         return list(self.actor.parameters()) + list(self.critic.parameters())
 
     def _heads(self):
-        return _GleetActorHead(self.actor), _GleetCriticHead(self.actor, self.critic)
+        head = _GleetActorHead(self.actor)
+        return head, _GleetCriticHead(self.actor, self.critic, head)
 
     def _engine(self, mine, lo):
         cfg = self.config

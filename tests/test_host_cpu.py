@@ -727,7 +727,8 @@ def test_gleet_ppo_losses_match_the_reference_formulas():
     T, L, NP = 4, 3, 12
     states, actions = torch.rand(T, L, NP, 27), torch.rand(T, L, NP)
     rewards, nxt = torch.rand(T, L) * 0.2, torch.rand(L, NP, 27)
-    ah, ch = mt._GleetActorHead(actor), mt._GleetCriticHead(actor, critic)
+    ah = mt._GleetActorHead(actor)
+    ch = mt._GleetCriticHead(actor, critic, ah)                                       # shares the decoder output of log_prob(states)
     with torch.no_grad():
         old_logp = ah.log_prob(states, actions) + 0.05 * torch.randn(T, L)
     weight = torch.ones(T, L)
