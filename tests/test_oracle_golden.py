@@ -574,3 +574,46 @@ def test_l2l_episodes_match_reference():
         np.testing.assert_allclose(r['cost'], G[f'f{fid}/cost'], rtol=2e-6)
         assert r['fes'] == int(G[f'f{fid}/fes']) == 100 and len(r['cost']) == 50
         np.testing.assert_allclose(r['ret'], float(G[f'f{fid}/ret']), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ NRLPSO (oracle only: groundwork for a CUDA path)
+def test_nrlpso_steps_match_reference():
+    """260 consecutive single-particle steps of the real NRLPSO_Optimizer per case (float32 storage contract, np.random re-seeded before
+    every step) vs the oracle carrying its OWN state: the moved row, its velocity, personal / global best incl. the gbest view aliasing and
+    the never-refreshed pbest costs, neighbourhood mutants, rewards, variable evaluation counts, the next particle's state."""
+    from oracle import nrlpso as on
+    G = load('nrlpso.npz')
+    n_mut = 0
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        cfg = on.Config(dim=dim, maxFEs=int(G[f'{key}/maxFEs']), n_logpoint=int(G[f'{key}/n_logpoint']))
+        np.random.seed(int(G[f'{key}/seed0']))
+        S, state = on.init_population(cfg, ev, optimum, lb, ub, on.NumpyTape(dim, nc))
+        np.testing.assert_array_equal(S.pop, G[f'{key}/s0/pop'], err_msg=f'{key} init')
+        np.testing.assert_allclose(S.cost, G[f'{key}/s0/cost'], rtol=1e-6, atol=1e-10)
+        assert state == int(G[f'{key}/s0/state']) and S.r_w == float(G[f'{key}/s0/r_w'])
+        S.cost = G[f'{key}/s0/cost'].copy(); S.pbest_cost = S.cost.copy(); S.gbest_cost = np.float32(S.cost.min())
+        for t in range(1, int(G['n_steps']) + 1):
+            np.random.seed(int(G[f'{key}/seed'][t - 1]))
+            j, fes0 = S.pointer, S.fes
+            S, state, reward, done = on.update(cfg, S, int(G[f'{key}/action'][t - 1]), ev, optimum, lb, ub, on.NumpyTape(dim, nc))
+            tag = f'{key} step {t}'
+            np.testing.assert_array_equal(S.vel[j], G[f'{key}/row_vel'][t - 1], err_msg=tag)
+            np.testing.assert_array_equal(S.pop[j], G[f'{key}/row_pop'][t - 1], err_msg=tag)
+            np.testing.assert_allclose(S.cost[j], G[f'{key}/row_cost'][t - 1], rtol=1e-6, atol=1e-10, err_msg=tag)
+            np.testing.assert_array_equal(S.pbest_pos[j], G[f'{key}/row_pbest_pos'][t - 1], err_msg=tag)
+            np.testing.assert_allclose(S.pbest_cost[j], G[f'{key}/row_pbest_cost'][t - 1], rtol=1e-6, atol=1e-10, err_msg=tag)
+            np.testing.assert_array_equal(S.gbest(), G[f'{key}/gbest_pos'][t - 1], err_msg=tag)
+            np.testing.assert_allclose(float(S.gbest_cost), float(G[f'{key}/gbest_cost'][t - 1]), rtol=1e-6, atol=1e-10, err_msg=tag)
+            assert S.stag[j] == int(G[f'{key}/stag'][t - 1]) and state == int(G[f'{key}/state'][t - 1]) and reward == int(G[f'{key}/reward'][t - 1]), tag
+            assert done == bool(G[f'{key}/done'][t - 1]) and S.fes == int(G[f'{key}/fes'][t - 1]) and S.log_index == int(G[f'{key}/log_index'][t - 1]), tag
+            assert len(S.curve) == int(G[f'{key}/curve_len'][t - 1]) and abs(S.w - float(G[f'{key}/w'][t - 1])) <= 1e-15, tag
+            n_mut += (S.fes - fes0 - 1) // 2
+            if f'{key}/pop/{t}' in G:
+                np.testing.assert_array_equal(S.pop, G[f'{key}/pop/{t}'], err_msg=tag)
+                np.testing.assert_allclose(S.cost, G[f'{key}/cost/{t}'], rtol=1e-6, atol=1e-10, err_msg=tag)
+                S.cost = G[f'{key}/cost/{t}'].copy()
+            S.cost[j] = G[f'{key}/row_cost'][t - 1]; S.pbest_cost[j] = G[f'{key}/row_pbest_cost'][t - 1]      # last-bit teacher forcing of costs
+            S.gbest_cost = np.float32(G[f'{key}/gbest_cost'][t - 1])
+    assert n_mut >= 40
