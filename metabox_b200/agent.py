@@ -350,6 +350,7 @@ class QLPSO_QTable(nn.Module):
             q[s, a] += alpha * (r + gamma * q[n].max() - q[s, a])
 
 
+NRLPSO_QTable = QLPSO_QTable            # NRLPSO_Agent (nrlpso_agent.py:13,22-25,36-37): the same tabular softmax policy (gamma 0.8, alpha 1)
 RL_HPSDE_QTable = QLPSO_QTable          # RL_HPSDE_Agent (rl_hpsde_agent.py:13,27-30,42-43) is the same tabular softmax policy over 4 states x 4 actions (gamma 0.5)
 
 

@@ -229,6 +229,25 @@ class DEDQN_Sweep(_Sweep):
         return torch.argmax(self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0)), dim=-1)
 
 
+class NRLPSO_Sweep(_Sweep):
+    """NRLPSO_Agent.rollout_episode: the strategy is sampled from softmax(Q[state]) of a 4 x 4 table (`agent.NRLPSO_QTable` or its
+    single-kernel twin); one particle per step, 1 (+2 with a neighbourhood mutation) charged evaluations.  Composed engine, run eagerly."""
+
+    def __init__(self, pack, lane_inst, policy, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=200, time_kernels=False, graph=False):
+        from .nrlpso import NRLPSO_Engine
+        eng = NRLPSO_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        super().__init__(eng, maxFEs - eng.NP, poll, False, 1, time_kernels)
+        self.policy = policy
+        self.finite_reward = True                    # rewards are 2 / 1 / 0 / -2
+        self.kernels_per_step = 3 + (1 if getattr(policy, 'fused_action', False) else 0)     # mbx_eval: the moved particle + two mutants
+
+    def _policy(self, feat):
+        if getattr(self.policy, 'takes_uniform', False):
+            u = torch.rand(feat.shape[0], generator=self.gen, device=feat.device, dtype=torch.float32)
+            return self.policy(feat, u=u).reshape(-1)
+        return self.policy(feat).reshape(-1)
+
+
 class RL_HPSDE_Sweep(_Sweep):
     """RL_HPSDE_Agent.rollout_episode (rl_hpsde_agent.py:62-72): the action is sampled from softmax(Q[state]) of a 4 x 4 table
     (`agent.RL_HPSDE_QTable`, or its single-kernel twin); every generation charges NP + 201 evaluations with NP shrinking from 18 dim to 4.

@@ -81,18 +81,56 @@ def f32(a):
 
 
 class NumpyTape:
-    """Reference draw order on the global np.random."""
+    """Reference draw order on the global np.random (the oracle asks for the draws in the reference's order); `rec` keeps them by name so
+    that the batched engine can replay a step."""
 
     def __init__(self, D, noise_counts=(0, 0)):
         self.D, self.nc = D, noise_counts
+        self.rec = {}
 
-    def rand(self, *shape): return np.random.rand(*shape)
-    def randint(self, high, size=None): return np.random.randint(0, high, size=size) if size is not None else np.random.randint(0, high)
+    def init_u(self):
+        self.rec['init_u'] = np.random.rand(NP_, self.D)
+        return self.rec['init_u']
+
+    def init_rw(self):
+        self.rec['r_w'] = float(np.random.rand())
+        return self.rec['r_w']
+
+    def init_state(self):
+        self.rec['qstate'] = np.random.randint(low=0, high=N_STATE, size=NP_)
+        return self.rec['qstate']
+
+    def scalars(self):
+        self.rec['r1'], self.rec['r2'] = float(np.random.rand()), float(np.random.rand())                # :138-139
+        return self.rec['r1'], self.rec['r2']
+
+    def pick(self, name):                                                                                # get_p_a / get_p_b (:126-132)
+        self.rec[name] = int(np.random.randint(0, K_))
+        return self.rec[name]
+
+    def vec(self, name):                                                                                 # r1 / r2 of strategy 3, mutation steps
+        self.rec[name] = np.random.rand(self.D)
+        return self.rec[name]
 
     def noise(self, n):
         nu, nn = self.nc
         d = tuple(np.random.rand(n) for _ in range(nu)) + tuple(np.random.randn(n) for _ in range(nn))
         return d if d else None
+
+
+class ArrayTape:
+    """Replays named draws (a NumpyTape's `rec`, or the tape the batched engine drew on the device)."""
+
+    def __init__(self, rec):
+        self.rec = rec
+
+    def init_u(self): return np.asarray(self.rec['init_u'], dtype=np.float64)
+    def init_rw(self): return float(self.rec['r_w'])
+    def init_state(self): return np.asarray(self.rec['qstate'])
+    def scalars(self): return float(self.rec['r1']), float(self.rec['r2'])
+    def pick(self, name): return int(self.rec[name])
+    def vec(self, name): return np.asarray(self.rec[name], dtype=np.float64)
+    def noise(self, n): return None
 
 
 def _cost(ev, optimum, x32, tape):
@@ -103,12 +141,12 @@ def _cost(ev, optimum, x32, tape):
 def init_population(cfg: Config, ev, optimum, lb, ub, tape):
     """:30-61 -> (State, state of particle 0)."""
     D = cfg.dim
-    pop = f32(tape.rand(NP_, D) * (ub - lb) + lb)
+    pop = f32(tape.init_u() * (ub - lb) + lb)
     f = ev(pop.astype(np.float64), tape.noise(NP_))
     cost = f32(f if optimum is None else f - optimum)
     g = int(np.argmin(cost))
-    r_w = float(tape.rand())
-    qstate = np.asarray(tape.randint(N_STATE, NP_), dtype=np.int64)
+    r_w = tape.init_rw()
+    qstate = np.asarray(tape.init_state(), dtype=np.int64)
     z = np.zeros
     S = State(pop=pop, vel=z((NP_, D), np.float32), cost=cost, pbest_pos=pop.copy(), pbest_cost=cost.copy(), gbest_row=g, gbest_pos=pop[g].copy(),
               gbest_cost=np.float32(cost[g]), stag=z(NP_, np.int64), qstate=qstate, r_w=r_w, w=0.0,
@@ -148,7 +186,7 @@ def _neb_mutation(cfg, S, i, ev, optimum, tape):
     pb = S.pbest_pos[i].astype(np.float64)
     nb = S.pbest_neb[i].astype(np.float64)
     order = np.argsort(np.sqrt(np.sum((pb[None, :] - nb) ** 2, axis=-1)), kind='stable')
-    P3 = f32(pb + tape.rand(cfg.dim) * (nb[order[0]] - nb[order[-1]]))
+    P3 = f32(pb + tape.vec('mut_p') * (nb[order[0]] - nb[order[-1]]))
     S.fes += 1
     c = _cost(ev, optimum, P3, tape)
     if c < S.pbest_cost[i]:
@@ -159,7 +197,7 @@ def _neb_mutation(cfg, S, i, ev, optimum, tape):
     g = S.gbest().astype(np.float64)
     nb = S.gbest_neb.astype(np.float64)
     order = np.argsort(np.sqrt(np.sum((g[None, :] - nb) ** 2, axis=-1)), kind='stable')
-    P3 = f32(g + tape.rand(cfg.dim) * (nb[order[0]] - nb[order[-1]]))
+    P3 = f32(g + tape.vec('mut_g') * (nb[order[0]] - nb[order[-1]]))
     S.fes += 1
     c = _cost(ev, optimum, P3, tape)
     if c < S.gbest_cost:
@@ -180,13 +218,13 @@ def update(cfg: Config, S: State, action, ev, optimum, lb, ub, tape):
     w = S.w
     v_max = 0.1 * (ub - lb)
     # ---- generate_v_vector (:136-187)
-    r1, r2 = tape.rand(), tape.rand()
+    r1, r2 = tape.scalars()
     x = S.pop[i].astype(np.float64)
     v = S.vel[i].astype(np.float64)
     pb, gb = S.pbest_pos[i].astype(np.float64), S.gbest().astype(np.float64)
     cs = _cs(pb, gb)
-    p_a = lambda: S.gbest_neb[tape.randint(K_)].astype(np.float64)
-    p_b = lambda: S.pbest_neb[i][tape.randint(K_)].astype(np.float64)
+    p_a = lambda: S.gbest_neb[tape.pick('pick_a')].astype(np.float64)
+    p_b = lambda: S.pbest_neb[i][tape.pick('pick_b')].astype(np.float64)
     if action == 0:
         c1, c2 = 2.2, 1.8
         if cs < 0:
@@ -210,7 +248,7 @@ def update(cfg: Config, S: State, action, ev, optimum, lb, ub, tape):
     elif action == 3:
         c1, c2 = 1.8, 2.2
         P1 = p_b(); P2 = p_a()
-        r1 = tape.rand(D); r2 = tape.rand(D)
+        r1 = tape.vec('r1v'); r2 = tape.vec('r2v')
         v = w * v + c1 * r1 * (P1 - x) + c2 * r2 * (P2 - x)
     else:
         raise ValueError(f'action error: {action}')                                        # (the reference would fail on `None` arithmetic)

@@ -591,3 +591,65 @@ def test_l2l_sweep_and_dropin_replay_reference_episodes():
         x = torch.cat((h, torch.tensor([[float(y), 1.0]], dtype=torch.float64).cuda()), dim=1)
     np.testing.assert_allclose(ys, G[f'f{fids[0]}/y'], rtol=2e-5)
     assert r == 0 and len(env.optimizer.cost) == 100
+
+
+# ------------------------------------------------------------------------------------------------ NRLPSO backbone (composed step, metabox_b200/nrlpso.py)
+@pending_first_device_run
+def test_nrlpso_engine_on_the_device_vs_oracle_sweep_and_dropin():
+    """The composed NRLPSO step with the real evaluation kernel: every step the oracle replays the engine's own draws from the engine's
+    previous state (120 steps: the pointer wraps); then a complete sweep with the tabular policy and the drop-in optimizer."""
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, environment as me, nrlpso as mn, optimizer as mo, problem as mp, sweep
+    from oracle import bbob as ob, nrlpso as on
+    dim, maxFEs, fids = 10, 20000, [1, 3, 15, 21]
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', dim, 5)
+    probs = {p.fid: p for p in tr.data + te.data}
+    otr, ote = ob.make_suite('bbob', dim, 5.0)
+    oin = {i.fid: i for i in otr + ote}
+    pack = mp.InstancePack([probs[f] for f in fids])
+    eng = mn.NRLPSO_Engine(pack, list(range(len(fids))), maxFEs, 50, seed=12)
+    cfg = on.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    g = np.random.RandomState(1)
+    for t in range(1, 121):
+        action = g.randint(0, 4, size=len(fids))
+        prev = [eng.read_state(b) for b in range(len(fids))]
+        j = eng.pointer
+        feat, reward, done = eng.update(torch.as_tensor(action).cuda(), check_action=True)
+        tp = {k: v.cpu().numpy() for k, v in eng.last_tape.items()}
+        for b, f in enumerate(fids):
+            I = oin[f]
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            q = prev[b]
+            S = on.State(pop=q['pop'], vel=q['vel'], cost=q['cost'], pbest_pos=q['pbest_pos'], pbest_cost=q['pbest_cost'], gbest_row=int(q['gbest_row']),
+                         gbest_pos=q['gbest_pos'], gbest_cost=np.float32(q['gbest_cost']), stag=q['stag'], qstate=q['qstate'], r_w=float(q['r_w']),
+                         w=float(q['w']), pbest_neb_index=q['pbest_neb_index'], pbest_neb=q['pbest_neb'], gbest_neb_index=q['gbest_neb_index'],
+                         gbest_neb=q['gbest_neb'], pointer=j, fes=int(q['fes']), log_index=int(q['log_index']), curve=list(q['curve'][:int(q['curve_len'])]))
+            N, state, r, d = on.update(cfg, S, int(action[b]), ev, I.optimum, -5., 5., on.ArrayTape({k: v[b] for k, v in tp.items()}))
+            st = eng.read_state(b)
+            tag = f'step {t} lane {b} (fid {f})'
+            np.testing.assert_array_equal(st['vel'], N.vel, err_msg=tag)
+            np.testing.assert_array_equal(st['pop'][j], N.pop[j], err_msg=tag)
+            np.testing.assert_allclose(st['cost'][j], N.cost[j], rtol=1e-6, atol=1e-10, err_msg=tag)
+            if int(st['fes']) == N.fes and int(st['gbest_row']) == N.gbest_row:          # same branch decisions (a last-bit cost difference may flip a strict comparison)
+                np.testing.assert_array_equal(st['pop'], N.pop, err_msg=tag)
+                np.testing.assert_array_equal(st['pbest_pos'], N.pbest_pos, err_msg=tag)
+                np.testing.assert_array_equal(st['stag'], N.stag, err_msg=tag)
+            assert int(feat[b]) == state and int(st['log_index']) == N.log_index, tag
+    qt = ma.NRLPSO_QTable(np.array([[1., 0, 0, 2], [0, 1, 0, 0], [0, 0, 1, 0], [2, 0, 0, 1]])).cuda()
+    pk, pr = _pack()
+    inst, _ = sweep.lane_table(len(pr), 2)
+    r = sweep.gather_results(sweep.NRLPSO_Sweep(pk, inst, ma.fuse(qt), 600, 50, seed=4).run(), 1).cpu().numpy()
+    assert np.all((r[:, 51] >= 600) | (r[:, 50] <= 1e-8)) and np.all(r[:, 51] <= 602) and np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all()
+    env = me.PBO_Env(pr[0], mo.NRLPSO_Optimizer(argparse.Namespace(dim=10, maxFEs=400, n_logpoint=50, log_interval=8)))
+    np.random.seed(0)
+    state = env.reset()
+    done, n = False, 0
+    while not done:
+        state, reward, done = env.step(int(np.random.randint(0, 4)))
+        assert state in (0, 1, 2, 3) and reward in (2, 1, 0, -2)
+        n += 1
+    assert n <= 300 and env.optimizer.fes >= 400
+    with pytest.raises(ValueError):
+        env.step(7)

@@ -1198,3 +1198,63 @@ def test_l2l_engine_and_policy_replay_reference_episodes():
     hs, cs = net.step(feat[:1], h[:1], c[:1])
     np.testing.assert_allclose(out[0].detach().numpy(), hs.numpy(), rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(c2[0].detach().numpy(), cs.numpy(), rtol=1e-12, atol=1e-14)
+
+
+# ----------------------------------------------------------------------------------------- NRLPSO engine: host logic with an injected evaluation kernel
+def test_nrlpso_engine_host_logic_vs_oracle_with_injected_kernel():
+    """The engine draws its own tape on (CPU) tensors, the oracle (pinned against the unmodified reference) replays exactly those draws
+    while carrying its OWN state for 230 steps (the pointer wraps twice): rows, velocities, personal / global bests incl. the gbest view
+    aliasing, neighbourhood snapshots, mutants, stagnation counters, rewards, variable evaluation counts, next-particle state."""
+    import torch
+    from metabox_b200 import nrlpso as mn
+    from oracle import bbob as ob, nrlpso as on
+    fids, dim, maxFEs = [1, 15, 21, 8], 10, 20000
+    tr, te = ob.make_suite('bbob', dim, 5.0, 'easy')
+    insts = [[i for i in tr + te if i.fid == f][0] for f in fids]
+
+    def ev(x, gen):
+        x = x.numpy().astype(np.float64)
+        return torch.as_tensor(np.stack([(ob.func_true(I, x[b]) - I.optimum).astype(np.float32) for b, I in enumerate(insts)]))
+
+    eng = mn.NRLPSO_Engine(None, list(range(len(fids))), maxFEs, 50, seed=5, _kernels=dict(dim=dim, lb=-5., ub=5., has_opt=True, eval=ev))
+    cfg = on.Config(dim=dim, maxFEs=maxFEs)
+    feat = eng.init_population()
+    t0 = {k: v.numpy() for k, v in eng.last_tape.items()}
+    S = []
+    for b, I in enumerate(insts):
+        evo = lambda x, draws, I=I: ob.func_true(I, x)
+        s, state = on.init_population(cfg, evo, I.optimum, -5., 5., on.ArrayTape({k: v[b] for k, v in t0.items()}))
+        assert int(feat[b]) == state
+        np.testing.assert_array_equal(eng.pop[b].numpy(), s.pop); np.testing.assert_array_equal(eng.cost[b].numpy(), s.cost)
+        S.append(s)
+    g = np.random.RandomState(2)
+    n_mut = 0
+    for t in range(1, 231):
+        action = g.randint(0, 4, size=len(fids))
+        j = eng.pointer
+        feat, reward, done = eng.update(torch.as_tensor(action), check_action=True)
+        tp = {k: v.numpy() for k, v in eng.last_tape.items()}
+        for b, I in enumerate(insts):
+            evo = lambda x, draws, I=I: ob.func_true(I, x)
+            fes0 = S[b].fes
+            s, state, r, d = on.update(cfg, S[b], int(action[b]), evo, I.optimum, -5., 5., on.ArrayTape({k: v[b] for k, v in tp.items()}))
+            n_mut += (s.fes - fes0 - 1) // 2
+            st = eng.read_state(b)
+            tag = f'step {t} lane {b}'
+            for k in ('pop', 'vel', 'cost', 'pbest_pos', 'pbest_cost', 'stag', 'qstate'):
+                np.testing.assert_array_equal(st[k], getattr(s, k), err_msg=f'{tag} {k}')
+            assert int(st['gbest_row']) == s.gbest_row and float(st['gbest_cost']) == float(s.gbest_cost), tag
+            if s.gbest_row < 0:
+                np.testing.assert_array_equal(st['gbest_pos'], s.gbest_pos, err_msg=tag)
+            if j == 0:
+                np.testing.assert_array_equal(st['pbest_neb_index'], s.pbest_neb_index, err_msg=tag)
+                np.testing.assert_array_equal(st['gbest_neb_index'], s.gbest_neb_index, err_msg=tag)
+                np.testing.assert_array_equal(st['pbest_neb'], s.pbest_neb, err_msg=tag)
+                assert abs(float(st['w']) - s.w) <= 1e-15 and abs(float(st['r_w']) - s.r_w) <= 1e-15, tag
+            assert int(feat[b]) == state and float(reward[b]) == r and bool(done[b]) == d, tag
+            assert int(st['fes']) == s.fes and int(st['log_index']) == s.log_index, tag
+            np.testing.assert_array_equal(st['curve'][:int(st['curve_len'])], np.array(s.curve, dtype=np.float32), err_msg=tag)
+            S[b] = s
+    assert n_mut >= 5 and eng.pointer == 30
+    with pytest.raises(ValueError):
+        eng.update(torch.as_tensor([0, 1, 2, 4]), check_action=True)
