@@ -26,8 +26,11 @@ maxFEs = 2000 * a.dim
 G = np.load(os.path.join(GOLD, 'agents2.npz'))
 dq = ma.load_reference_weights(ma.DEDQN_Net(), {k[6:]: G[k] for k in G.files if k.startswith('dedqn/')}).cuda().eval()
 qt = ma.RL_HPSDE_QTable(G['rl_hpsde_q']).cuda()           # the shipped agent's Q-table
+nq = ma.NRLPSO_QTable(G['qlpso_q']).cuda()                  # (no NRLPSO agent is shipped; any 4 x 4 table drives the backbone)
+small = sweep.lane_table(len(probs), 8)[0]                  # NRLPSO: [lanes, 100, 100, D] float64 distance temporaries, one particle per step
 for name, make in (('DEDQN', lambda: sweep.DEDQN_Sweep(pack, inst, dq, maxFEs, 50, seed=1)),
-                   ('RL_HPSDE', lambda: sweep.RL_HPSDE_Sweep(pack, inst, ma.fuse(qt), maxFEs, 50, seed=1))):
+                   ('RL_HPSDE', lambda: sweep.RL_HPSDE_Sweep(pack, inst, ma.fuse(qt), maxFEs, 50, seed=1)),
+                   ('NRLPSO', lambda: sweep.NRLPSO_Sweep(pack, small, ma.fuse(nq), min(maxFEs, 3000), 50, seed=1))):
     sw = make()
     sw.run()                                               # warm-up
     torch.cuda.synchronize()
@@ -38,5 +41,5 @@ for name, make in (('DEDQN', lambda: sweep.DEDQN_Sweep(pack, inst, dq, maxFEs, 5
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     fes = int(res['fes'].sum())
-    print(f'{name:9s} dim {a.dim}: {len(inst)} lanes x {res["steps"]} steps, {fes / 1e6:8.1f} M charged evaluations in {ms:8.1f} ms = '
+    print(f'{name:9s} dim {a.dim}: {sw.engine.B} lanes x {res["steps"]} steps, {fes / 1e6:8.1f} M charged evaluations in {ms:8.1f} ms = '
           f'{fes / ms / 1e3:8.1f} M evals/s ({ms / max(1, res["steps"]):6.2f} ms per step, composed / eager)')
