@@ -43,10 +43,13 @@ class DEDQN_Engine:
             self.has_opt = pack.kind == _lib.KIND_BBOB
             self._eval = lambda x, gen: pack.eval_device(self.lane_inst, x, subtract_optimum=self.has_opt, seed=self._eval_seed, gen=gen)
             self._features = lambda sample, cost: landscape.features(sample, cost)[:, :4]
+            hh = getattr(pack, 'h_headers', None)
+            self._noisy = True if hh is None or 'noise' not in (hh.dtype.names or ()) else bool((hh['noise'] != 0).any())
         else:                                                         # tests inject CPU stand-ins for the two kernels
             self.device = torch.device(device or 'cpu')
             self.dim, self.lb, self.ub, self.has_opt = _kernels['dim'], float(_kernels['lb']), float(_kernels['ub']), bool(_kernels['has_opt'])
             self._eval, self._features = _kernels['eval'], _kernels['features']
+            self._noisy = bool(_kernels.get('noisy', True))
         self.lane_base, self.seed = int(lane_base), int(seed)
         self._eval_seed = (self.seed * 0x9E3779B97F4A7C15 + self.lane_base * 0xD1B54A32D192ED03 + 0x2545F491) & (2 ** 63 - 1)
         self.NP = int(NP or DEDQN_Engine.NP)
@@ -94,7 +97,9 @@ class DEDQN_Engine:
         x = self.pop.to(torch.float64)
         pmin, pmax = x.min(dim=1, keepdim=True).values, x.max(dim=1, keepdim=True).values
         sample = pmin + (pmax - pmin) * walk
-        c = self._eval(self.pop, gen).to(torch.float64)                                       # the POPULATION's costs (reference quirk)
+        # the POPULATION's costs, not the walk's (reference quirk).  A noise-free evaluation of the stored population reproduces `self.cost`
+        # bit for bit (same kernel, same float32 inputs), so only noisy suites pay for the NP re-evaluations
+        c = (self._eval(self.pop, gen) if self._noisy else self.cost).to(torch.float64)
         self.last_sample, self.last_cost = sample, c                                          # (read by the parity tests)
         f = self._features(sample.contiguous(), c.contiguous())
         alive = (self.done == 0)[:, None]

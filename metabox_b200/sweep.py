@@ -223,7 +223,7 @@ class DEDQN_Sweep(_Sweep):
         eng = DEDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
         super().__init__(eng, int(math.ceil(maxFEs / (2 * eng.NP))) + 1, poll, False, 1, time_kernels)
         self.net = net
-        self.kernels_per_step = 3                         # mbx_eval (trial), mbx_eval (population), mbx_landscape_features
+        self.kernels_per_step = 3 if eng._noisy else 2    # mbx_eval (trial), mbx_eval (population; noisy suites only), mbx_landscape_features
 
     def _policy(self, feat):
         return torch.argmax(self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0)), dim=-1)

@@ -909,7 +909,7 @@ def test_bench_product_arm_refuses_to_run_without_a_gpu():
 
 
 # ----------------------------------------------------------------------------------------- DEDQN engine: host logic with injected kernels
-def _dedqn_cpu_engine(fids, dim, maxFEs, seed=3):
+def _dedqn_cpu_engine(fids, dim, maxFEs, seed=3, noisy=True):
     """DEDQN_Engine on CPU tensors: the two CUDA kernels it composes (mbx_eval, mbx_landscape_features) are replaced by the oracle's
     functions, everything else -- the batched single-row DE arithmetic, selection, survival, accounting, curve protocol -- is the product
     code.  (Only tests can inject kernels; the product constructor needs a CUDA InstancePack.)"""
@@ -927,7 +927,8 @@ def _dedqn_cpu_engine(fids, dim, maxFEs, seed=3):
         s, c = sample.numpy(), cost.numpy()
         return torch.as_tensor(np.array([[ola.cal_fdc(s[b], c[b]), ola.cal_rie(c[b]), ola.cal_acf(c[b]), ola.cal_nop(s[b], c[b])] for b in range(len(s))]))
 
-    eng = md.DEDQN_Engine(None, list(range(len(fids))), maxFEs, 50, seed=seed, _kernels=dict(dim=dim, lb=-5., ub=5., has_opt=True, eval=ev, features=feats))
+    eng = md.DEDQN_Engine(None, list(range(len(fids))), maxFEs, 50, seed=seed,
+                          _kernels=dict(dim=dim, lb=-5., ub=5., has_opt=True, eval=ev, features=feats, noisy=noisy))
     return eng, insts
 
 
@@ -994,7 +995,7 @@ def test_dedqn_engine_replays_the_reference_tape():
     from oracle import bbob as ob, dedqn as od
     G = np.load(os.path.join(GOLDEN, 'dedqn.npz'))
     key, dim = 'f15_d10', 10
-    eng, insts = _dedqn_cpu_engine([15], dim, int(G[f'{key}/maxFEs']))
+    eng, insts = _dedqn_cpu_engine([15], dim, int(G[f'{key}/maxFEs']), noisy=False)       # noise-free suite: the features reuse the stored costs
     nt = od.NumpyTape(100, dim)
     np.random.seed(int(G[f'{key}/seed0']))
     nt.init_u(); nt.walk_u()
