@@ -341,7 +341,7 @@ def test_dedqn_sweep_tester_and_dropin():
     r2 = sweep.gather_results(sweep.DEDQN_Sweep(pack, inst, net, 3000, 50, seed=4).run(), 1).cpu().numpy()
     np.testing.assert_array_equal(r1, r2)                                                  # same seed -> same rows
     assert np.all((r1[:, 51] == 3000) | (r1[:, 50] <= 1e-8)) and np.all(np.diff(r1[:, :51], axis=1) <= 0) and np.isfinite(r1).all()
-    assert np.all(r1[:, 52] > 0) and sw.launches >= 3 * 14
+    assert np.all(r1[:, 52] > 0) and sw.launches >= 2 * 14
     # drop-in: PBO_Env + DEDQN_Optimizer with the reference's signatures
     cfg = argparse.Namespace(dim=10, maxFEs=3000, n_logpoint=50, log_interval=60)
     env = me.PBO_Env(probs[0], mo.DEDQN_Optimizer(cfg))
