@@ -95,9 +95,14 @@ class NRLPSO_Engine:
 
     @staticmethod
     def _pairwise(a, b):
-        """[B,n,D], [B,m,D] float64 -> [B,n,m] Euclidean distances, summed over D like the reference (no GEMM expansion)."""
+        """[B,n,D], [B,m,D] float64 -> [B,n,m] Euclidean distances.  Accumulated dimension by dimension: the temporaries stay [B,n,m] (a
+        broadcast difference tensor would be D times larger: 2.4 MB per lane at D = 30), and no GEMM expansion loses digits."""
         import torch
-        return torch.sqrt(torch.sum((a[:, :, None, :] - b[:, None, :, :]) ** 2, dim=-1))
+        acc = torch.zeros(a.shape[0], a.shape[1], b.shape[1], dtype=a.dtype, device=a.device)
+        for d in range(a.shape[2]):
+            diff = a[:, :, None, d] - b[:, None, :, d]
+            acc += diff * diff
+        return torch.sqrt(acc)
 
     def _ef(self, x, i):
         """:107-121 for particle i of every lane; x [B,NP,D] float64."""
