@@ -124,6 +124,7 @@ def test_rl_pso_sweep_with_the_reference_policy_net():
 
 
 # ------------------------------------------------------------------------------------------------ fused policy kernel (mbx_gleet_policy)
+@pending_first_device_run          # (passed on a B200 with exp2f in the softmax; the one-instruction ex2.approx variant has not run yet)
 def test_fused_gleet_policy_kernel_known_answers_and_torch_module():
     """One CTA per swarm: against forwards of the unmodified reference (both checkpoints; random, ragged and reference-produced states) and
     against the torch module on the device under the same action noise."""
