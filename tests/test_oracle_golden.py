@@ -617,3 +617,31 @@ def test_nrlpso_steps_match_reference():
             S.cost[j] = G[f'{key}/row_cost'][t - 1]; S.pbest_cost[j] = G[f'{key}/row_pbest_cost'][t - 1]      # last-bit teacher forcing of costs
             S.gbest_cost = np.float32(G[f'{key}/gbest_cost'][t - 1])
     assert n_mut >= 40
+
+
+# ------------------------------------------------------------------------------------------ LES
+def test_les_generations_match_reference():
+    """40 consecutive generations of the real LES_Optimizer per case (stepped with its own skip_step = 1, np.random re-seeded before every
+    generation) vs the oracle carrying its OWN float64 state: population, raw costs, mean / step size, the six evolution paths, gbest,
+    evaluation count and log index."""
+    from oracle import les as ol
+    G = load('les.npz')
+    attn, mlp = G['attn'], G['mlp']
+    assert len(attn) == ol.N_ATTN and len(mlp) == ol.N_MLP
+    for key in G['cases']:
+        fid, dim = str(G[f'{key}/fid']), int(G[f'{key}/dim'])
+        I, ev, optimum, lb, ub, nc = _problem_for(fid, dim)
+        maxFEs, log_interval = int(G[f'{key}/maxFEs']), int(G[f'{key}/log_interval'])
+        np.random.seed(int(G[f'{key}/seed0']))
+        S = ol.init_population(dim, maxFEs, ev, lb, ub)
+        np.testing.assert_array_equal(S.parents, G[f'{key}/s0/parents']); np.testing.assert_array_equal(S.mu, G[f'{key}/s0/mu'])
+        np.testing.assert_allclose(S.cost, G[f'{key}/s0/cost'], rtol=1e-12)
+        for t in range(1, int(G['n_gen']) + 1):
+            np.random.seed(int(G[f'{key}/seed'][t - 1]))
+            S = ol.generation(S, attn, mlp, dim, maxFEs, log_interval, ev, optimum, lb, ub)
+            tag = f'{key} generation {t}'
+            for k in ('parents', 'mu', 'sigma', 'Pc', 'Ps'):
+                np.testing.assert_allclose(getattr(S, k), G[f'{key}/{k}'][t - 1], rtol=1e-9, atol=1e-12, err_msg=f'{tag} {k}')
+            np.testing.assert_allclose(S.cost, G[f'{key}/cost'][t - 1], rtol=1e-9, err_msg=tag)
+            np.testing.assert_allclose(S.gbest, float(G[f'{key}/gbest'][t - 1]), rtol=1e-12, err_msg=tag)
+            assert S.fes == int(G[f'{key}/fes'][t - 1]) == 16 * (t + 1) and S.t == t and S.log_index == int(G[f'{key}/log_index'][t - 1]), tag
