@@ -208,7 +208,7 @@ class DEDQN_Engine:
 
     def read_state(self, b):
         keys = ('pop', 'cost', 'survival', 'gbest', 'gbest_cost', 'gbest_row', 'fes', 'log_index', 'curve_len', 'curve', 'done', 'feature64')
-        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+        return {k: getattr(self, k)[b].cpu().numpy().copy() for k in keys}
 
     def load_state(self, b, **arrays):
         import torch

@@ -289,7 +289,7 @@ class NRLPSO_Engine:
     def read_state(self, b):
         keys = ('pop', 'vel', 'cost', 'pbest_pos', 'pbest_cost', 'gbest_pos', 'gbest_cost', 'gbest_row', 'stag', 'qstate', 'r_w', 'w',
                 'pbest_neb_index', 'pbest_neb', 'gbest_neb_index', 'gbest_neb', 'fes', 'log_index', 'curve_len', 'curve', 'done', 'feature')
-        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+        return {k: getattr(self, k)[b].cpu().numpy().copy() for k in keys}
 
 
 class NRLPSO_Optimizer:

@@ -849,3 +849,4 @@ from .dedqn import DEDQN_Engine, DEDQN_Optimizer  # noqa: E402,F401
 from .rl_hpsde import RL_HPSDE_Engine, RL_HPSDE_Optimizer  # noqa: E402,F401  (composed step, see rl_hpsde.py)
 from .l2l import L2L_Engine, L2L_Optimizer  # noqa: E402,F401
 from .nrlpso import NRLPSO_Engine, NRLPSO_Optimizer  # noqa: E402,F401
+from .les import LES_Engine, LES_Optimizer  # noqa: E402,F401

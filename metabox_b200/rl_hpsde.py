@@ -272,7 +272,7 @@ class RL_HPSDE_Engine:
 
     def read_state(self, b):
         keys = ('group', 'cost', 'MF', 'MCr', 'k', 'gbest', 'fes', 'log_index', 'curve_len', 'curve', 'done', 'feature', 'dfdc', 'drie')
-        return {k: getattr(self, k)[b].cpu().numpy() for k in keys}
+        return {k: getattr(self, k)[b].cpu().numpy().copy() for k in keys}
 
 
 class RL_HPSDE_Optimizer:

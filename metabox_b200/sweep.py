@@ -248,6 +248,26 @@ class NRLPSO_Sweep(_Sweep):
         return self.policy(feat).reshape(-1)
 
 
+class LES_Sweep(_Sweep):
+    """LES_Agent.rollout_episode: ONE `update(action)` of the reference runs the whole episode with the agent's best network parameters
+    (`params` = {'attn': [68], 'mlp': [178]}); here every generation is one engine step.  Composed engine, run eagerly (`mbx_eval`'s step
+    index is a host argument)."""
+
+    def __init__(self, pack, lane_inst, params, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=64, time_kernels=False, graph=False):
+        from .les import LES_Engine, NP_
+        eng = LES_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base).set_params(params['attn'], params['mlp'])
+        super().__init__(eng, int(math.ceil(maxFEs / NP_)) + 1, poll, False, 1, time_kernels)
+        self.finite_reward = True
+
+    def _policy(self, feat):
+        return None                                   # the parameters installed at construction are the whole policy
+
+    def _result(self):
+        res = super()._result()
+        res['ret'] = self.engine.episode_return().to(torch.float32)
+        return res
+
+
 class RL_HPSDE_Sweep(_Sweep):
     """RL_HPSDE_Agent.rollout_episode (rl_hpsde_agent.py:62-72): the action is sampled from softmax(Q[state]) of a 4 x 4 table
     (`agent.RL_HPSDE_QTable`, or its single-kernel twin); every generation charges NP + 201 evaluations with NP shrinking from 18 dim to 4.

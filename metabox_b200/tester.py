@@ -23,7 +23,7 @@ import numpy as np
 
 N_RUNS_TEST, N_RUNS_ROLLOUT = 51, 5           # tester.py:121, :318
 AGENT_ALGO = {'RLEPSO_Agent': 'rlepso', 'LDE_Agent': 'lde', 'DE_DDQN_Agent': 'deddqn', 'GLEET_Agent': 'gleet', 'RL_PSO_Agent': 'rl_pso',
-              'QLPSO_Agent': 'qlpso', 'DEDQN_Agent': 'dedqn', 'RL_HPSDE_Agent': 'rl_hpsde', 'L2L_Agent': 'l2l', 'NRLPSO_Agent': 'nrlpso'}
+              'QLPSO_Agent': 'qlpso', 'DEDQN_Agent': 'dedqn', 'RL_HPSDE_Agent': 'rl_hpsde', 'L2L_Agent': 'l2l', 'NRLPSO_Agent': 'nrlpso', 'LES_Agent': 'les'}
 
 
 def cal_t0(dim, fes):
@@ -76,6 +76,8 @@ def _make_sweep(algo, pack, lanes, policy, config, seed, lane_base, stripes):
             return ms.GLEET_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
         if algo == 'rl_pso':                                  # policy: state [B,2D] -> action [B]
             return ms.RL_PSO_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
+        if algo == 'les':                                     # policy: {'attn': [68], 'mlp': [178]} network parameters (the agent's best solution)
+            return ms.LES_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
         if algo == 'nrlpso':                                  # policy: state [B] int32 in 0..3 -> strategy [B] in 0..3 (tabular)
             return ms.NRLPSO_Sweep(pack, ln, policy, config.maxFEs, n_log, seed=seed, lane_base=lb)
         if algo == 'l2l':                                     # policy: agent.L2L_PolicyNet (float64 LSTM with projection)

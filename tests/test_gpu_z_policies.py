@@ -654,3 +654,44 @@ def test_nrlpso_engine_on_the_device_vs_oracle_sweep_and_dropin():
     assert n <= 300 and env.optimizer.fes >= 400
     with pytest.raises(ValueError):
         env.step(7)
+
+
+# ------------------------------------------------------------------------------------------------ LES (metabox_b200/les.py)
+@pending_first_device_run
+def test_les_engine_on_the_device_replays_reference_generations_sweep_and_dropin():
+    """Golden generations of the unmodified reference (tests/golden/les.npz) through the engine with the real float64 evaluation kernel,
+    then a complete sweep and the drop-in optimizer."""
+    import argparse
+    import torch
+    from metabox_b200 import environment as me, les as ml, optimizer as mo, problem as mp, sweep
+    G = np.load(os.path.join(GOLDEN, 'les.npz'))
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', 10, 5)
+    probs = {p.fid: p for p in tr.data + te.data}
+    pack = mp.InstancePack([probs[1], probs[15]])
+    eng = ml.LES_Engine(pack, [0, 1], 20000, 50, seed=3).set_params(G['attn'], G['mlp'])
+    keys = ['f1_d10', 'f15_d10']
+    mu_u, zn = [], []
+    for key in keys:
+        np.random.seed(int(G[f'{key}/seed0']))
+        mu_u.append(np.random.rand(10)); zn.append(np.random.standard_normal((16, 10)))
+    eng.init_population(tape={'mu_u': np.stack(mu_u), 'normal': np.stack(zn)})
+    for b, key in enumerate(keys):
+        np.testing.assert_allclose(eng.cost[b].cpu().numpy(), G[f'{key}/s0/cost'], rtol=1e-10)
+    for t in range(1, 41):
+        zn = []
+        for key in keys:
+            np.random.seed(int(G[f'{key}/seed'][t - 1])); zn.append(np.random.standard_normal((16, 10)))
+        eng.update(tape={'normal': np.stack(zn)})
+        for b, key in enumerate(keys):
+            for k in ('parents', 'mu', 'sigma', 'Pc', 'Ps', 'cost'):
+                np.testing.assert_allclose(getattr(eng, k)[b].cpu().numpy(), G[f'{key}/{k}'][t - 1], rtol=1e-4, atol=1e-6, err_msg=f'{key} generation {t} {k}')
+            assert int(eng.fes[b]) == int(G[f'{key}/fes'][t - 1])
+    pk, pr = _pack()
+    inst, _ = sweep.lane_table(len(pr), 2)
+    r = sweep.gather_results(sweep.LES_Sweep(pk, inst, {'attn': G['attn'], 'mlp': G['mlp']}, 1600, 50, seed=4).run(), 1).cpu().numpy()
+    assert np.all(r[:, 51] == 1600) and np.all(np.diff(r[:, :51], axis=1) <= 0) and np.isfinite(r).all() and np.all(r[:, 52] >= 0)
+    opt = mo.LES_Optimizer(argparse.Namespace(dim=10, maxFEs=1600, n_logpoint=50, log_interval=32))
+    env = me.PBO_Env(pr[0], opt)
+    assert env.reset() is None
+    gb, ret, is_end, info = env.step({'attn': G['attn'], 'mlp': G['mlp']})
+    assert is_end and opt.FEs == 1600 and 0 <= ret < 1 and len(opt.cost) == 51 and abs(gb - opt.cost[-1]) <= 1e-5 * abs(gb) and info == {}

@@ -1259,3 +1259,72 @@ def test_nrlpso_engine_host_logic_vs_oracle_with_injected_kernel():
     assert n_mut >= 5 and eng.pointer == 30
     with pytest.raises(ValueError):
         eng.update(torch.as_tensor([0, 1, 2, 4]), check_action=True)
+
+
+# ----------------------------------------------------------------------------------------- LES engine: host logic with an injected evaluation kernel
+def test_les_engine_host_logic_vs_oracle_and_golden_generations():
+    """(1) Golden generations of the unmodified reference (tests/golden/les.npz) through the ENGINE's batched update rule: the reference's
+    normal draws are recovered by re-seeding np.random and handed over as a tape.  (2) Free-running lanes: every generation the oracle
+    replays the engine's own draws from the engine's previous state; a whole episode ends with the curve protocol intact."""
+    import torch
+    from metabox_b200 import les as ml
+    from oracle import bbob as ob, les as ol
+    G = np.load(os.path.join(GOLDEN, 'les.npz'))
+    tr, te = ob.make_suite('bbob', 10, 5.0, 'easy')
+    insts = [[i for i in tr + te if i.fid == f][0] for f in (1, 15)]
+
+    def ev(x, gen):
+        x = x.numpy().astype(np.float64)
+        return torch.as_tensor(np.stack([ob.func_true(I, x[b]) for b, I in enumerate(insts)]))
+
+    mk = lambda maxFEs: ml.LES_Engine(None, [0, 1], maxFEs, 50, seed=3, _kernels=dict(dim=10, lb=-5., ub=5., has_opt=True, eval=ev)).set_params(G['attn'], G['mlp'])
+    # (1) replay of the reference
+    eng = mk(20000)
+    keys = ['f1_d10', 'f15_d10']
+    mu_u, zn = [], []
+    for key in keys:
+        np.random.seed(int(G[f'{key}/seed0']))
+        mu_u.append(np.random.rand(10)); zn.append(np.random.standard_normal((16, 10)))
+    eng.init_population(tape={'mu_u': np.stack(mu_u), 'normal': np.stack(zn)})
+    for b, key in enumerate(keys):
+        np.testing.assert_allclose(eng.parents[b].numpy(), G[f'{key}/s0/parents'], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(eng.cost[b].numpy(), G[f'{key}/s0/cost'], rtol=1e-12)
+    for t in range(1, 41):
+        zn = []
+        for key in keys:
+            np.random.seed(int(G[f'{key}/seed'][t - 1])); zn.append(np.random.standard_normal((16, 10)))
+        eng.update(tape={'normal': np.stack(zn)})
+        for b, key in enumerate(keys):
+            for k in ('parents', 'mu', 'sigma', 'Pc', 'Ps', 'cost'):
+                np.testing.assert_allclose(getattr(eng, k)[b].numpy(), G[f'{key}/{k}'][t - 1], rtol=2e-5, atol=1e-7, err_msg=f'{key} generation {t} {k}')
+            assert int(eng.fes[b]) == int(G[f'{key}/fes'][t - 1]) and int(eng.log_index[b]) == int(G[f'{key}/log_index'][t - 1])
+            np.testing.assert_allclose(float(eng.gbest[b]), float(G[f'{key}/gbest'][t - 1]), rtol=1e-6)
+    # (2) free-running, oracle from the engine's previous state
+    eng = mk(800)
+    eng.init_population()
+    for t in range(1, 50):
+        prev = [eng.read_state(b) for b in range(2)]
+        was_done = eng.done.numpy().copy()
+        t_before = eng.t
+        eng.update()
+        zn = eng.last_tape['normal'].numpy()
+        for b, I in enumerate(insts):
+            if was_done[b]:
+                continue
+            q = prev[b]
+            S = ol.State(parents=q['parents'], cost=q['cost'], t=t_before, gbest=float(q['gbest']), Pc=q['Pc'], Ps=q['Ps'], mu=q['mu'], sigma=q['sigma'],
+                         fes=int(q['fes']), log_index=int(q['log_index']), curve=list(q['curve'][:int(q['curve_len'])]))
+            N = ol.generation(S, G['attn'], G['mlp'], 10, 800, 16, lambda x, d, I=I: ob.func_true(I, x), I.optimum, -5., 5., normal=zn[b])
+            st = eng.read_state(b)
+            for k in ('parents', 'mu', 'sigma', 'Pc', 'Ps', 'cost'):
+                np.testing.assert_allclose(st[k], getattr(N, k), rtol=2e-5, atol=1e-7, err_msg=f'generation {t} lane {b} {k}')
+            assert int(st['fes']) == N.fes and int(st['log_index']) == N.log_index and bool(st['done']) == N.done
+    assert bool((eng.done != 0).all()) and int(eng.fes.max()) == 800 and all(len(c) == 51 for c in eng.cost_curves())
+    r = eng.episode_return().numpy()
+    assert np.all(r >= 0) and np.all(r < 1)
+    eng2 = mk(800)
+    eng2.init_population()
+    gb, ret, done = eng2.run_episode()
+    assert bool((done != 0).all()) and int(eng2.fes.max()) == 800
+    with pytest.raises(AssertionError):
+        eng2.set_params(G['attn'][:-1], G['mlp'])
