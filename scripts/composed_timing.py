@@ -24,13 +24,15 @@ pack = mp.InstancePack(probs)
 inst, _ = sweep.lane_table(len(probs), a.runs)
 maxFEs = 2000 * a.dim
 G = np.load(os.path.join(GOLD, 'agents2.npz'))
+GL = np.load(os.path.join(GOLD, 'les.npz'))                  # seeded LES network parameters (the backbone's action)
 dq = ma.load_reference_weights(ma.DEDQN_Net(), {k[6:]: G[k] for k in G.files if k.startswith('dedqn/')}).cuda().eval()
 qt = ma.RL_HPSDE_QTable(G['rl_hpsde_q']).cuda()           # the shipped agent's Q-table
 nq = ma.NRLPSO_QTable(G['qlpso_q']).cuda()                  # (no NRLPSO agent is shipped; any 4 x 4 table drives the backbone)
 small = sweep.lane_table(len(probs), 8)[0]                  # NRLPSO: [lanes, 100, 100, D] float64 distance temporaries, one particle per step
 for name, make in (('DEDQN', lambda: sweep.DEDQN_Sweep(pack, inst, dq, maxFEs, 50, seed=1)),
                    ('RL_HPSDE', lambda: sweep.RL_HPSDE_Sweep(pack, inst, ma.fuse(qt), maxFEs, 50, seed=1)),
-                   ('NRLPSO', lambda: sweep.NRLPSO_Sweep(pack, small, ma.fuse(nq), min(maxFEs, 3000), 50, seed=1))):
+                   ('NRLPSO', lambda: sweep.NRLPSO_Sweep(pack, small, ma.fuse(nq), min(maxFEs, 3000), 50, seed=1)),
+                   ('LES', lambda: sweep.LES_Sweep(pack, inst, {'attn': GL['attn'], 'mlp': GL['mlp']}, maxFEs, 50, seed=1))):
     sw = make()
     sw.run()                                               # warm-up
     torch.cuda.synchronize()
