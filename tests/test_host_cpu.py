@@ -1328,3 +1328,54 @@ def test_les_engine_host_logic_vs_oracle_and_golden_generations():
     assert bool((done != 0).all()) and int(eng2.fes.max()) == 800
     with pytest.raises(AssertionError):
         eng2.set_params(G['attn'][:-1], G['mlp'])
+
+
+def test_fused_policy_headers_with_random_weights():
+    """The host builds of the four policy headers against their torch modules for freshly initialised (random) weights and inputs: the packing
+    order and every layer are exercised with values that do not come from one trained checkpoint."""
+    import ctypes as C
+    import torch
+    from metabox_b200 import agent as ma
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    for seed in (1, 2, 3):
+        torch.manual_seed(seed)
+        g = np.random.RandomState(seed)
+        # GLEET attention actor
+        actor = ma.GLEET_Actor()
+        with torch.no_grad():
+            for p in actor.parameters():
+                p.mul_(0.7).sub_(0.2)                                     # the reference initialises the attention matrices in [0, 1): mix the signs
+        NP = int(g.choice([3, 50, 100]))
+        x = g.randn(2, NP, 27).astype(np.float32)
+        act, mu, sg, lg = _emul_forward(actor.pack().numpy(), x)
+        m2, s2, l2 = actor.distribution(torch.as_tensor(x))
+        np.testing.assert_allclose(lg, l2.detach().numpy(), rtol=5e-4, atol=5e-5)
+        np.testing.assert_allclose(mu, m2.detach().numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(sg, s2.detach().numpy(), rtol=2e-4, atol=2e-5)
+        # DE-DDQN Q-network
+        net = ma.DE_DDQN_Net()
+        L = _emul_lib('deddqn_policy')
+        w = np.ascontiguousarray(net.pack().numpy())
+        xs = np.ascontiguousarray(g.randn(13, 99).astype(np.float32))
+        a = np.empty(13, np.int32); q = np.empty((13, 4), np.float32)
+        assert L.ddq_host_forward(xs.ctypes.data_as(fp), w.ctypes.data_as(fp), a.ctypes.data_as(ip), q.ctypes.data_as(fp), 13) == 0
+        want = net(torch.as_tensor(xs)).detach().numpy()
+        np.testing.assert_allclose(q, want, rtol=1e-4, atol=1e-5)
+        np.testing.assert_array_equal(a, np.argmax(want, axis=1))
+        # RLEPSO actor
+        ra = ma.RLEPSO_Actor()
+        L = _emul_lib('rlepso_policy')
+        w = np.ascontiguousarray(ra.pack().numpy())
+        xs = np.ascontiguousarray(g.rand(9).astype(np.float32)); nz = np.ascontiguousarray(g.randn(9, 35).astype(np.float32))
+        act = np.empty((9, 35), np.float32)
+        assert L.rlp_host_forward(xs.ctypes.data_as(fp), w.ctypes.data_as(fp), nz.ctypes.data_as(fp), act.ctypes.data_as(fp), None, None, 9) == 0
+        np.testing.assert_allclose(act, ra(torch.as_tensor(xs)[:, None], noise=torch.as_tensor(nz)).numpy(), rtol=1e-5, atol=2e-6)
+        # RL_PSO policy network
+        dim = int(g.choice([10, 12, 30]))
+        rp = ma.RL_PSO_PolicyNet(dim)
+        L = _emul_lib('pso_policies')
+        w = np.ascontiguousarray(rp.pack().numpy())
+        xs = np.ascontiguousarray(g.randn(7, 2 * dim).astype(np.float32)); nz = np.ascontiguousarray((2 * g.randn(7)).astype(np.float32))
+        act = np.empty(7, np.float32)
+        assert L.rpp_host_forward(xs.ctypes.data_as(fp), w.ctypes.data_as(fp), nz.ctypes.data_as(fp), act.ctypes.data_as(fp), None, None, 7, 2 * dim) == 0
+        np.testing.assert_allclose(act, rp(torch.as_tensor(xs), noise=torch.as_tensor(nz)[:, None]).numpy()[:, 0], rtol=1e-5, atol=2e-6)
