@@ -105,7 +105,80 @@ def gleet_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoin
     return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=gens, seconds=time.perf_counter() - t0)
 
 
-ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout, 'gleet': gleet_rollout}
+def _table_action(q_table, state):
+    """Tabular agents (qlpso / rl_hpsde / nrlpso `__get_action`): sample from softmax(Q[state]) with np.random.choice like the reference."""
+    e = np.exp(q_table[state])
+    return int(np.random.choice(len(e), size=1, p=e / e.sum())[0])
+
+
+def dedqn_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One DEDQN rollout (dedqn_agent.py:87-96): greedy argmax of the 4 -> 10 -> 10 -> 3 Q-network; `max_gens` bounds the STEPS (200 charged
+    evaluations each).  `weights` = the reference state_dict of the Q-network."""
+    from . import dedqn as od
+    np.random.seed(run_seed)
+    cfg = od.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    w = {('.' + k): torch.as_tensor(np.asarray(v)) for k, v in weights.items()}
+    t0 = time.perf_counter()
+    S, state = od.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, od.NumpyTape(cfg.NP, dim, nc))
+    R, steps, done = 0., 0, False
+    while not done and (max_gens is None or steps < max_gens):
+        q = oag._mlp(w, '', torch.as_tensor(np.nan_to_num(state).astype(np.float32)), 3)
+        S, state, reward, done = od.update(cfg, S, int(torch.argmax(q)), ev, inst.optimum, inst.lb, inst.ub, od.NumpyTape(cfg.NP, dim, nc))
+        R += float(reward); steps += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=steps, seconds=time.perf_counter() - t0)
+
+
+def rl_hpsde_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One RL_HPSDE rollout (rl_hpsde_agent.py:62-72); `weights` = the [4, 4] Q-table."""
+    from . import rl_hpsde as oh
+    np.random.seed(run_seed)
+    cfg = oh.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    t0 = time.perf_counter()
+    S, state = oh.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, oh.NumpyTape(dim, nc))
+    R, gens, done = 0., 0, False
+    while not done and (max_gens is None or gens < max_gens):
+        S, state, reward, done = oh.update(cfg, S, _table_action(np.asarray(weights), state), ev, inst.optimum, inst.lb, inst.ub, oh.NumpyTape(dim, nc))
+        R += float(reward); gens += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=gens, seconds=time.perf_counter() - t0)
+
+
+def nrlpso_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One NRLPSO rollout; `weights` = a [4, 4] Q-table; `max_gens` bounds the single-particle STEPS."""
+    from . import nrlpso as on
+    np.random.seed(run_seed)
+    cfg = on.Config(dim=dim, maxFEs=maxFEs, n_logpoint=n_logpoint)
+    nc = ob.noise_draw_count(inst)
+    ev = lambda x, draws: ob.apply_noise(inst, ob.func_true(inst, x), draws=draws)
+    t0 = time.perf_counter()
+    S, state = on.init_population(cfg, ev, inst.optimum, inst.lb, inst.ub, on.NumpyTape(dim, nc))
+    R, steps, done = 0., 0, False
+    while not done and (max_gens is None or steps < max_gens):
+        S, state, reward, done = on.update(cfg, S, _table_action(np.asarray(weights), state), ev, inst.optimum, inst.lb, inst.ub, on.NumpyTape(dim, nc))
+        R += float(reward); steps += 1
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=R, gens=steps, seconds=time.perf_counter() - t0)
+
+
+def les_rollout(inst, dim, maxFEs, weights, run_seed, max_gens=None, n_logpoint=50):
+    """One LES episode; `weights` = {'attn': [68], 'mlp': [178]} (noise-free functions: the oracle's LES evaluates raw function values)."""
+    from . import les as ol
+    np.random.seed(run_seed)
+    ev = lambda x, draws: ob.func_true(inst, x)
+    t0 = time.perf_counter()
+    S = ol.init_population(dim, maxFEs, ev, inst.lb, inst.ub, n_logpoint)
+    gens, y0 = 0, None
+    while not S.done and (max_gens is None or gens < max_gens):
+        S = ol.generation(S, weights['attn'], weights['mlp'], dim, maxFEs, maxFEs // n_logpoint, ev, inst.optimum, inst.lb, inst.ub)
+        gens += 1
+        y0 = S.gbest if y0 is None else y0
+    return dict(cost=[float(c_) for c_ in S.curve], fes=S.fes, ret=float((y0 - S.gbest) / y0) if y0 else 0.0, gens=gens, seconds=time.perf_counter() - t0)
+
+
+ROLLOUTS = {'rlepso': rlepso_rollout, 'lde': lde_rollout, 'deddqn': deddqn_rollout, 'gleet': gleet_rollout, 'dedqn': dedqn_rollout,
+            'rl_hpsde': rl_hpsde_rollout, 'nrlpso': nrlpso_rollout, 'les': les_rollout}
 
 
 _SUITES = {}

@@ -645,3 +645,24 @@ def test_les_generations_match_reference():
             np.testing.assert_allclose(S.cost, G[f'{key}/cost'][t - 1], rtol=1e-9, err_msg=tag)
             np.testing.assert_allclose(S.gbest, float(G[f'{key}/gbest'][t - 1]), rtol=1e-12, err_msg=tag)
             assert S.fes == int(G[f'{key}/fes'][t - 1]) == 16 * (t + 1) and S.t == t and S.log_index == int(G[f'{key}/log_index'][t - 1]), tag
+
+
+def test_oracle_rollouts_of_the_composed_backbones_run_bounded_samples():
+    """CPU-arm rollouts (oracle/rollout.py) of DEDQN / RL_HPSDE / NRLPSO / LES with the shipped or golden policies: bounded samples run,
+    charge the reference's evaluation counts and are repeatable under a seed (what `bench.py --impl reference` times for the six native
+    workloads is available for the composed ones too)."""
+    from oracle import agents as oag, rollout as orr
+    A2, GL = load('agents2.npz'), load('les.npz')
+    tr, te = ob.make_suite('bbob', 10, 5.0)
+    inst = [i for i in tr + te if i.fid == 15][0]
+    w_dq = {k[len('dedqn/'):]: A2[k] for k in A2.files if k.startswith('dedqn/')}
+    r = orr.dedqn_rollout(inst, 10, 20000, w_dq, run_seed=1, max_gens=5)
+    assert r['gens'] == 5 and r['fes'] == 200 + 5 * 200
+    r = orr.rl_hpsde_rollout(inst, 10, 20000, A2['rl_hpsde_q'], run_seed=1, max_gens=3)
+    r2 = orr.rl_hpsde_rollout(inst, 10, 20000, A2['rl_hpsde_q'], run_seed=1, max_gens=3)
+    assert r['gens'] == 3 and r['fes'] > 381 + 3 * 201 and r['cost'] == r2['cost'] and r['fes'] == r2['fes']
+    r = orr.nrlpso_rollout(inst, 10, 20000, A2['qlpso_q'], run_seed=1, max_gens=120)
+    assert r['gens'] == 120 and 220 <= r['fes'] <= 100 + 3 * 120
+    r = orr.les_rollout(inst, 10, 20000, {'attn': GL['attn'], 'mlp': GL['mlp']}, run_seed=1, max_gens=10)
+    assert r['gens'] == 10 and r['fes'] == 16 * 11 and 0 <= r['ret'] < 1
+    assert set(orr.ROLLOUTS) >= {'rlepso', 'lde', 'deddqn', 'gleet', 'dedqn', 'rl_hpsde', 'nrlpso', 'les'}
