@@ -8,6 +8,10 @@ A *lane* is one (instance, run) rollout.  Lanes are independent (fresh seed, `pr
 as torch calls on the same stream, the pair captured once in a CUDA graph and replayed -- with no host
 synchronisation inside the loop except a done-poll every `poll` steps -> ONE all-gather of the result rows
 {curve[51], fes, return} at the end (NCCL over NVLink/NVSwitch).
+
+Sweeps of the six backbones with a fused step kernel (graph-captured): RLEPSO, LDE, DE_DDQN, GLEET, RL_PSO, QLPSO.  Sweeps of the composed
+backbones (library kernels + batched torch ops, run eagerly): DEDQN, RL_HPSDE, NRLPSO, L2L, LES.  A policy that has a single-kernel twin
+(`agent.fuse`) makes the environment step two library kernels.
 """
 from __future__ import annotations
 
