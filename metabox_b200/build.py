@@ -48,16 +48,19 @@ def _compile(src, verbose, extra=(), bdir=BUILD):
     return obj
 
 
-def build(force=False, verbose=False, profile=False):
+def build(force=False, verbose=False, profile=False, variant=None, defines=()):
     """profile=True builds the phase-instrumented variant libmbx_prof.so (-DMBX_PROFILE; measurement only, selected with
-    the MBX_LIB environment variable -- the product library is never instrumented)."""
+    the MBX_LIB environment variable -- the product library is never instrumented).  variant='name' with defines=['-DMBX_FDR_UNROLL=4', ...]
+    builds libmbx_<name>.so with those compile-time tuning knobs for A/B measurements (scripts/variant_sweep.sh); the product library is
+    always the default configuration."""
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    lib = LIB.replace('libmbx.so', 'libmbx_prof.so') if profile else LIB
-    bdir = BUILD + '_prof' if profile else BUILD
-    if not profile and not force and not needs_build():
+    tag = 'prof' if profile else variant
+    lib = LIB.replace('libmbx.so', f'libmbx_{tag}.so') if tag else LIB
+    bdir = BUILD + f'_{tag}' if tag else BUILD
+    if not tag and not force and not needs_build():
         return LIB
     os.makedirs(bdir, exist_ok=True)
-    extra = ['-DMBX_PROFILE=1'] if profile else []
+    extra = (['-DMBX_PROFILE=1'] if profile else []) + list(defines)
     with cf.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose, extra, bdir), srcs))
     cmd = [NVCC, '-shared', '-o', lib] + objs + ['-lcudart']
@@ -68,4 +71,6 @@ def build(force=False, verbose=False, profile=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, profile='--profile' in sys.argv))
+    var = sys.argv[sys.argv.index('--variant') + 1] if '--variant' in sys.argv else None
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, profile='--profile' in sys.argv, variant=var,
+                defines=[a for a in sys.argv[1:] if a.startswith('-D')]))

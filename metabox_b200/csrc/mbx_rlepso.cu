@@ -111,6 +111,15 @@ __device__ __forceinline__ bool log_and_done(const MbxRunConfig& cfg, bool has_o
 // FDR pass 1: float32 screening (see the comment at the call site).  Work item = (pair of 2-rank blocks {m, nb-1-m},
 // pair of dimensions): every item scans ~NP candidates.  Sign convention: a = pf[s]-pf[r] <= 0; the carried best is
 // (nab, bb) = (-a_best, q_best); candidate wins iff  a*bb + nab*q < 0.
+// Compile-time tuning knobs (defaults = the measured configuration; scripts/variant_sweep.sh builds and benches alternatives):
+#ifndef MBX_FDR_UNROLL
+#define MBX_FDR_UNROLL 2            // unroll factor of the FDR candidate scan
+#endif
+#ifndef MBX_RLEPSO_MIN_CTAS
+#define MBX_RLEPSO_MIN_CTAS 4       // __launch_bounds__ minimum CTAs per SM of the step kernel (4 -> 128 registers)
+#endif
+#define MBX_PRAGMA_(x) _Pragma(#x)
+#define MBX_UNROLL(n) MBX_PRAGMA_(unroll n)
 #define FDR_TAU 1e-6f
 #define FDR_TINY 1e-35f
 #define FDR_NEAR 2e-4f
@@ -151,7 +160,7 @@ __device__ __forceinline__ void fdr_screen(const int NP, const int tid, const fl
             const float2 npxb = make_float2(-pxb.x, -pxb.y), npfb = make_float2(-pfb.x, -pfb.y);
             FdrChain A{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), ra, ra, false};      // start from j = i (ratio 0)
             FdrChain B{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), rb, rb, false};
-#pragma unroll 2
+            MBX_UNROLL(MBX_FDR_UNROLL)
             for (int s = 0; s < ra; ++s) {
                 const float2 x2 = *reinterpret_cast<const float2*>(spx + s * D + d), s2 = spf2[s];
                 fdr_visit(A, s2, x2, npfa, npxa, s);
@@ -220,7 +229,7 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, 4)
+__global__ void __launch_bounds__(MBX_NT, MBX_RLEPSO_MIN_CTAS)
 rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                    MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, const double* __restrict__ pci,
                    const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
