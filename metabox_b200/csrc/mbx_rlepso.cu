@@ -118,6 +118,9 @@ __device__ __forceinline__ bool log_and_done(const MbxRunConfig& cfg, bool has_o
 #ifndef MBX_RLEPSO_MIN_CTAS
 #define MBX_RLEPSO_MIN_CTAS 4       // __launch_bounds__ minimum CTAs per SM of the step kernel (4 -> 128 registers)
 #endif
+#ifndef MBX_RLEPSO_P2_CH
+#define MBX_RLEPSO_P2_CH 12         // elements per thread whose x / v loads are issued ahead in the velocity phase
+#endif
 #define MBX_PRAGMA_(x) _Pragma(#x)
 #define MBX_UNROLL(n) MBX_PRAGMA_(unroll n)
 #define FDR_TAU 1e-6f
@@ -336,7 +339,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     // ---- P2: velocity + position, element-wise over (i,d)   (:76-95, :105-109, :179-195) ---------------
     // the loads of x and v for a chunk of P2_CH elements are issued before their first use: one exposed DRAM latency per
     // chunk instead of one per element
-    constexpr int P2_CH = 12;
+    constexpr int P2_CH = MBX_RLEPSO_P2_CH;
 #pragma unroll 1
     for (int k0 = 0; k0 * MBX_NT < NP * D; k0 += P2_CH) {
     float xr[P2_CH], vr[P2_CH];

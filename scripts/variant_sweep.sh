@@ -1,9 +1,9 @@
-# A/B of compile-time tuning knobs of the headline kernel (metabox_b200/csrc/mbx_rlepso.cu: MBX_FDR_UNROLL, MBX_RLEPSO_MIN_CTAS).
+# A/B of compile-time tuning knobs of the headline kernel (metabox_b200/csrc/mbx_rlepso.cu: MBX_FDR_UNROLL, MBX_RLEPSO_MIN_CTAS, MBX_RLEPSO_P2_CH).
 #   step 1 (build container, no GPU):   bash scripts/variant_sweep.sh build     -> metabox_b200/csrc/libmbx_<name>.so (travel with gpurun)
 #   step 2 (GPU box):                   bash scripts/variant_sweep.sh bench     -> gpurun_out/variants.txt
 # Every variant must pass the bit-exact RLEPSO device tests before its number counts (the `bench` step runs them first).
 set -e
-VARIANTS="fdr1:-DMBX_FDR_UNROLL=1 fdr4:-DMBX_FDR_UNROLL=4 ctas3:-DMBX_RLEPSO_MIN_CTAS=3 fdr4ctas3:-DMBX_FDR_UNROLL=4,-DMBX_RLEPSO_MIN_CTAS=3"
+VARIANTS="fdr1:-DMBX_FDR_UNROLL=1 fdr4:-DMBX_FDR_UNROLL=4 ctas3:-DMBX_RLEPSO_MIN_CTAS=3 fdr4ctas3:-DMBX_FDR_UNROLL=4,-DMBX_RLEPSO_MIN_CTAS=3 p2ch6:-DMBX_RLEPSO_P2_CH=6 p2ch24:-DMBX_RLEPSO_P2_CH=24"
 if [ "$1" = "build" ]; then
   for v in $VARIANTS; do
     name=${v%%:*}; defs=$(echo ${v#*:} | tr ',' ' ')
