@@ -229,7 +229,10 @@ deddqn_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, 8)
+#ifndef MBX_DEDDQN_MIN_CTAS
+#define MBX_DEDDQN_MIN_CTAS 8        // compile-time knob: minimum CTAs per SM of the step kernel (A/B builds: python -m metabox_b200.build --variant)
+#endif
+__global__ void __launch_bounds__(MBX_NT, MBX_DEDDQN_MIN_CTAS)
 deddqn_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                    MbxRunConfig cfg, MbxDdqnState S, MbxDdqnTape T, const int32_t* __restrict__ action,
                    float* __restrict__ feature, float* __restrict__ reward, float* __restrict__ dbg) {

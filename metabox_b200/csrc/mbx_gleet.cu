@@ -183,7 +183,10 @@ gleet_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, 4)
+#ifndef MBX_GLEET_MIN_CTAS
+#define MBX_GLEET_MIN_CTAS 4        // compile-time knob: minimum CTAs per SM of the step kernel (A/B builds: python -m metabox_b200.build --variant)
+#endif
+__global__ void __launch_bounds__(MBX_NT, MBX_GLEET_MIN_CTAS)
 gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                   MbxRunConfig cfg, MbxGleetState S, MbxGleetTape T, const float* __restrict__ action, float* __restrict__ state,
                   float* __restrict__ reward) {

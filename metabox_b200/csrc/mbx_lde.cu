@@ -192,7 +192,10 @@ lde_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
 
 // =====================================================================================================
 template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, 4)
+#ifndef MBX_LDE_MIN_CTAS
+#define MBX_LDE_MIN_CTAS 4        // compile-time knob: minimum CTAs per SM of the step kernel (A/B builds: python -m metabox_b200.build --variant)
+#endif
+__global__ void __launch_bounds__(MBX_NT, MBX_LDE_MIN_CTAS)
 lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                 MbxRunConfig cfg, MbxLdeState S, MbxLdeTape T, const float* __restrict__ action, float* __restrict__ feature,
                 float* __restrict__ reward, float* __restrict__ dbg) {
