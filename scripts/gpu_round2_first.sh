@@ -13,3 +13,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:dedd
 ls -la gpurun_out | tail -8
 timeout 600 python scripts/train_timing.py > gpurun_out/r2a_train_timing.txt 2>&1; cat gpurun_out/r2a_train_timing.txt
 timeout 600 python scripts/composed_timing.py > gpurun_out/r2a_composed_timing.txt 2>&1; cat gpurun_out/r2a_composed_timing.txt
+# A/B of the packed-f32x2 variant of the GLEET policy kernel (build it first in the build container:
+#   python -m metabox_b200.build --variant glp2 -DGLP_PACKED_F32X2 ): same timing script, selected through MBX_LIB
+if [ -f metabox_b200/csrc/libmbx_glp2.so ]; then MBX_LIB=$PWD/metabox_b200/csrc/libmbx_glp2.so timeout 200 python scripts/policy_timing.py --only gleet > gpurun_out/r2a_policy_timing_glp2.txt 2>&1; cat gpurun_out/r2a_policy_timing_glp2.txt; fi

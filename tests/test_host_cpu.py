@@ -204,17 +204,18 @@ def test_gleet_and_rl_pso_policies_match_reference_kats():
         assert a.tolist() == [min(w, 3) for w in want] and G[key].shape == (4, 4)
 
 
-def _emul_lib(name='gleet_policy'):
+def _emul_lib(name='gleet_policy', defines=()):
     """g++ build of tests/emul/<name>_host.cpp (the device header compiled for the host); built once per session in a temp dir."""
     import ctypes as C
     import subprocess
     import tempfile
     cache = _emul_lib.__dict__.setdefault('cache', {})
-    if name not in cache:
+    key = (name,) + tuple(defines)
+    if key not in cache:
         d = tempfile.mkdtemp(prefix='mbx_emul_')
         so = os.path.join(d, name + '_host.so')
         src = os.path.join(os.path.dirname(__file__), 'emul', name + '_host.cpp')
-        subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', src, '-o', so], check=True)
+        subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-ffp-contract=off', *defines, src, '-o', so], check=True)
         L = C.CDLL(so)
         fp = C.POINTER(C.c_float)
         if name == 'gleet_policy':
@@ -231,13 +232,13 @@ def _emul_lib(name='gleet_policy'):
         else:
             L.ddq_host_forward.restype = C.c_int
             L.ddq_host_forward.argtypes = [fp, fp, C.POINTER(C.c_int32), fp, C.c_int]
-        cache[name] = L
-    return cache[name]
+        cache[key] = L
+    return cache[key]
 
 
-def _emul_forward(w, x, noise=None):
+def _emul_forward(w, x, noise=None, defines=()):
     import ctypes as C
-    L = _emul_lib()
+    L = _emul_lib('gleet_policy', defines)
     fp = C.POINTER(C.c_float)
     x = np.ascontiguousarray(x, dtype=np.float32); w = np.ascontiguousarray(w, dtype=np.float32)
     B, NP, _ = x.shape
@@ -274,6 +275,13 @@ def test_fused_gleet_policy_arithmetic_on_the_host_matches_the_reference():
             np.testing.assert_allclose(act, want, rtol=1e-4, atol=2e-5)
             assert act.min() >= 0 and act.max() <= 1
             np.testing.assert_allclose(_emul_forward(w, x)[0], np.clip(mu, 0, 1), rtol=0, atol=0)        # null noise -> the mean action
+    # the A/B variant with packed f32x2 arithmetic sums the head dot products in another order: same answers to rounding
+    actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet0/'))
+    x = G['gleet0_kat/r/x']
+    act, mu, sg, lg = _emul_forward(actor.pack().numpy(), x, defines=('-DGLP_PACKED_F32X2',))
+    np.testing.assert_allclose(lg, G['gleet0_kat/r/logits'], rtol=2e-4, atol=3e-5)
+    np.testing.assert_allclose(mu, G['gleet0_kat/r/mu'][..., 0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sg, G['gleet0_kat/r/sigma'][..., 0], rtol=1e-4, atol=1e-5)
     # edge swarm sizes (1 particle: the unbiased variance has 15 degrees of freedom; 128 = the kernel's maximum)
     actor = ma.load_reference_weights(ma.GLEET_Actor(), sub('gleet0/'))
     for NP in (1, 2, 37, 128):
