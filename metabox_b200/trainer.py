@@ -340,12 +340,19 @@ class GLEET_Trainer(_PPOTrainer):
     actor + critic (lr 1e-4; the reference builds an ExponentialLR scheduler but never steps it), loss = baseline + reinforce in one
     backward pass, gradient-norm clipping at 0.1 per parameter group (actor, critic) after the all-reduce (`clip_grad_norms`, :472-487)."""
 
-    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None):
+    def __init__(self, config, problems, actor=None, critic=None, seed=0, device=None, fused_collection=False):
+        """`fused_collection=True`: trajectories are sampled by the single-kernel actor (`agent.GLEET_FusedActor`: action, mu, sigma in one
+        launch per generation, log-probability from those) instead of the torch module; the packed weights are refreshed after every
+        optimiser step.  The update epochs always differentiate through the torch module."""
         from .agent import GLEET_Actor, GLEET_Critic
         self._setup(config, problems, seed, device)
         self.actor = (actor if actor is not None else GLEET_Actor()).to(self.device)
         self.critic = (critic if critic is not None else GLEET_Critic()).to(self.device)
         self.optimizer = torch.optim.Adam([{'params': self.actor.parameters(), 'lr': GLEET_LR}, {'params': self.critic.parameters(), 'lr': GLEET_LR}])
+        self._fused = None
+        if fused_collection:
+            from .agent import GLEET_FusedActor
+            self._fused = GLEET_FusedActor(self.actor)
 
     def _params(self):
         return list(self.actor.parameters()) + list(self.critic.parameters())
@@ -363,6 +370,9 @@ class GLEET_Trainer(_PPOTrainer):
         return eng.feature.clone()
 
     def _sample(self, x):
+        if self._fused is not None:
+            a, mu, sigma, _ = self._fused(x, noise=torch.randn(x.shape[:2], device=x.device), outputs=True)
+            return a, torch.distributions.Normal(mu, sigma).log_prob(a).sum(-1)
         a = self.actor(x)
         return a, self.actor.log_prob(x, a)
 
@@ -376,3 +386,5 @@ class GLEET_Trainer(_PPOTrainer):
         for group in self.optimizer.param_groups:
             torch.nn.utils.clip_grad_norm_(group['params'], GLEET_MAX_GRAD_NORM, norm_type=2)
         self.optimizer.step()
+        if self._fused is not None:
+            self._fused.refresh()

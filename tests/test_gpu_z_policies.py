@@ -695,3 +695,27 @@ def test_les_engine_on_the_device_replays_reference_generations_sweep_and_dropin
     assert env.reset() is None
     gb, ret, is_end, info = env.step({'attn': G['attn'], 'mlp': G['mlp']})
     assert is_end and opt.FEs == 1600 and 0 <= ret < 1 and len(opt.cost) == 51 and abs(gb - opt.cost[-1]) <= 1e-5 * abs(gb) and info == {}
+
+
+@pending_first_device_run
+def test_gleet_trainer_with_fused_collection():
+    """Trajectories sampled by the single-kernel actor: the stored log-probabilities equal the torch module's for the same (state, action),
+    the packed weights follow the optimiser steps."""
+    import argparse
+    import torch
+    from metabox_b200 import agent as ma, problem as mp, trainer as mt
+    from metabox_b200.optimizer import GLEET_Engine
+    cfg = argparse.Namespace(dim=10, maxFEs=2500, n_logpoint=50, log_interval=50)
+    tr, te = mp.BBOB_Dataset.get_datasets('bbob', 10, 5)
+    W, _ = _weights('gleet0')
+    T = mt.GLEET_Trainer(cfg, tr.data, actor=ma.load_reference_weights(ma.GLEET_Actor(), W), seed=5, fused_collection=True)
+    eng = GLEET_Engine(T.pack, np.arange(3, dtype=np.int32), 2500, 50, 50, seed=1)
+    eng.init_population()
+    seg = T.collect_segment(eng)
+    with torch.no_grad():
+        want = mt._GleetActorHead(T.actor).log_prob(seg['states'], seg['actions'])
+    np.testing.assert_allclose(seg['logp'].cpu().numpy(), want.cpu().numpy(), rtol=2e-4, atol=2e-3)
+    packed0 = T._fused.packed.clone()
+    info = T.train_episodes([0, 1])
+    assert info['learn_steps'] == 9 and not torch.equal(T._fused.packed, packed0)
+    assert torch.equal(T._fused.packed, T.actor.pack())
