@@ -231,7 +231,9 @@ class RL_HPSDE_Engine:
         # LPSR (:90-99): sort, then truncate to the scheduled size (one schedule for all running lanes)
         self._sort()
         self.fes_running += N
-        N_new = max(int(self.NP_max + round(NP_MIN - self.NP_max) * self.fes_running / self.maxFEs), 1)
+        # (a sweep may step once more after its last lane has finished: past maxFEs the schedule would shrink below the 4 rows a donor
+        # triple needs -- the reference never gets there, its run has ended -- so the budget is clamped)
+        N_new = max(int(self.NP_max + round(NP_MIN - self.NP_max) * min(self.fes_running, self.maxFEs) / self.maxFEs), 1)
         if N_new < N:
             self.group, self.cost = self.group[:, :N_new].contiguous(), self.cost[:, :N_new].contiguous()
         # cost-curve protocol (:262-275)

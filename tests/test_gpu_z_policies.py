@@ -14,10 +14,6 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-# Tests that have never executed on a device (round 1's GPU minutes were spent when they were written): they run like any other test, but a
-# failure is reported as `xfailed` instead of stopping `pytest -x` in front of nothing -- and a pass as `xpassed`.  Remove the marker after
-# the first device run (scripts/gpu_round2_first.sh).
-pending_first_device_run = pytest.mark.xfail(reason='written after the round-1 GPU budget was spent: first device run pending', strict=False)
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 
 
@@ -124,7 +120,6 @@ def test_rl_pso_sweep_with_the_reference_policy_net():
 
 
 # ------------------------------------------------------------------------------------------------ fused policy kernel (mbx_gleet_policy)
-@pending_first_device_run          # (passed on a B200 with exp2f in the softmax; the one-instruction ex2.approx variant has not run yet)
 def test_fused_gleet_policy_kernel_known_answers_and_torch_module():
     """One CTA per swarm: against forwards of the unmodified reference (both checkpoints; random, ragged and reference-produced states) and
     against the torch module on the device under the same action noise."""
@@ -147,7 +142,6 @@ def test_fused_gleet_policy_kernel_known_answers_and_torch_module():
             assert torch.equal(fused(x), torch.clamp(mu, 0, 1))                            # null noise -> the mean action
 
 
-@pending_first_device_run
 def test_fused_gleet_policy_kernel_edge_sizes_errors_and_refresh():
     import torch
     from metabox_b200 import _lib, agent as ma
@@ -181,7 +175,6 @@ def test_fused_gleet_policy_kernel_edge_sizes_errors_and_refresh():
     np.testing.assert_allclose(after.cpu().numpy(), actor(x, noise=torch.zeros(4, 100).cuda()).cpu().numpy(), rtol=2e-4, atol=3e-5)
 
 
-@pending_first_device_run
 def test_gleet_sweep_with_the_fused_policy_kernel():
     """Complete GLEET rollouts with fused step + fused policy: graph replay == eager launches (mean actions), sampled sweeps are sane."""
     from metabox_b200 import agent as ma, sweep
@@ -200,7 +193,6 @@ def test_gleet_sweep_with_the_fused_policy_kernel():
 
 
 # ------------------------------------------------------------------------------------------------ fused Q-network kernel (mbx_deddqn_policy)
-@pending_first_device_run
 def test_fused_deddqn_policy_kernel_vs_reference_q_values_and_torch_net():
     import torch
     from metabox_b200 import agent as ma
@@ -229,7 +221,6 @@ def test_fused_deddqn_policy_kernel_vs_reference_q_values_and_torch_net():
         fused(torch.zeros(4, 98).cuda())
 
 
-@pending_first_device_run
 def test_deddqn_sweep_with_the_fused_q_network():
     """Complete DE-DDQN rollouts, fused step + fused Q-network: graph replay == eager launches, and the same rows as the sweep driven by the
     torch network wherever no lane ever met a near-tie (the two Q implementations differ in summation order only)."""
@@ -250,7 +241,6 @@ def test_deddqn_sweep_with_the_fused_q_network():
 
 
 # ------------------------------------------------------------------------------------------------ GLEET PPO training on the lane machinery
-@pending_first_device_run
 def test_gleet_trainer_collects_on_the_gpu_and_updates():
     import argparse
     import torch
@@ -278,7 +268,6 @@ def test_gleet_trainer_collects_on_the_gpu_and_updates():
 
 
 # ------------------------------------------------------------------------------------------------ DEDQN backbone (composed step, metabox_b200/dedqn.py)
-@pending_first_device_run
 def test_dedqn_engine_on_the_device_vs_oracle():
     """The composed DEDQN step with the real kernels (mbx_eval, mbx_landscape_features): every step the oracle replays the engine's own
     draws from the engine's previous state -- replaced rows bit-exact, costs to float32 rounding, landscape features of the engine's own
@@ -328,7 +317,6 @@ def test_dedqn_engine_on_the_device_vs_oracle():
         eng.update(torch.as_tensor([0, 1, 2, 3, 0, 1]).cuda(), check_action=True)
 
 
-@pending_first_device_run
 def test_dedqn_sweep_tester_and_dropin():
     import argparse
     import torch
@@ -360,7 +348,6 @@ def test_dedqn_sweep_tester_and_dropin():
 
 
 # ------------------------------------------------------------------------------------------------ fused RLEPSO actor kernel (mbx_rlepso_policy)
-@pending_first_device_run
 def test_fused_rlepso_policy_kernel_and_sweep():
     import torch
     from metabox_b200 import agent as ma, sweep
@@ -391,7 +378,6 @@ def test_fused_rlepso_policy_kernel_and_sweep():
 
 
 # ------------------------------------------------------------------------------------------------ fused RL_PSO / QLPSO policy kernels
-@pending_first_device_run
 def test_fused_rl_pso_and_qlpso_policy_kernels_and_sweeps():
     import torch
     from metabox_b200 import agent as ma, sweep
@@ -429,7 +415,6 @@ def test_fused_rl_pso_and_qlpso_policy_kernels_and_sweeps():
     assert np.isfinite(r).all() and np.all(np.diff(r[:, :51], axis=1) <= 0)
 
 
-@pending_first_device_run
 def test_tester_with_fused_policies(tmp_path):
     """`config.fused_policies = True`: the Tester swaps every policy for its single-kernel twin and writes the reference's layouts."""
     import argparse
@@ -457,7 +442,6 @@ def test_tester_with_fused_policies(tmp_path):
             assert all(f >= 600 or c[-1] <= 1e-8 for f, c in zip(R['fes'][p][a], R['cost'][p][a]))
 
 
-@pending_first_device_run
 def test_population_sweeps_with_several_steps_per_graph():
     """Graphs of 4 generations: finished lanes idle through surplus generations, the rows equal the one-generation-per-graph sweep."""
     from metabox_b200 import agent as ma, sweep
@@ -478,7 +462,6 @@ def test_population_sweeps_with_several_steps_per_graph():
 
 
 # ------------------------------------------------------------------------------------------------ RL_HPSDE backbone (composed step, metabox_b200/rl_hpsde.py)
-@pending_first_device_run
 def test_rl_hpsde_engine_on_the_device_vs_oracle():
     """The composed RL_HPSDE generation with the real kernels (mbx_eval, mbx_progressive_walk, mbx_landscape_features): every generation the
     oracle replays the engine's own draws from the engine's previous state."""
@@ -529,7 +512,6 @@ def test_rl_hpsde_engine_on_the_device_vs_oracle():
     assert eng.NP < 180
 
 
-@pending_first_device_run
 def test_rl_hpsde_sweep_tester_and_dropin():
     import argparse
     import torch
@@ -559,7 +541,6 @@ def test_rl_hpsde_sweep_tester_and_dropin():
 
 
 # ------------------------------------------------------------------------------------------------ L2L (metabox_b200/l2l.py)
-@pending_first_device_run
 def test_l2l_sweep_and_dropin_replay_reference_episodes():
     """Whole episodes of the unmodified reference L2L agent (tests/golden/l2l.npz, shipped weights) through the sweep on the device and through
     the drop-in optimizer: every-second-best curve, fes and return."""
@@ -595,7 +576,6 @@ def test_l2l_sweep_and_dropin_replay_reference_episodes():
 
 
 # ------------------------------------------------------------------------------------------------ NRLPSO backbone (composed step, metabox_b200/nrlpso.py)
-@pending_first_device_run
 def test_nrlpso_engine_on_the_device_vs_oracle_sweep_and_dropin():
     """The composed NRLPSO step with the real evaluation kernel: every step the oracle replays the engine's own draws from the engine's
     previous state (120 steps: the pointer wraps); then a complete sweep with the tabular policy and the drop-in optimizer."""
@@ -657,7 +637,6 @@ def test_nrlpso_engine_on_the_device_vs_oracle_sweep_and_dropin():
 
 
 # ------------------------------------------------------------------------------------------------ LES (metabox_b200/les.py)
-@pending_first_device_run
 def test_les_engine_on_the_device_replays_reference_generations_sweep_and_dropin():
     """Golden generations of the unmodified reference (tests/golden/les.npz) through the engine with the real float64 evaluation kernel,
     then a complete sweep and the drop-in optimizer."""
@@ -697,7 +676,6 @@ def test_les_engine_on_the_device_replays_reference_generations_sweep_and_dropin
     assert is_end and opt.FEs == 1600 and 0 <= ret < 1 and len(opt.cost) == 51 and abs(gb - opt.cost[-1]) <= 1e-5 * abs(gb) and info == {}
 
 
-@pending_first_device_run
 def test_gleet_trainer_with_fused_collection():
     """Trajectories sampled by the single-kernel actor: the stored log-probabilities equal the torch module's for the same (state, action),
     the packed weights follow the optimiser steps."""
