@@ -54,14 +54,14 @@ def parse():
     ap.add_argument('--workload', default='rlepso', choices=sorted(WORKLOADS),
                     help='rlepso = the headline (BASELINE.json metric); lde / deddqn = the DE-family configs C4 / C3; '
                          'gleet = the GLEET backbone (SURVEY 8f N1), policy chosen by --gleet-policy')
-    ap.add_argument('--gleet-policy', default='actor', choices=['actor', 'fused', 'stand-in'],
+    ap.add_argument('--gleet-policy', default='fused', choices=['actor', 'fused', 'stand-in'],
                     help="actor = the reference's attention actor with the weights of its shipped checkpoint 20 (agent.GLEET_Actor, torch); "
                          'fused = the same actor as ONE CUDA kernel per generation (agent.GLEET_FusedActor -> mbx_gleet_policy); '
                          'stand-in = a per-particle MLP 27->64->1 (what the r1g / r1h gleet lines under profiles/ were measured with)')
-    ap.add_argument('--fused-policy', action='store_true',
-                    help='rlepso: the actor as ONE kernel per generation (agent.RLEPSO_FusedActor -> mbx_rlepso_policy); '
-                         'deddqn: the Q-network + argmax as ONE kernel per step (agent.DE_DDQN_FusedNet -> mbx_deddqn_policy); '
-                         'gleet: same as --gleet-policy fused')
+    ap.add_argument('--torch-policy', action='store_true',
+                    help='keep the policy a torch module between the step kernels (round-1 path).  Default: the single-kernel twin of the '
+                         'policy -- rlepso: agent.RLEPSO_FusedActor -> mbx_rlepso_policy; deddqn: Q-network + argmax, '
+                         'agent.DE_DDQN_FusedNet -> mbx_deddqn_policy; gleet: agent.GLEET_FusedActor -> mbx_gleet_policy')
     ap.add_argument('--steps-per-graph', type=int, default=None,
                     help='environment steps captured per CUDA graph (default: 1 for the population backbones, 10 for deddqn); more steps = fewer '
                          'graph launches, finished lanes idle through the surplus steps')
@@ -195,8 +195,8 @@ def run_reference_unmodified(args):
     import ref_runner as rr
     W = WORKLOADS[args.workload]
     algo, problem, difficulty, subset, max_steps, note = REF_RUNS[args.workload]
-    if args.cpu_gens is not None and max_steps is not None:
-        max_steps = args.cpu_gens
+    if args.cpu_gens is not None:                                   # explicit bound: the first --cpu-gens environment steps of each rollout
+        max_steps, note = args.cpu_gens, f'first {args.cpu_gens} environment steps of each rollout'
     cores = os.cpu_count() or 1
     pool = rr.make_pool(cores, algo, problem, DIM, difficulty)
     names = rr.problem_names(algo, problem, DIM, difficulty)       # train + test order of the reference's dataset factory
@@ -358,13 +358,13 @@ def main():
     tr, te = mp.BBOB_Dataset.get_datasets(W['suit'], DIM, 5, difficulty='difficult' if W['subset'] == 'difficult-test' else 'easy')
     problems = te.data if W['subset'] == 'difficult-test' else tr.data + te.data
     pack = mp.InstancePack(problems, dev)                      # also computes every optimum on the GPU
-    if args.fused_policy and args.workload == 'gleet':
-        args.gleet_policy = 'fused'
+    if args.torch_policy and args.workload == 'gleet' and args.gleet_policy == 'fused':
+        args.gleet_policy = 'actor'
     net, wsrc = build_policy(args.workload, dev, NP, args.gleet_policy)
-    if args.fused_policy and args.workload == 'deddqn':
+    if not args.torch_policy and args.workload == 'deddqn':
         from metabox_b200 import agent as magent
         net, wsrc = magent.DE_DDQN_FusedNet(net), wsrc + ', fused Q-network kernel (mbx_deddqn_policy)'
-    if args.fused_policy and args.workload == 'rlepso':
+    if not args.torch_policy and args.workload == 'rlepso':
         from metabox_b200 import agent as magent
         net, wsrc = magent.RLEPSO_FusedActor(net), wsrc + ', fused actor kernel (mbx_rlepso_policy)'
     inst, run = msweep.lane_table(len(problems), args.runs)

@@ -125,7 +125,9 @@ class Tester:
     log_interval, upperbound, test_log_dir, agent_for_cp (names out of RLEPSO_Agent / LDE_Agent / DE_DDQN_Agent / GLEET_Agent /
     RL_PSO_Agent / QLPSO_Agent),
     t_optimizer_for_cp (only 'Random_search' has a B200 path).  `policies`: {agent name: torch module on the GPU}.
-    `config.fused_policies = True` swaps every policy that has a single-kernel twin in the library for it (`agent.fuse`)."""
+    Every policy that has a single-kernel twin in the library is swapped for it (`agent.fuse`: same weights, one launch per step, validated
+    against the torch modules and the reference's known answers in tests/test_gpu_z_policies.py); `config.fused_policies = False` keeps the
+    torch modules."""
 
     def __init__(self, config, policies, device=None, data_folder=None):
         import torch
@@ -134,7 +136,7 @@ class Tester:
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.train_set, self.test_set = construct_problem_set(config, data_folder)
         self.policies = dict(policies)
-        if getattr(config, 'fused_policies', False):
+        if getattr(config, 'fused_policies', True):
             from .agent import fuse
             self.policies = {k: fuse(v) for k, v in self.policies.items()}
         for name in getattr(config, 'agent_for_cp', list(self.policies)):
@@ -239,6 +241,9 @@ def rollout(config, checkpoints, n_runs=N_RUNS_ROLLOUT, seed=0, stripes=2, devic
             for key in R:
                 R[key].setdefault(str(p), {})[name] = []
         for ck, net in enumerate(nets):
+            if getattr(config, 'fused_policies', True):
+                from .agent import fuse
+                net = fuse(net)
             rows, _ = sweep_rows(AGENT_ALGO[name], pack, len(probs), n_runs, net, config, seed + 7919 * ck, stripes)
             tmp = rows_to_results(rows, probs, n_runs, name, {'cost': {}, 'fes': {}, 'return': {}})
             for p in probs:

@@ -882,24 +882,49 @@ def test_qlpso_qtable_policy_on_cpu():
 
 
 # ----------------------------------------------------------------------------------------- bench.py contract (CPU side)
-@pytest.mark.parametrize('workload', ['rlepso', 'gleet'])
-def test_bench_reference_arm_prints_one_contract_line(workload):
-    """`bench.py --impl reference` = the oracle port on the host cores, a bounded sample: ONE JSON line with the contract's keys."""
+@pytest.mark.parametrize('workload,kind', [('rlepso', 'port'), ('gleet', 'port'), ('rlepso', 'reference'), ('deddqn', 'reference')])
+def test_bench_reference_arm_prints_one_contract_line(workload, kind):
+    """`bench.py --impl reference` on the host cores, a bounded sample: ONE JSON line with the contract's keys.  kind "reference" = the
+    unmodified reference staged under baseline/_ref (git-ignored; staged by __graft_entry__.build() in the build container and shipped
+    with the snapshot); kind "port" = the oracle restatement."""
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if kind == 'reference' and not os.path.exists(os.path.join(root, 'baseline', '_ref', 'MANIFEST.json')):
+        pytest.skip('baseline/_ref is not staged here')
     r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-gens', '2',
-                        '--workload', workload], capture_output=True, text=True, timeout=600, cwd=root)
+                        '--workload', workload, '--cpu-kind', kind], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['higher_is_better'] is True and d['vs_baseline'] is None
     assert d['metric'] == 'candidate evals/sec on BBOB dim=30 pop=100' and d['value'] > 0 and d['gpu_launches'] == 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['cpu_baseline']['kind'] == kind and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['cpu_baseline']['evals_per_s_per_core'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and 'model' not in d['config']
+
+
+def test_staged_reference_is_byte_identical_to_its_manifest():
+    """baseline/_ref (when present): every staged python source hashes to what the staging script recorded from /root/reference, and
+    nothing under metabox_b200/ imports the staged reference or the oracle."""
+    import hashlib
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    man = os.path.join(root, 'baseline', '_ref', 'MANIFEST.json')
+    if os.path.exists(man):
+        M = json.load(open(man))['python_sources_sha256']
+        assert len(M) > 60
+        for rel, sha in M.items():
+            with open(os.path.join(root, 'baseline', '_ref', 'src', rel), 'rb') as f:
+                assert hashlib.sha256(f.read()).hexdigest() == sha, rel
+    for dirpath, _, files in os.walk(os.path.join(root, 'metabox_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'ref_runner' not in src and 'baseline/_ref' not in src and 'import oracle' not in src and 'from oracle' not in src, f
 
 
 def test_bench_product_arm_refuses_to_run_without_a_gpu():
