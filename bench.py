@@ -385,7 +385,7 @@ def main():
 
     def one_sweep(sw):
         res = sw.run()
-        rows = msweep.gather_results(res, world)               # the single collective of the sweep
+        rows = msweep.gather_results(res, world, n_max=n_local)   # the single collective of the sweep
         return res, rows
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
@@ -432,7 +432,7 @@ def main():
         for lo, hi, eng in sweep_engines(sw):                   # lane table of every stripe
             eng.lane_inst.copy_(h_lane[lo:hi], non_blocking=True)
         res = sw.run()
-        rows = msweep.gather_results(res, world)
+        rows = msweep.gather_results(res, world, n_max=n_local)
         h_rows.copy_(rows, non_blocking=True)                  # D2H of the step's result
         torch.cuda.synchronize()
         return float(h_rows[:, 51].sum())

@@ -218,6 +218,20 @@ int mbx_deddqn_step(const MbxInstance* d_inst, const double* d_consts, const int
                     const MbxRunConfig* cfg, const MbxDdqnState* st, const MbxDdqnTape* tape, const int32_t* d_action,
                     float* d_feature, float* d_reward, float* d_dbg, int B, void* stream);
 
+/* Persistent DE-DDQN rollout segment: `n_steps` consecutive function evaluations of every unfinished lane in ONE launch --
+ * the agent's greedy action (agent/de_ddqn_agent.py:59-68: argmax of the Q-network on the NaN/inf-sanitised 99 features, weights packed as
+ * for mbx_deddqn_policy) followed by DE_DDQN_Optimizer.update (optimizer/de_ddqn_optimizer.py:131-220), i.e. the body of
+ * DE_DDQN_Agent.rollout_episode (agent/de_ddqn_agent.py:108-117) -- with the lane's population, costs, credit history and window resident in
+ * shared memory for the whole launch.  Bit-identical to n_steps x (mbx_deddqn_policy ; mbx_deddqn_step): same state `st`, same `d_feature`
+ * [B,99] (in: the features mbx_deddqn_init / a previous step or run wrote; out: the features after the last step).
+ *   d_return [B] f32  in/out: the episode return, += max(parent - trial, 0) per step (a NaN / inf reward counts as 0)
+ * Lanes with st->done set are left untouched; a lane that finishes inside the launch stops there.  Philox only (cfg->use_tape must be 0). */
+int mbx_deddqn_run(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxDdqnState* st, float* d_feature, const float* d_weights, int n_weights, float* d_return, int n_steps, int B,
+                   void* stream);
+/* lanes that share one CTA of the persistent kernel (a build-time constant, for grid sizing by callers that care) */
+int mbx_deddqn_run_lanes_per_cta(void);
+
 /* ---------------------------------------------------------------------------------------------
  * GLEET backbone (PSO family, whole swarm per step, per-particle action) -- replaces GLEET_Optimizer.init_population /
  * update / observe (optimizer/gleet_optimizer.py:76-112, 193-314, 128-158) for B lanes at once; the reference's fixed

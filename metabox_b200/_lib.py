@@ -137,13 +137,16 @@ SIGNATURES = {
     'mbx_rl_pso_policy_weight_count': (C.c_int, [C.c_int]),
     'mbx_rl_pso_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     'mbx_qlpso_policy': (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    'mbx_deddqn_run': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), C.POINTER(MbxDdqnState), _P, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    'mbx_deddqn_run_lanes_per_cta': (C.c_int, []),
     'mbx_deddqn_policy_weight_count': (C.c_int, []),
     'mbx_deddqn_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     'mbx_gleet_policy_weight_count': (C.c_int, []),
     'mbx_gleet_policy': (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     'mbx_random_search': (C.c_int, [_P, _P, _P, C.POINTER(MbxRunConfig), _P, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
-OPTIONAL_SIGNATURES = {'mbx_prof_read': (C.c_int, [_P, C.c_int]), 'mbx_prof_read_deddqn': (C.c_int, [_P, C.c_int])}     # only in libmbx_prof.so
+OPTIONAL_SIGNATURES = {'mbx_prof_read': (C.c_int, [_P, C.c_int]), 'mbx_prof_read_deddqn': (C.c_int, [_P, C.c_int]),
+                       'mbx_prof_read_deddqn_run': (C.c_int, [_P, C.c_int])}     # only in libmbx_prof.so
 
 
 def lib():

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(CSRC, 'build')
 LIB = os.path.join(CSRC, 'libmbx.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-SOURCES = ['mbx_capi.cu', 'mbx_kernels.cu', 'mbx_rlepso.cu', 'mbx_lde.cu', 'mbx_deddqn.cu', 'mbx_gleet.cu', 'mbx_rlpso.cu', 'mbx_qlpso.cu', 'mbx_landscape.cu', 'mbx_gleet_policy.cu', 'mbx_deddqn_policy.cu', 'mbx_rlepso_policy.cu', 'mbx_pso_policies.cu', 'mbx_walk.cu']
+SOURCES = ['mbx_capi.cu', 'mbx_kernels.cu', 'mbx_rlepso.cu', 'mbx_lde.cu', 'mbx_deddqn.cu', 'mbx_deddqn_run.cu', 'mbx_gleet.cu', 'mbx_rlpso.cu', 'mbx_qlpso.cu', 'mbx_landscape.cu', 'mbx_gleet_policy.cu', 'mbx_deddqn_policy.cu', 'mbx_rlepso_policy.cu', 'mbx_pso_policies.cu', 'mbx_walk.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-fmad=false',
          '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

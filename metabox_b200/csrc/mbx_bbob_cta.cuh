@@ -10,7 +10,7 @@
 //   * the reductions over k stay sequential per candidate (thread i sums row i in ascending k).
 // Scratch: B[n][ZS] float64 in shared memory, ZS = D + 1 (odd: rows hit distinct banks for the per-candidate passes).
 // ALL threads of the CTA must call (barriers inside).  Returns f(x) incl. bias and boundary handling for candidate
-// `threadIdx.x` (valid when threadIdx.x < n and the candidate is not masked out); requires n <= blockDim.x.
+// `MBX_TID` (valid when MBX_TID < n and the candidate is not masked out); requires n <= MBX_BDIM.
 #pragma once
 #include "mbx_bbob.cuh"
 
@@ -28,7 +28,7 @@ struct BbobCta {
 template <int D, int TI, int TK>
 __device__ __forceinline__ void matvec_cta(const double* __restrict__ M, double* B, const int n, const double add) {
     constexpr int ZS = BbobCta<D>::ZS, KT = D / TK;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = MBX_TID, NT = MBX_BDIM;
     const int IT = (n + TI - 1) / TI, per_round = NT / KT;
     const int lit = tid / KT, kt = tid - lit * KT;
     for (int it0 = 0; it0 < IT; it0 += per_round) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void matvec_cta(const double* __restrict__ M, double*
                     for (int m = 0; m < TK; ++m) acc[j][m] = fma(mv[m], yv[j], acc[j][m]);
             }
         }
-        __syncthreads();
+        MBX_SYNC();
         if (on) {
 #pragma unroll
             for (int j = 0; j < TI; ++j)
@@ -68,7 +68,7 @@ __device__ __forceinline__ void matvec_cta(const double* __restrict__ M, double*
                     for (int m = 0; m < TK; ++m) B[(it * TI + j) * ZS + kt * TK + m] = acc[j][m] + add;
                 }
         }
-        __syncthreads();
+        MBX_SYNC();
     }
 }
 template <int D>
@@ -126,7 +126,7 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
                                                 const unsigned char* only_mask, float4* tile, const int tile_bytes) {
     constexpr int HD = D / 2, ZS = BbobCta<D>::ZS;
     PROF_INIT
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = MBX_TID, NT = MBX_BDIM;
     const double* gC = G + ConstView<D>::kDoubles + P * D;
     const double* gw = gC + P * D;
     const double* gRy = gw + P;
@@ -160,7 +160,7 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
         sc.visit(acc2.x + acc2.y, lw, coef32, K1, p);
     };
     int TP = tile != nullptr ? tile_bytes / (16 * HD + 4) : 0;     // peaks per staged tile; a tile too small for one peak is not used
-    if (TP * HD > 2 * (int)blockDim.x) TP = 2 * (int)blockDim.x / HD;                // two prefetch registers per thread
+    if (TP * HD > 2 * (int)MBX_BDIM) TP = 2 * (int)MBX_BDIM / HD;                // two prefetch registers per thread
     if (TP < 1) {
         if (act) {
 #pragma unroll 1
@@ -189,11 +189,11 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
 #pragma unroll 1
         for (int p0 = 0; p0 < P; p0 += TP) {
             const int m = min(TP, P - p0);
-            __syncthreads();                                     // previous tile fully consumed
+            MBX_SYNC();                                     // previous tile fully consumed
             if (tid < m * HD) tile[tid] = r0;
             if (tid + NT < m * HD) tile[tid + NT] = r1;
             if (tid < m) tl[tid] = rl;
-            __syncthreads();
+            MBX_SYNC();
             if (p0 + TP < P) fetch(p0 + TP);                     // in flight while this tile is consumed
             if (act) {
                 // peaks of this tile with p = g (mod GP)
@@ -202,7 +202,7 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
                 for (; q < m; q += GP) visit(tile + q * HD, tl[q], p0 + q);
             }
         }
-        __syncthreads();                                         // the tile may be reused by the caller
+        MBX_SYNC();                                         // the tile may be reused by the caller
     }
     PROF_MARK(8);
     // merge the GP partial scans of a candidate (GP is a power of two <= 32, groups are warp-aligned)
@@ -224,11 +224,11 @@ __device__ __forceinline__ double gallagher_cta(const double* __restrict__ G, co
         }
     }
     // hand the value to thread ci (the caller's convention: thread i owns candidate i)
-    __syncthreads();
+    MBX_SYNC();
     PROF_MARK(9);
     double* slot = const_cast<double*>(B) + ci * ZS + D;         // the padding column of row ci
     if (act && g == 0) *slot = gval;
-    __syncthreads();
+    MBX_SYNC();
     return (tid < n) ? B[tid * ZS + D] : 0.;
 }
 
@@ -237,7 +237,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
                                 const TX* __restrict__ X, const int n, double* B, const unsigned char* only_mask,
                                 float4* gtile, const int gtile_bytes) {
     constexpr int ZS = BbobCta<D>::ZS;
-    const int tid = threadIdx.x, NT = blockDim.x, nD = n * D;
+    const int tid = MBX_TID, NT = MBX_BDIM, nD = n * D;
     ConstView<D> c(C);
     const int base = h.base;
     const double bias = h.bias, ub = h.ub;
@@ -259,7 +259,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
         double& z = B[i * ZS + k];                                           \
         __VA_ARGS__                                                          \
     }                                                                        \
-    __syncthreads();
+    MBX_SYNC();
     // pair terms read (B[i][k], B[i][k+1]) and overwrite B[i][k]: read -> barrier -> write, round by round
 #define MBX_PAIR(...)                                                        \
     for (int e0 = 0; e0 < nD; e0 += NT) {                                    \
@@ -267,9 +267,9 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
         const bool on = e < nD && k + 1 < D && act(i);                       \
         double t = 0.;                                                       \
         if (on) { const double a = B[i * ZS + k], b = B[i * ZS + k + 1]; __VA_ARGS__ } \
-        __syncthreads();                                                     \
+        MBX_SYNC();                                                     \
         if (on) B[i * ZS + k] = t;                                           \
-        __syncthreads();                                                     \
+        MBX_SYNC();                                                     \
     }
     const double* zr = B + (mine ? tid : 0) * ZS;                    // this thread's row for the per-candidate passes
     // ---------------------------------------------------------------- first linear map
@@ -317,7 +317,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
 #pragma unroll 1
             for (int k = 0; k < D; ++k) { const double z = zr[k]; sq += z * z; }
         }
-        __syncthreads();
+        MBX_SYNC();
         MBX_EW(z = cospi(2. * z);)
         double scs = 0.;
         if (mine) {
@@ -357,7 +357,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
     }
     case 7: {                                                        // Step ellipsoidal
         const double zh0 = mine ? fabs(zr[0]) : 0.;
-        __syncthreads();
+        MBX_SYNC();
         MBX_EW(z = fabs(z) > 0.5 ? floor(0.5 + z) : floor(0.5 + 10. * z) / 10.;)
         matvec_cta_auto<D>(c.M2, B, n);
         double f = 0.;
@@ -476,7 +476,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
             z = 100. * (c.cv0[d] * (z - c.cv1[d]) + c.cv1[d]);
             B[i * ZS + d] = z * sin(sqrt(fabs(z)));
         }
-        __syncthreads();
+        MBX_SYNC();
         double f = 0., pen = 0.;
         if (mine) {
             double prev = 0.;

@@ -126,6 +126,20 @@ int mbx_deddqn_step(const MbxInstance* d_inst, const double* d_consts, const int
                                   B, (cudaStream_t)stream);
 }
 
+int mbx_deddqn_run(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
+                   const MbxDdqnState* st, float* d_feature, const float* d_weights, int n_weights, float* d_return, int n_steps, int B,
+                   void* stream) {
+    int rc = check_cfg("mbx_deddqn_run", cfg, B);
+    if (rc) return rc;
+    MBX_REQUIRE(n_steps >= 0, "mbx_deddqn_run: n_steps=%d", n_steps);
+    MBX_REQUIRE(n_weights == ddq::N_WEIGHTS, "mbx_deddqn_run: %d packed weights, expected %d", n_weights, ddq::N_WEIGHTS);
+    MBX_REQUIRE(!cfg->use_tape, "mbx_deddqn_run: the persistent kernel draws from Philox only (tape replay goes through mbx_deddqn_step)");
+    if (B == 0 || n_steps == 0) return MBX_OK;
+    MBX_REQUIRE(d_inst && d_consts && d_lane_inst && st && d_feature && d_weights && d_return, "mbx_deddqn_run: null pointer");
+    return mbx_launch_deddqn_run(cfg->kind, d_inst, d_consts, d_lane_inst, cfg, st, d_feature, d_weights, d_return, n_steps, B,
+                                 (cudaStream_t)stream);
+}
+
 int mbx_random_search(const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst, const MbxRunConfig* cfg,
                       const double* d_tape_u, int n_tape_iter, float* d_curve, int32_t* d_curve_len, int32_t* d_fes, int B,
                       void* stream) {

@@ -6,7 +6,34 @@
 #include <stdint.h>
 #include "../../include/metabox_b200.h"
 
-#define MBX_NT 128                 // threads per CTA for the population kernels (one CTA = one lane)
+// Threads per lane (a lane = one (instance, run) population).  The population kernels give a lane a whole CTA of 128 threads; a translation
+// unit may choose another group size BEFORE including the shared device code (the persistent DE-DDQN kernel, mbx_deddqn_run.cu: one WARP per
+// lane, so that many lanes are resident per SM and their serial per-step chains overlap).
+#ifndef MBX_NT
+#define MBX_NT 128
+#endif
+
+// Lane groups.  A translation unit whose kernels advance several lanes per CTA defines MBX_LANE_GROUPS > 1 before including the shared
+// device code: thread ids become group-local and the barriers inside the cooperative evaluator / reductions become barriers of the group
+// (__syncwarp for one-warp groups, else the named barrier 1 + group), so that lanes of one CTA may take different paths (different
+// functions, finished lanes).  With the defaults the macros are the plain built-ins.
+#ifndef MBX_LANE_GROUPS
+#define MBX_LANE_GROUPS 1
+#endif
+#if MBX_LANE_GROUPS == 1
+#define MBX_TID ((int)threadIdx.x)
+#define MBX_BDIM ((int)blockDim.x)
+#define MBX_SYNC() __syncthreads()
+#else
+static_assert(MBX_NT % 32 == 0 && (MBX_NT & (MBX_NT - 1)) == 0, "lane groups are whole warps, a power of two of threads");
+#define MBX_TID ((int)(threadIdx.x & (MBX_NT - 1)))
+#define MBX_BDIM MBX_NT
+#if MBX_NT == 32
+#define MBX_SYNC() __syncwarp()
+#else
+#define MBX_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / MBX_NT)), "n"(MBX_NT) : "memory")
+#endif
+#endif
 
 // ---- draw-group tags (numpy twin: oracle/rng.py) -------------------------------------------------
 #define MBX_TAG_INIT 1u
@@ -93,10 +120,10 @@ __device__ __forceinline__ void warp_argmin(float& v, int& i) {
 template <int NT>
 __device__ __forceinline__ void block_argmin(float& v, int& i, float* sv, int* si) {
     warp_argmin(v, i);
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
+    int w = MBX_TID >> 5, l = MBX_TID & 31;
+    MBX_SYNC();
     if (l == 0) { sv[w] = v; si[w] = i; }
-    __syncthreads();
+    MBX_SYNC();
     v = sv[0]; i = si[0];
 #pragma unroll
     for (int k = 1; k < NT / 32; ++k) argmin_pair(v, i, sv[k], si[k]);
@@ -105,10 +132,10 @@ template <int NT>
 __device__ __forceinline__ float block_max(float v, float* sv) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
+    int w = MBX_TID >> 5, l = MBX_TID & 31;
+    MBX_SYNC();
     if (l == 0) sv[w] = v;
-    __syncthreads();
+    MBX_SYNC();
     v = sv[0];
 #pragma unroll
     for (int k = 1; k < NT / 32; ++k) v = fmaxf(v, sv[k]);

@@ -21,10 +21,10 @@ __device__ __forceinline__ void stage_instance(const MbxInstance* __restrict__ i
                                                MbxInstance* sh, double* sC) {
     const int n = EvalTraits<D, KIND>::kConstDoubles;
     const double* src = consts + inst->off;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) sC[k] = __ldg(src + k);
+    for (int k = MBX_TID; k < n; k += MBX_BDIM) sC[k] = __ldg(src + k);
     const int* hs = reinterpret_cast<const int*>(inst);
     int* hd = reinterpret_cast<int*>(sh);
-    for (int k = threadIdx.x; k < (int)(sizeof(MbxInstance) / 4); k += blockDim.x) hd[k] = hs[k];
+    for (int k = MBX_TID; k < (int)(sizeof(MbxInstance) / 4); k += MBX_BDIM) hd[k] = hs[k];
 }
 
 // Evaluate candidates [0,n) of a shared-memory tile (row-major [n][D], element type TX) and write
@@ -40,7 +40,7 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
                                               const unsigned char* only_mask = nullptr, const int zst = MBX_NT,
                                               void* gtile = nullptr, const int gtile_bytes = 0) {
     if (KIND == MBX_KIND_PROTEIN) {
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const int w = MBX_TID >> 5, l = MBX_TID & 31;
         double* ws = scratch + w * MBX_PROT_WARP_SCRATCH;
         for (int i = w; i < n; i += (MBX_NT >> 5)) {
             if (only_mask && !only_mask[i]) continue;
@@ -52,7 +52,7 @@ __device__ __forceinline__ void cta_eval_tile(const MbxInstance& h, const double
         }
     } else {
         // CTA-cooperative BBOB evaluation (mbx_bbob_cta.cuh): every thread participates, thread i receives f(x_i)
-        const int i = threadIdx.x;
+        const int i = MBX_TID;
         const bool act = i < n && !(only_mask && !only_mask[i]);
         double f = bbob_eval_cta<D, TX>(h, sC, gC, tile, n, scratch, only_mask, reinterpret_cast<float4*>(gtile), gtile_bytes);
         if (act) {
@@ -80,13 +80,13 @@ __device__ __forceinline__ double cta_eval_one(const MbxInstance& h, const doubl
                                               const double* noise_tape, int tape_stride) {
     double f = 0.;
     if (KIND == MBX_KIND_PROTEIN) {
-        if (threadIdx.x < 32) {
+        if (MBX_TID < 32) {
             XF32 X{x};
-            f = protein_energy_warp(sC, X, scratch, threadIdx.x & 31, reinterpret_cast<const unsigned short*>(gC + MBX_PROT_DOUBLES), h.n_peaks, h.ub);
+            f = protein_energy_warp(sC, X, scratch, MBX_TID & 31, reinterpret_cast<const unsigned short*>(gC + MBX_PROT_DOUBLES), h.n_peaks, h.ub);
         }
     } else {
         f = bbob_eval_cta<D, float>(h, sC, gC, x, 1, scratch, nullptr, nullptr, 0);
-        if (threadIdx.x == 0) {
+        if (MBX_TID == 0) {
             if (h.noise != MBX_NOISE_NONE) {
                 double d0, d1, d2;
                 if (noise_tape) { d0 = noise_tape[0]; d1 = noise_tape[tape_stride]; d2 = noise_tape[2 * tape_stride]; }

@@ -333,10 +333,10 @@ template <int D, int KIND>
 static int gl_launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                             const MbxGleetState* s, const MbxGleetTape* tape, float* state, int B, cudaStream_t st) {
     auto kern = gleet_init_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_done.set();
     }
     MbxGleetTape t{};
     if (tape) t = *tape;
@@ -349,11 +349,11 @@ static int gl_launch_step_t(const MbxInstance* inst, const double* consts, const
                             const MbxGleetState* s, const MbxGleetTape* tape, const float* action, float* state, float* reward,
                             int B, cudaStream_t st) {
     auto kern = gleet_step_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        attr_done.set();
     }
     MbxGleetTape t{};
     if (tape) t = *tape;

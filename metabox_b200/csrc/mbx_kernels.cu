@@ -47,10 +47,10 @@ static int launch_eval_t(const MbxInstance* inst, const double* consts, const in
     size_t smem = sizeof(MbxInstance) + sizeof(double) * (EvalTraits<D, KIND>::kConstDoubles + EvalTraits<D, KIND>::kScratchDoubles) +
                   sizeof(TX) * RPC * D;
     auto kern = eval_kernel<D, KIND, TX>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done.set();
     }
     dim3 grid((NP + RPC - 1) / RPC, B);
     kern<<<grid, MBX_NT, smem, st>>>(inst, consts, lane_inst, (const TX*)x, (TX*)out, NP, subtract_opt, seed, gen, noise_tape);
@@ -147,10 +147,10 @@ static int launch_rs_t(const MbxInstance* inst, const double* consts, const int3
                        const double* tape_u, int n_tape_iter, float* curve, int32_t* curve_len, int32_t* fes, int B,
                        cudaStream_t st) {
     auto kern = random_search_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PopSmem<D, KIND>::kBytes));
-        attr_done = true;
+        attr_done.set();
     }
     kern<<<B, MBX_NT, PopSmem<D, KIND>::kBytes, st>>>(inst, consts, lane_inst, *cfg, tape_u, n_tape_iter, curve, curve_len, fes);
     MBX_CUDA(cudaGetLastError());

@@ -15,6 +15,16 @@ void mbx_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+// "done once" flag PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only, and one process may
+// drive several GPUs (InstancePack / Tester / Trainers take a device).  Racing host threads at worst set the attribute twice.
+#define MBX_MAX_DEVICES 64
+struct MbxPerDevice {
+    volatile unsigned char flag[MBX_MAX_DEVICES];
+    static int dev() { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < MBX_MAX_DEVICES) ? d : -1; }
+    bool get() const { const int d = dev(); return d >= 0 && flag[d]; }
+    void set() { const int d = dev(); if (d >= 0) flag[d] = 1; }
+};
+
 int mbx_launch_eval(int kind, int D, int x_is_f64, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                     const void* x, void* out, int B, int NP, int subtract_opt, uint64_t seed, uint32_t gen,
                     const double* noise_tape, cudaStream_t st);
@@ -38,6 +48,8 @@ int mbx_launch_deddqn_init(int kind, const MbxInstance* inst, const double* cons
 int mbx_launch_deddqn_step(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                            const MbxRunConfig* cfg, const MbxDdqnState* s, const MbxDdqnTape* tape, const int32_t* action,
                            float* feature, float* reward, float* dbg, int B, cudaStream_t st);
+int mbx_launch_deddqn_run(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                          const MbxDdqnState* s, float* feature, const float* weights, float* ret, int n_steps, int B, cudaStream_t st);
 int mbx_launch_gleet_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                           const MbxRunConfig* cfg, const MbxGleetState* s, const MbxGleetTape* tape, float* state, int B,
                           cudaStream_t st);

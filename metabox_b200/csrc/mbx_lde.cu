@@ -330,10 +330,10 @@ template <int D, int KIND>
 static int lde_launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                              const MbxLdeState* s, const MbxLdeTape* tape, float* feature, int B, cudaStream_t st) {
     auto kern = lde_init_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_done.set();
     }
     MbxLdeTape t{};
     if (tape) t = *tape;
@@ -346,11 +346,11 @@ static int lde_launch_step_t(const MbxInstance* inst, const double* consts, cons
                              const MbxLdeState* s, const MbxLdeTape* tape, const float* action, float* feature, float* reward,
                              float* dbg, int B, cudaStream_t st) {
     auto kern = lde_step_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        attr_done.set();
     }
     MbxLdeTape t{};
     if (tape) t = *tape;

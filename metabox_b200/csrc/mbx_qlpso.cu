@@ -234,10 +234,10 @@ template <int D, int KIND>
 static int ql_launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                             const MbxQlpsoState* s, const MbxQlpsoTape* tape, int32_t* state, int B, cudaStream_t st) {
     auto kern = qlpso_init_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PopSmem<D, KIND>::kBytes));
-        attr_done = true;
+        attr_done.set();
     }
     MbxQlpsoTape t{};
     if (tape) t = *tape;

@@ -495,10 +495,10 @@ template <int D, int KIND>
 static int launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                          const MbxRlepsoState* s, const MbxRlepsoTape* tape, float* feature, int B, cudaStream_t st) {
     auto kern = rlepso_init_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_done.set();
     }
     MbxRlepsoTape t{};
     if (tape) t = *tape;
@@ -511,11 +511,11 @@ static int launch_step_t(const MbxInstance* inst, const double* consts, const in
                          const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci, const float* action,
                          float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
     auto kern = rlepso_step_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        attr_done.set();
     }
     MbxRlepsoTape t{};
     if (tape) t = *tape;

@@ -173,10 +173,10 @@ template <int D, int KIND>
 static int rp_launch_init_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                             const MbxRlPsoState* s, const MbxRlPsoTape* tape, float* state, int B, cudaStream_t st) {
     auto kern = rlpso_init_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PopSmem<D, KIND>::kBytes));
-        attr_done = true;
+        attr_done.set();
     }
     MbxRlPsoTape t{};
     if (tape) t = *tape;
@@ -189,10 +189,10 @@ static int rp_launch_step_t(const MbxInstance* inst, const double* consts, const
                             const MbxRlPsoState* s, const MbxRlPsoTape* tape, const float* action, float* state, float* reward,
                             int B, cudaStream_t st) {
     auto kern = rlpso_step_kernel<D, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RpSmem<D, KIND>::kBytes));
-        attr_done = true;
+        attr_done.set();
     }
     MbxRlPsoTape t{};
     if (tape) t = *tape;

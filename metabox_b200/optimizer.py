@@ -217,7 +217,8 @@ class Random_search(Basic_Optimizer):
         self.log_interval = config.log_interval
         self.cost, self.log_index = None, None
 
-    def run_lanes(self, pack, lane_inst, seed=0, tape_u=None):
+    def run_lanes(self, pack, lane_inst, seed=0, tape_u=None, lane_base=0):
+        """`lane_base`: Philox lane id of lane 0 (the global lane index when a sweep is sharded over ranks)."""
         import torch
         cfg = self.__config
         B = len(lane_inst)
@@ -226,7 +227,7 @@ class Random_search(Basic_Optimizer):
         clen = torch.zeros(B, dtype=torch.int32, device=dev)
         fes = torch.zeros(B, dtype=torch.int32, device=dev)
         li = torch.as_tensor(np.asarray(lane_inst, dtype=np.int32)).to(dev)
-        rc_cfg = _run_config(pack.kind, self.__NP, pack.dim, cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, tape_u is not None, seed)
+        rc_cfg = _run_config(pack.kind, self.__NP, pack.dim, cfg.maxFEs, cfg.n_logpoint, cfg.log_interval, tape_u is not None, seed, int(lane_base))
         n_it, tp = 0, None
         if tape_u is not None:
             tp = torch.as_tensor(tape_u, dtype=torch.float64).to(dev).contiguous()
@@ -445,6 +446,23 @@ class DE_DDQN_Engine:
                                             _lib.stream_ptr())
         _lib.check(rc, 'mbx_deddqn_step')
         return self.feature, self.reward, self.done
+
+    def run_steps(self, packed_weights, ret, n_steps):
+        """`n_steps` consecutive environment steps of every unfinished lane in ONE launch of the persistent kernel (`mbx_deddqn_run`): the
+        greedy action of the Q-network (`packed_weights` = `agent.DE_DDQN_Net.pack()`, float32 on this device) and the fused step, state
+        resident in shared memory.  `ret` [B] float32 accumulates the episode return in place.  -> (feature, done) device tensors."""
+        import torch
+        if ret.dtype != torch.float32 or tuple(ret.shape) != (self.B,) or ret.device != self.device or not ret.is_contiguous():
+            raise ValueError(f'ret must be a contiguous float32 [B] = {(self.B,)} tensor on {self.device}')
+        if packed_weights.dtype != torch.float32 or packed_weights.device != self.device or not packed_weights.is_contiguous():
+            raise ValueError(f'packed_weights must be a contiguous float32 vector on {self.device}')
+        cfg = self._cfg(False)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mbx_deddqn_run(_lib.ptr(self.pack.headers), _lib.ptr(self.pack.consts), _lib.ptr(self.lane_inst), C.byref(cfg),
+                                           C.byref(self._state), _lib.ptr(self.feature), _lib.ptr(packed_weights), packed_weights.numel(),
+                                           _lib.ptr(ret), int(n_steps), self.B, _lib.stream_ptr())
+        _lib.check(rc, 'mbx_deddqn_run')
+        return self.feature, self.done
 
     cost_curves = RLEPSO_Engine.cost_curves
     load_state = RLEPSO_Engine.load_state

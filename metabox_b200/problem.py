@@ -321,8 +321,13 @@ class InstancePack:
                 p._optimum = float(f[k, 0])
                 self.h_headers[k]['optimum'] = p._optimum
             self._upload_headers()
+        # A problem object is bound to the FIRST pack that holds it (`problem.eval`, `*_Optimizer.init_population(problem)` route through
+        # `_pack` / `_index`): a later, larger pack over the same objects (Tester.test_for_random_search packs train + test) must not
+        # silently re-route them to another table / index / device.  Every pack keeps its own index map.
+        self.index_of = {id(p): k for k, p in enumerate(self.problems)}
         for k, p in enumerate(self.problems):
-            p._pack, p._index = self, k
+            if getattr(p, '_pack', None) is None:
+                p._pack, p._index = self, k
 
     @classmethod
     def from_pinned(cls, problems, h_headers_u8, h_consts, device):
@@ -332,7 +337,10 @@ class InstancePack:
         self.problems = list(problems)
         self.kind, self.dim = self.problems[0].kind, self.problems[0].dim
         self.device = device
-        self.h_headers, self.h_consts = None, None
+        # host copies stay available (eval_lanes(noise_free=True) and Tester.cal_t1 patch the headers on the host)
+        self.h_headers = np.frombuffer(h_headers_u8.cpu().numpy().tobytes(), dtype=_lib.INSTANCE_DTYPE).copy()
+        self.h_consts = h_consts.cpu().numpy() if hasattr(h_consts, 'cpu') else np.asarray(h_consts)
+        self.index_of = {id(p): k for k, p in enumerate(self.problems)}
         self.headers = h_headers_u8.to(device, non_blocking=True)
         self.consts = h_consts.to(device, non_blocking=True)
         return self

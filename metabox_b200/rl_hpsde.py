@@ -118,6 +118,8 @@ class RL_HPSDE_Engine:
         ascending order."""
         import torch
         B = self.B
+        if N < 4:       # only past maxFEs (the generation that crosses the budget shrinks below 4, like the reference's): every lane has
+            return torch.zeros(B, N, 3, dtype=torch.int64, device=self.device)     # finished, a sweep's surplus step must not draw
         i = torch.arange(N, device=self.device)[None, :].expand(B, N)
         pick = lambda n: torch.randint(0, n, (B, N), generator=self.gen, device=self.device)
         r0 = pick(N - 1); r0 = r0 + (r0 >= i).to(r0.dtype)
@@ -231,9 +233,7 @@ class RL_HPSDE_Engine:
         # LPSR (:90-99): sort, then truncate to the scheduled size (one schedule for all running lanes)
         self._sort()
         self.fes_running += N
-        # (a sweep may step once more after its last lane has finished: past maxFEs the schedule would shrink below the 4 rows a donor
-        # triple needs -- the reference never gets there, its run has ended -- so the budget is clamped)
-        N_new = max(int(self.NP_max + round(NP_MIN - self.NP_max) * min(self.fes_running, self.maxFEs) / self.maxFEs), 1)
+        N_new = max(int(self.NP_max + round(NP_MIN - self.NP_max) * self.fes_running / self.maxFEs), 1)
         if N_new < N:
             self.group, self.cost = self.group[:, :N_new].contiguous(), self.cost[:, :N_new].contiguous()
         # cost-curve protocol (:262-275)

@@ -201,20 +201,46 @@ class LDE_Sweep(_Sweep):
 
 
 class DE_DDQN_Sweep(_Sweep):
-    """DE_DDQN_Agent.rollout_episode (de_ddqn_agent.py:108-117): greedy argmax of the Q-network, one FE per step."""
+    """DE_DDQN_Agent.rollout_episode (de_ddqn_agent.py:108-117): greedy argmax of the Q-network, one FE per step.
+
+    With the single-kernel twin of the Q-network (`agent.DE_DDQN_FusedNet`) the sweep is PERSISTENT by default: `poll` environment steps
+    per launch of `mbx_deddqn_run` (Q-network inside the kernel, lane state resident in shared memory; bit-identical to `poll` x (policy
+    kernel, step kernel)).  `persistent=False` keeps one policy launch + one step launch per function evaluation (CUDA graph of
+    `steps_per_graph` steps); a torch module as the policy always runs that way."""
 
     def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=500, time_kernels=False,
-                 graph=True, steps_per_graph=10):
+                 graph=True, steps_per_graph=10, persistent=None):
         eng = DE_DDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
-        super().__init__(eng, maxFEs - eng.NP, poll, graph, steps_per_graph, time_kernels)
+        fused = bool(getattr(net, 'fused_action', False))
+        if persistent and not fused:
+            raise ValueError('persistent=True needs agent.DE_DDQN_FusedNet (the packed Q-network) as the policy')
+        self.persistent = fused if persistent is None else bool(persistent)
+        super().__init__(eng, maxFEs - eng.NP, poll, graph and not self.persistent, steps_per_graph, time_kernels)
         self.net = net
-        self.kernels_per_step = 2 if getattr(net, 'fused_action', False) else 1
+        self.kernels_per_step = 2 if fused else 1
 
     def _policy(self, feat):
         if getattr(self.net, 'fused_action', False):            # agent.DE_DDQN_FusedNet: sanitising, 5 layers and argmax in one kernel
             return self.net(feat)
         q = self.net(torch.nan_to_num(feat, nan=0.0, posinf=0.0, neginf=0.0))
         return torch.argmax(q, dim=-1).to(torch.int32)
+
+    def _advance(self):
+        if not self.persistent:
+            return super()._advance()
+        n = min(self.poll, self.max_steps - self.steps)
+        if n <= 0:
+            return
+        if self.time_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.engine.run_steps(self.net.packed, self.ret, n)
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        else:
+            self.engine.run_steps(self.net.packed, self.ret, n)
+        self.launches += 1
+        self.steps += n
 
 
 class DEDQN_Sweep(_Sweep):
@@ -399,12 +425,24 @@ class StripedSweep:
             for j in live:
                 with torch.cuda.stream(self.streams[j]):
                     self.children[j]._advance()
-            live = [j for j in live if self.children[j].steps < self.children[j].max_steps
-                    and not bool(torch.all(self.children[j].engine.done != 0))]
+            nxt = []
+            for j in live:
+                c = self.children[j]
+                # the done-poll is ordered on the STRIPE's stream, behind the kernels that write `done` (on the caller's stream it would
+                # race with them: a reused sweep could read last run's all-ones flags before init_population has executed)
+                with torch.cuda.stream(self.streams[j]):
+                    finished = bool(torch.all(c.engine.done != 0))
+                if c.steps < c.max_steps and not finished:
+                    nxt.append(j)
+            live = nxt
         res = []
         for c, st in zip(self.children, self.streams):
             with torch.cuda.stream(st):
-                res.append(c._result())
+                r = c._result()
+            for v in r.values():
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(cur)             # allocated on the stripe's stream, consumed (torch.cat) on the caller's
+            res.append(r)
             cur.wait_stream(st)
         self.launches = sum(c.launches for c in self.children)
         out = {k: torch.cat([r[k] for r in res]) for k in ('curve', 'curve_len', 'fes', 'ret')}
@@ -412,12 +450,28 @@ class StripedSweep:
         return out
 
 
-def gather_results(res, world):
-    """ONE all-gather of the packed result rows [n_local, 51+2] over the default process group."""
+def gather_results(res, world, n_max=None):
+    """The result rows [n_local, 51+2] = (curve[51], fes, return) of all ranks, in rank order, over the default process group.
+
+    `n_max` = the largest per-rank row count, when the caller knows it (lanes sharded with `shard_range`: ceil(n / world); weak scaling:
+    the common count): ONE all-gather -- the local count travels in a header row of the payload.  Without it the counts are gathered
+    first (two collectives).  `fes` rides in a float32 column: exact below 2^24, and no suite charges more than 2000 * MBX_MAX_DIM =
+    128 000 evaluations per run."""
     import torch.distributed as dist
     row = torch.cat([res['curve'], res['fes'].to(torch.float32)[:, None], res['ret'][:, None]], dim=1).contiguous()
     if world == 1:
         return row
+    if n_max is not None:
+        if row.shape[0] > n_max:
+            raise ValueError(f'gather_results: {row.shape[0]} local rows > n_max = {n_max}')
+        pad = torch.zeros(n_max + 1, row.shape[1], device=row.device, dtype=row.dtype)
+        pad[0, 0] = float(row.shape[0])
+        pad[1:1 + row.shape[0]] = row
+        out = torch.empty(world * (n_max + 1), row.shape[1], device=row.device, dtype=row.dtype)
+        dist.all_gather_into_tensor(out, pad)
+        out = out.reshape(world, n_max + 1, row.shape[1])
+        counts = [int(c) for c in out[:, 0, 0].tolist()]
+        return torch.cat([out[r, 1:1 + counts[r]] for r in range(world)], dim=0)
     n = torch.tensor([row.shape[0]], device=row.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n)

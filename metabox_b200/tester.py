@@ -104,7 +104,7 @@ def sweep_rows(algo, pack, n_problems, n_runs, policy, config, seed=0, stripes=2
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sw = _make_sweep(algo, pack, inst[lo:hi], policy, config, seed, lo, stripes)
-    rows = ms.gather_results(sw.run(), world)
+    rows = ms.gather_results(sw.run(), world, n_max=-(-len(inst) // world))
     torch.cuda.synchronize()
     return rows.cpu().numpy(), time.perf_counter() - t0
 
@@ -170,18 +170,25 @@ class Tester:
         return self._t1
 
     def _random_search(self, problems, pack, n_runs, seed):
+        """Random_search over all (problem, run) lanes, sharded over the ranks like the agents' sweeps (one gather of the rows)."""
+        import torch
         from . import optimizer as mo, sweep as ms
         rank, world = _dist()
         inst, _ = ms.lane_table(len(problems), n_runs)
+        lo, hi = ms.shard_range(len(inst), rank, world)
         opt = mo.Random_search(self.config)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = opt.run_lanes(pack, inst, seed=seed)           # one launch per lane batch, whole episodes in-kernel
-        rows = np.zeros((len(inst), 53), dtype=np.float64)
+        res = opt.run_lanes(pack, inst[lo:hi], seed=seed, lane_base=lo)      # one launch per lane batch, whole episodes in-kernel
+        rows = np.zeros((hi - lo, 53), dtype=np.float32)
         for b, r in enumerate(res):
             c = list(r['cost'])
             c += [c[-1]] * (51 - len(c))                       # tester.py:204-205
             rows[b, :51], rows[b, 51] = c[:51], r['fes']
-        return rows, time.perf_counter() - t0
+        if world > 1:
+            t = torch.as_tensor(rows).to(pack.device)
+            rows = ms.gather_results({'curve': t[:, :51], 'fes': t[:, 51], 'ret': t[:, 52]}, world, n_max=-(-len(inst) // world)).cpu().numpy()
+        return rows.astype(np.float64), time.perf_counter() - t0
 
     def test(self, n_runs=N_RUNS_TEST, seed=0, stripes=2, random_search_baseline=True):
         R = self.test_results

@@ -432,8 +432,10 @@ def _gloo_worker(rank, world, port, n_lanes, q):
         # a fake per-rank sweep result whose content encodes the global lane id
         res = dict(curve=lanes[:, None] + torch.arange(51, dtype=torch.float32)[None, :] / 100.,
                    fes=(1000 + lanes).to(torch.int32), ret=-lanes)
-        rows = sweep.gather_results(res, world)
-        q.put((rank, rows.numpy()))
+        rows = sweep.gather_results(res, world)                                   # counts gathered first (two collectives)
+        rows1 = sweep.gather_results(res, world, n_max=-(-n_lanes // world))      # ONE collective: the count rides in the payload
+        assert torch.equal(rows, rows1)
+        q.put((rank, rows1.numpy()))
     finally:
         dist.destroy_process_group()
 
