@@ -115,6 +115,38 @@ def rollout_job(job):
     return int(info['fes']) - init_fes, time.perf_counter() - t, float(info['cost'][-1])
 
 
+_TRAIN = {}
+
+
+def lde_train_job(job):
+    """job = (problem, dim, difficulty, problem index, seed) -> (fes, seconds): ONE `LDE_Agent.train_episode(PBO_Env(problem, LDE_Optimizer))`
+    of the unmodified reference (lde_agent.py:85-145: 20 trajectories x 50 generations at the reference's fixed NP = 50, then one REINFORCE
+    step), with a freshly constructed agent per worker process (src/trainer.py:160-161 drives exactly this call per problem)."""
+    problem, dim, difficulty, k, seed = job
+    problems, _, opt, PBO_Env, _ = _setup('lde', problem, dim, difficulty)
+    import copy
+    import numpy as np
+    import torch
+    key = (problem, dim, difficulty)
+    if key not in _TRAIN:
+        import agent as ragent
+        cfg = make_config(problem, dim, difficulty)
+        cfg.agent_save_dir = f'/tmp/_mbx_ref_agents/{os.getpid()}/'
+        torch.manual_seed(0)
+        _TRAIN[key] = ragent.LDE_Agent(copy.deepcopy(cfg))
+    ag = _TRAIN[key]
+    p = problems[k]
+    t = time.perf_counter()
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    p.reset()
+    env = PBO_Env(p, opt)
+    ag.train_episode(env)
+    # evaluations of the episode: every trajectory re-initialises the population (NP) and runs TRAJECTORY_LENGTH generations of NP
+    NP, n_traj, n_len = 50, 20, 50
+    return n_traj * (NP + n_len * NP), time.perf_counter() - t, 0.0
+
+
 def problem_names(algo, problem, dim, difficulty):
     problems = _setup(algo, problem, dim, difficulty)[0]
     return [str(p) for p in problems]
@@ -134,9 +166,9 @@ def make_pool(procs, algo, problem, dim, difficulty):
     return pool
 
 
-def timed_batch(pool, jobs):
+def timed_batch(pool, jobs, fn=None):
     """Run the jobs (longest expected first when the caller sorted them) -> (sum of fes, wall seconds, per-job (fes, seconds, cost))."""
     t = time.perf_counter()
-    out = list(pool.imap(rollout_job, jobs, chunksize=1))
+    out = list(pool.imap(fn or rollout_job, jobs, chunksize=1))
     wall = time.perf_counter() - t
     return sum(o[0] for o in out), wall, out

@@ -86,25 +86,33 @@ class LDE_Trainer:
         self.learn_steps = 0
 
     @torch.no_grad()
-    def collect(self, problem_ids, lane_base=0):
-        """20 trajectories x 50 steps for each problem id -> dict of device tensors [T, L, ...] (+ engine for inspection)."""
+    def collect(self, problem_ids, lane_base=0, time_kernels=False):
+        """20 trajectories x 50 steps for each problem id -> dict of device tensors [T, L, ...] (+ engine for inspection).
+        `time_kernels`: CUDA events around every fused-step launch (`kernel_events` in the result; measurement only)."""
         inst = np.repeat(np.asarray(problem_ids, dtype=np.int32), TRAJECTORY_NUM)
         eng = LDE_Engine(self.pack, inst, self.config.maxFEs, self.config.n_logpoint, getattr(self.config, 'log_interval', None),
                          seed=self.seed + 7919 * self.learn_steps, NP=self.NP, lane_base=lane_base)
         L, C = len(inst), self.net.cell
         feat = eng.init_population()
         h = torch.zeros(L, C, device=self.device); c = torch.zeros(L, C, device=self.device)
-        I, A, H, Cc, R, W = [], [], [], [], [], []
+        I, A, H, Cc, R, W, events = [], [], [], [], [], [], []
         for _ in range(TRAJECTORY_LENGTH):
             alive = (eng.done == 0).to(torch.float32)
             x = feat.clone()
             action, h2, c2 = self.net.step(x, h, c)
             I.append(x); A.append(action); H.append(h); Cc.append(c); W.append(alive)
-            feat, reward, _ = eng.update(action)
+            if time_kernels:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                feat, reward, _ = eng.update(action)
+                e1.record()
+                events.append((e0, e1))
+            else:
+                feat, reward, _ = eng.update(action)
             R.append(torch.nan_to_num(reward.clone(), nan=0.0, posinf=0.0, neginf=0.0) * alive)
             h, c = h2, c2
         st = lambda xs: torch.stack(xs, dim=0)
-        return dict(inputs=st(I), actions=st(A), hs=st(H), cs=st(Cc), rewards=st(R), weight=st(W), engine=eng)
+        return dict(inputs=st(I), actions=st(A), hs=st(H), cs=st(Cc), rewards=st(R), weight=st(W), engine=eng, kernel_events=events)
 
     def train_step(self, problem_ids):
         """One learn step over `problem_ids` (sharded over the ranks of the default process group).
