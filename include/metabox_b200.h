@@ -95,7 +95,14 @@ int mbx_sizeof_runconfig(void);
  *   d_out       [B, NP]  f(x) as float32 / float64 (same width as x); raw f(x) incl. bias, i.e. what
  *               `problem.eval(x)` returns;  if subtract_optimum != 0 returns eval(x) - optimum
  *   noise: when the instance is noisy, draws come from Philox(seed, lane, gen) unless d_noise_tape
- *          is non-null: [B, 3, NP] float64 in the reference draw order (uniforms, then normals).   */
+ *          is non-null: [B, 3, NP] float64 in the reference draw order (uniforms, then normals).
+ *   kind:  MBX_KIND_*, optionally OR-ed with ONE promise about the lanes of this launch.  BBOB lanes go through two kernels: a streaming
+ *          kernel (one thread per candidate, no shared memory) for the functions without a rotation (base shapes 5, 8, 20 -- Linear slope,
+ *          Rosenbrock, Schwefel, and the noisy ids built on Rosenbrock), a CTA-cooperative kernel for the rest; each skips the other's
+ *          lanes.  MBX_EVAL_ALL_STREAMING / MBX_EVAL_NONE_STREAMING: every / no lane is of the first sort, the idle kernel is not
+ *          launched.  A wrong promise leaves the mis-promised lanes' outputs unwritten.                                            */
+#define MBX_EVAL_ALL_STREAMING 0x100
+#define MBX_EVAL_NONE_STREAMING 0x200
 int mbx_eval(int kind, const MbxInstance* d_inst, const double* d_consts, const int32_t* d_lane_inst,
              const void* d_x, int x_is_f64, void* d_out, int B, int NP, int D, int subtract_optimum,
              uint64_t seed, uint32_t gen, const double* d_noise_tape, void* stream);

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get('MBX_LIB') or os.path.join(_HERE, 'csrc', 'libmbx.so')
 
 MAX_DIM, MAX_NP, CURVE_LEN = 64, 128, 51
 KIND_BBOB, KIND_PROTEIN = 0, 1
+EVAL_ALL_STREAMING, EVAL_NONE_STREAMING = 0x100, 0x200      # promises OR-ed into mbx_eval's `kind` (include/metabox_b200.h)
 
 
 class MbxError(RuntimeError):

@@ -3,6 +3,7 @@
 // re-initialisation -> cost-curve log, one CTA per lane, state float32 in HBM / float64 in registers.
 // Reference: optimizer/rlepso_optimizer.py:39-65 (init_population), :76-132 (velocity parts,
 // coefficients), :134-168 (re-init), :173-263 (update).  numpy twin: oracle/rlepso.py.
+#include <stdlib.h>
 #include "mbx_eval.cuh"
 #include "mbx_launch.h"
 
@@ -24,8 +25,32 @@ extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
 struct RlLayout {
     int NP, NPp;
     size_t oConst, oA, oSpf, oR1, oR2, oGco, oRank, oOrder, oTileEnd, oGx, oTmpf, oUr, oXs, oF, oPni, oMask, oRed, bytes;
-    __host__ __device__ RlLayout(int np, int D, int kConst, bool protein) {
+    // `move_only`: the layout of rlepso_move_kernel (P0-P2 only: no instance constants, no evaluation scratch, no cost arrays besides
+    // pf32); the list of ambiguous FDR items gets its own region (NP*D u16)
+    __host__ __device__ RlLayout(int np, int D, int kConst, bool protein, bool move_only = false) {
         NP = np; NPp = (np + 3) & ~3;
+        if (move_only) {
+            oConst = 0;
+            oA = 0;                                              // spx f32 [NP*D] | tgt u8 [NP*D]
+            oSpf = oA + (sizeof(float) + 1) * (size_t)NPp * D;
+            oSpf = (oSpf + 15) & ~(size_t)15;
+            oR1 = oSpf + sizeof(float2) * NPp;
+            oR2 = oR1 + 4 * NPp;
+            oGco = (oR2 + 4 * NPp + 7) & ~(size_t)7;
+            oRank = oGco + sizeof(double) * 26;
+            oOrder = oRank + NPp;
+            oTileEnd = oOrder + NPp;
+            oGx = (oTileEnd + 7) & ~(size_t)7;
+            oTmpf = oGx + sizeof(double) * D;
+            oUr = oTmpf;
+            oXs = (oUr + 15) & ~(size_t)15;                      // fbl u16 [NP*D]
+            oF = oXs + sizeof(unsigned short) * NPp * D;         // pf32 only
+            oPni = oF + sizeof(float) * NPp;
+            oMask = oPni;
+            oRed = (oMask + 15) & ~(size_t)15;
+            bytes = oRed + 96;
+            return;
+        }
         const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)(D + 1) * NPp;   // bbob_eval_cta tile [NP][D+1]
         const size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
@@ -231,49 +256,66 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 }
 
 // =====================================================================================================
-template <int D, int KIND>
-__global__ void __launch_bounds__(MBX_NT, MBX_RLEPSO_MIN_CTAS)
+// PH selects the phases of a generation the kernel runs: RL_ALL = the fused step (P0-P6, one launch per generation); RL_MOVE = P0-P2 (ranks,
+// FDR targets, velocity / position: no fitness code, no instance constants -> 24 KB of shared memory and fewer registers, so more CTAs per SM
+// for the part of the step that is bound by instruction issue and latency); RL_EVAL = P3-P6 (fitness of the positions RL_MOVE wrote, pbest /
+// gbest, re-initialisation, log).  MOVE followed by EVAL leaves exactly the bits of ALL: same code, same order, the hand-over is the HBM state.
+#define RL_ALL 0
+#define RL_MOVE 1
+#define RL_EVAL 2
+#ifndef MBX_RLEPSO_MOVE_MIN_CTAS
+#define MBX_RLEPSO_MOVE_MIN_CTAS 6
+#endif
+template <int D, int KIND, int PH>
+__global__ void __launch_bounds__(MBX_NT, PH == RL_MOVE ? MBX_RLEPSO_MOVE_MIN_CTAS : MBX_RLEPSO_MIN_CTAS)
 rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                    MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, const double* __restrict__ pci,
                    const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
                    int32_t* __restrict__ dbg) {
     const int b = blockIdx.x;
-    if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
+    if (S.done[b]) { if (PH != RL_MOVE && threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PROF_INIT
     const int NP = cfg.NP, tid = threadIdx.x;
-    const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN);
+    const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN, PH == RL_MOVE);
     RlepsoViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
-    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    if (PH != RL_MOVE) stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b];
     Philox ph(cfg.seed);
     // ---- P0: per-particle scalars, draws, coefficients (:112-132) -------------------------------------------
-    for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
+    if (PH != RL_EVAL)
+        for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
     if (tid < NP) {
         const int i = tid;
-        V.pf32[i] = S.pbest[pb + i]; V.cc[i] = S.c_cost[pb + i];
-        const int pni = S.pni[pb + i];
-        V.pni[i] = pni;
+        V.pf32[i] = S.pbest[pb + i];
+        if (PH != RL_MOVE) { V.cc[i] = S.c_cost[pb + i]; V.pni[i] = S.pni[pb + i]; }
         if (!cfg.use_tape) {                                          // tape mode reads its float64 draws from the tape directly
             uint4 w4 = ph((uint32_t)i, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_P);
-            V.r1u[i] = w4.x; V.r2u[i] = w4.y; V.uru[i] = w4.z;
+            if (PH != RL_EVAL) { V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
+            if (PH != RL_MOVE) V.uru[i] = w4.z;
         }
     }
     if (tid < 5) {                                                   // float32 coefficient math (numpy-2 promotion)
         const float* a = action + (size_t)b * 35 + tid * 5;
-        const float a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6];
-        const float w = a1 * 0.8f + 0.1f;
-        float ssum = a3 + a4; ssum = ssum + a5; ssum = ssum + a6; ssum = ssum + 1e-5f;
-        float scale = 1.f / ssum; scale = scale * a2; scale = scale * 8.f;
-        double* gc = V.gco + tid * 5;
-        V.a0c[tid] = a[0] * 0.01f;                                   // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
-        gc[0] = (double)w; gc[1] = (double)(scale * a3); gc[2] = (double)(scale * a4);
-        gc[3] = (double)(scale * a5); gc[4] = (double)(scale * a6);
+        if (PH != RL_EVAL) {
+            const float a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6];
+            const float w = a1 * 0.8f + 0.1f;
+            float ssum = a3 + a4; ssum = ssum + a5; ssum = ssum + a6; ssum = ssum + 1e-5f;
+            float scale = 1.f / ssum; scale = scale * a2; scale = scale * 8.f;
+            double* gc = V.gco + tid * 5;
+            gc[0] = (double)w; gc[1] = (double)(scale * a3); gc[2] = (double)(scale * a4);
+            gc[3] = (double)(scale * a5); gc[4] = (double)(scale * a6);
+        }
+        if (PH != RL_MOVE) V.a0c[tid] = a[0] * 0.01f;                 // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
     }
+    if (PH == RL_EVAL)                                                // the positions the move kernel wrote
+        for (int e = tid; e < NP * D; e += MBX_NT) V.xs[e] = S.x[base + e];
     __syncthreads();
     PROF_MARK(0);
+    const double lb = PH == RL_MOVE ? gi->lb : V.h->lb, ub = PH == RL_MOVE ? gi->ub : V.h->ub, vmax = 0.1 * (ub - lb);
+    if (PH != RL_EVAL) {
     // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
     float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
     float2* spf2 = V.spf2;                               // sorted pbest, duplicated (f, f) for the packed FDR scan
@@ -288,8 +330,6 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; spx[V.rank[i] * D + (e - i * D)] = S.pbest_x[base + e]; }
     __syncthreads();
     PROF_MARK(1);
-    const MbxInstance& h = *V.h;
-    const double lb = h.lb, ub = h.ub, vmax = 0.1 * (ub - lb);
     // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5), first minimum   (:97-103) ----
     // The minimum is <= 0 (j = i gives 0), so only particles with a strictly better pbest -- the ones BEFORE i in the
     // sorted order -- can win (equal costs tie with j = i at ratio 0 and are resolved by the index rule).
@@ -380,10 +420,13 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         nv = fmin(fmax(nv, -vmax), vmax);
         double nx = fmin(fmax(x + nv, lb), ub);
         const float nx32 = (float)nx;
-        V.xs[e] = nx32;
+        if (PH == RL_ALL) V.xs[e] = nx32;
         S.x[base + e] = nx32; S.v[base + e] = (float)nv;
     }
     }
+    }   // PH != RL_EVAL
+    if (PH == RL_MOVE) return;
+    const MbxInstance& h = *V.h;
     __syncthreads();
     PROF_MARK(3);
     // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
@@ -506,20 +549,49 @@ static int launch_init_t(const MbxInstance* inst, const double* consts, const in
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
+// One generation = the fused kernel, or the move kernel followed by the evaluation kernel (same bits; see RL_MOVE above).
+// MBX_RLEPSO_SPLIT=0/1 in the environment overrides the default (read once per process; A/B measurements).
+#ifndef MBX_RLEPSO_SPLIT_DEFAULT
+#define MBX_RLEPSO_SPLIT_DEFAULT 0
+#endif
+static int rl_split() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MBX_RLEPSO_SPLIT"); v = e ? (atoi(e) != 0) : MBX_RLEPSO_SPLIT_DEFAULT; }
+    return v;
+}
 template <int D, int KIND>
 static int launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                          const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci, const float* action,
                          float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
-    auto kern = rlepso_step_kernel<D, KIND>;
-    static MbxPerDevice attr_done;
-    if (!attr_done.get()) {
-        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done.set();
-    }
     MbxRlepsoTape t{};
     if (tape) t = *tape;
-    kern<<<B, MBX_NT, RlLayout(cfg->NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN).bytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
+    const size_t full = RlLayout(cfg->NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN).bytes;
+    if (!rl_split()) {
+        auto kern = rlepso_step_kernel<D, KIND, RL_ALL>;
+        static MbxPerDevice attr_done;
+        if (!attr_done.get()) {
+            MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            attr_done.set();
+        }
+        kern<<<B, MBX_NT, full, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
+        MBX_CUDA(cudaGetLastError());
+        return MBX_OK;
+    }
+    auto kmove = rlepso_step_kernel<D, KIND, RL_MOVE>;
+    auto keval = rlepso_step_kernel<D, KIND, RL_EVAL>;
+    static MbxPerDevice attr_done2;
+    if (!attr_done2.get()) {
+        MBX_CUDA(cudaFuncSetAttribute(kmove, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MBX_CUDA(cudaFuncSetAttribute(keval, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MBX_CUDA(cudaFuncSetAttribute(kmove, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MBX_CUDA(cudaFuncSetAttribute(keval, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done2.set();
+    }
+    const size_t mv = RlLayout(cfg->NP, D, 0, false, true).bytes;
+    kmove<<<B, MBX_NT, mv, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
+    MBX_CUDA(cudaGetLastError());
+    keval<<<B, MBX_NT, full, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }

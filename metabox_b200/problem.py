@@ -311,6 +311,7 @@ class InstancePack:
         self.kind, self.dim = kinds.pop(), dims.pop()
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
         self.h_headers, self.h_consts = pack_host(self.problems)
+        self._set_eval_kind()
         self.consts = torch.from_numpy(self.h_consts).to(self.device)
         self._upload_headers()
         if self.kind == _lib.KIND_BBOB and any(p._optimum is None for p in self.problems):
@@ -341,9 +342,21 @@ class InstancePack:
         self.h_headers = np.frombuffer(h_headers_u8.cpu().numpy().tobytes(), dtype=_lib.INSTANCE_DTYPE).copy()
         self.h_consts = h_consts.cpu().numpy() if hasattr(h_consts, 'cpu') else np.asarray(h_consts)
         self.index_of = {id(p): k for k, p in enumerate(self.problems)}
+        self._set_eval_kind()
         self.headers = h_headers_u8.to(device, non_blocking=True)
         self.consts = h_consts.to(device, non_blocking=True)
         return self
+
+    def _set_eval_kind(self):
+        """`kind` argument of mbx_eval with the pack-wide promise about its lanes (include/metabox_b200.h): when every / no instance of the
+        pack is one of the no-rotation functions (base shapes 5, 8, 20), the kernel that would skip all lanes is not launched."""
+        self.eval_kind = self.kind
+        if self.kind == _lib.KIND_BBOB and self.h_headers is not None:
+            light = np.isin(np.asarray(self.h_headers['base']), (5, 8, 20))
+            if light.all():
+                self.eval_kind = self.kind | _lib.EVAL_ALL_STREAMING
+            elif not light.any():
+                self.eval_kind = self.kind | _lib.EVAL_NONE_STREAMING
 
     def _upload_headers(self):
         import torch
@@ -372,7 +385,7 @@ class InstancePack:
             hdr = torch.from_numpy(np.frombuffer(hh.tobytes(), dtype=np.uint8).copy()).to(self.device)
         nt = None if noise_tape is None else torch.as_tensor(noise_tape, dtype=torch.float64).to(self.device).contiguous()
         with torch.cuda.device(self.device):
-            rc = _lib.lib().mbx_eval(self.kind, _lib.ptr(hdr), _lib.ptr(self.consts), _lib.ptr(li), _lib.ptr(xt),
+            rc = _lib.lib().mbx_eval(self.eval_kind, _lib.ptr(hdr), _lib.ptr(self.consts), _lib.ptr(li), _lib.ptr(xt),
                                      int(xt.dtype == torch.float64), _lib.ptr(out), B, NP, D, int(subtract_optimum),
                                      seed, gen, _lib.ptr(nt), _lib.stream_ptr())
             _lib.check(rc, 'mbx_eval')
@@ -390,7 +403,7 @@ class InstancePack:
         B, NP, D = x.shape
         out = torch.empty((B, NP), dtype=x.dtype, device=self.device)
         with torch.cuda.device(self.device):
-            rc = _lib.lib().mbx_eval(self.kind, _lib.ptr(self.headers), _lib.ptr(self.consts), _lib.ptr(lane_inst), _lib.ptr(x),
+            rc = _lib.lib().mbx_eval(self.eval_kind, _lib.ptr(self.headers), _lib.ptr(self.consts), _lib.ptr(lane_inst), _lib.ptr(x),
                                      int(x.dtype == torch.float64), _lib.ptr(out), B, NP, D, int(subtract_optimum), seed, gen, None,
                                      _lib.stream_ptr())
         _lib.check(rc, 'mbx_eval')
