@@ -187,8 +187,7 @@ static int dd_launch_step_t(const MbxInstance* inst, const double* consts, const
 }
 
 #define MBX_DISPATCH(FN, ...)                                                                         \
-    if (cfg->dim == 10 && kind == MBX_KIND_BBOB) return FN<10, MBX_KIND_BBOB>(__VA_ARGS__);           \
-    if (cfg->dim == 30 && kind == MBX_KIND_BBOB) return FN<30, MBX_KIND_BBOB>(__VA_ARGS__);           \
+    MBX_FOR_BBOB_DIMS(MBX_CASE_BBOB_, FN, __VA_ARGS__)                                                 \
     if (cfg->dim == 12 && kind == MBX_KIND_PROTEIN) return FN<12, MBX_KIND_PROTEIN>(__VA_ARGS__);
 
 int mbx_launch_deddqn_init(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,

@@ -219,8 +219,7 @@ static int dd_launch_run_t(const MbxInstance* inst, const double* consts, const 
 
 int mbx_launch_deddqn_run(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                           const MbxDdqnState* s, float* feature, const float* weights, float* ret, int n_steps, int B, cudaStream_t st) {
-    if (cfg->dim == 10 && kind == MBX_KIND_BBOB) return dd_launch_run_t<10, MBX_KIND_BBOB>(inst, consts, lane_inst, cfg, s, feature, weights, ret, n_steps, B, st);
-    if (cfg->dim == 30 && kind == MBX_KIND_BBOB) return dd_launch_run_t<30, MBX_KIND_BBOB>(inst, consts, lane_inst, cfg, s, feature, weights, ret, n_steps, B, st);
+    MBX_FOR_BBOB_DIMS(MBX_CASE_BBOB_, dd_launch_run_t, inst, consts, lane_inst, cfg, s, feature, weights, ret, n_steps, B, st)
     if (cfg->dim == 12 && kind == MBX_KIND_PROTEIN) return dd_launch_run_t<12, MBX_KIND_PROTEIN>(inst, consts, lane_inst, cfg, s, feature, weights, ret, n_steps, B, st);
     mbx_set_error("mbx_deddqn_run: (kind=%d, dim=%d) is not compiled", kind, cfg->dim);
     return MBX_EUNSUP;

@@ -209,11 +209,12 @@ int mbx_launch_eval(int kind, int D, int x_is_f64, const MbxInstance* inst, cons
     if (D == DD && kind == KK)                                                                                         \
         return x_is_f64 ? launch_eval_t<DD, KK, double>(inst, consts, lane_inst, x, out, B, NP, subtract_opt, seed, gen, noise_tape, st, paths) \
                         : launch_eval_t<DD, KK, float>(inst, consts, lane_inst, x, out, B, NP, subtract_opt, seed, gen, noise_tape, st, paths);
-    MBX_EVAL_CASE(10, MBX_KIND_BBOB)
-    MBX_EVAL_CASE(30, MBX_KIND_BBOB)
+#define MBX_EVAL_BBOB_(d, ...) MBX_EVAL_CASE(d, MBX_KIND_BBOB)
+    MBX_FOR_BBOB_DIMS(MBX_EVAL_BBOB_, 0)
+#undef MBX_EVAL_BBOB_
     MBX_EVAL_CASE(12, MBX_KIND_PROTEIN)
 #undef MBX_EVAL_CASE
-    mbx_set_error("mbx_eval: (kind=%d, dim=%d) is not compiled; BBOB dims {10,30}, protein dim 12", kind, D);
+    mbx_set_error("mbx_eval: (kind=%d, dim=%d) is not compiled; BBOB dims {10, 20, 30} (+ -DMBX_DIM_EXTRA at build time), protein dim 12", kind, D);
     return MBX_EUNSUP;
 }
 
@@ -303,8 +304,7 @@ static int launch_rs_t(const MbxInstance* inst, const double* consts, const int3
 
 int mbx_launch_rs(int kind, const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                   const double* tape_u, int n_tape_iter, float* curve, int32_t* curve_len, int32_t* fes, int B, cudaStream_t st) {
-    if (cfg->dim == 10 && kind == MBX_KIND_BBOB) return launch_rs_t<10, MBX_KIND_BBOB>(inst, consts, lane_inst, cfg, tape_u, n_tape_iter, curve, curve_len, fes, B, st);
-    if (cfg->dim == 30 && kind == MBX_KIND_BBOB) return launch_rs_t<30, MBX_KIND_BBOB>(inst, consts, lane_inst, cfg, tape_u, n_tape_iter, curve, curve_len, fes, B, st);
+    MBX_FOR_BBOB_DIMS(MBX_CASE_BBOB_, launch_rs_t, inst, consts, lane_inst, cfg, tape_u, n_tape_iter, curve, curve_len, fes, B, st)
     if (cfg->dim == 12 && kind == MBX_KIND_PROTEIN) return launch_rs_t<12, MBX_KIND_PROTEIN>(inst, consts, lane_inst, cfg, tape_u, n_tape_iter, curve, curve_len, fes, B, st);
     mbx_set_error("mbx_random_search: (kind=%d, dim=%d) is not compiled", kind, cfg->dim);
     return MBX_EUNSUP;

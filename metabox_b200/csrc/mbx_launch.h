@@ -25,6 +25,18 @@ struct MbxPerDevice {
     void set() { const int d = dev(); if (d >= 0) flag[d] = 1; }
 };
 
+// BBOB dimensions compiled into the library.  Every kernel is specialised on the dimension (unrolled rotations, shared-memory plans, the
+// packed FDR scan over dimension pairs), so the reference's free `--dim` (src/config.py:10) becomes a build-time list: the product build
+// carries 10, 20 and 30 (the dimensions the reference's experiments and BASELINE.json use); `python -m metabox_b200.build -DMBX_DIM_EXTRA=<d>`
+// adds one more even d <= 32.  M(d, ...) is expanded once per dimension.
+#ifdef MBX_DIM_EXTRA
+#define MBX_EXTRA_DIM_(M, ...) M(MBX_DIM_EXTRA, __VA_ARGS__)
+#else
+#define MBX_EXTRA_DIM_(M, ...)
+#endif
+#define MBX_FOR_BBOB_DIMS(M, ...) M(10, __VA_ARGS__) M(20, __VA_ARGS__) M(30, __VA_ARGS__) MBX_EXTRA_DIM_(M, __VA_ARGS__)
+#define MBX_CASE_BBOB_(d, FN, ...) if (cfg->dim == d && kind == MBX_KIND_BBOB) return FN<d, MBX_KIND_BBOB>(__VA_ARGS__);
+
 int mbx_launch_eval(int kind, int D, int x_is_f64, const MbxInstance* inst, const double* consts, const int32_t* lane_inst,
                     const void* x, void* out, int B, int NP, int subtract_opt, uint64_t seed, uint32_t gen,
                     const double* noise_tape, cudaStream_t st);

@@ -49,7 +49,7 @@ def points_for(inst, dim, g):
 
 
 def gen_bbob():
-    for dim in (10, 30):
+    for dim in (10, 20, 30):                               # 20: the third compiled dimension (csrc/mbx_launch.h MBX_FOR_BBOB_DIMS)
         out = dict(meta=str(META))
         for suit in ('bbob', 'bbob-noisy'):
             tr, te = rbbob.BBOB_Dataset.get_datasets(suit=suit, dim=dim, upperbound=5, difficulty='easy')

@@ -25,12 +25,12 @@ GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 DIM, NP, MAXFES = 30, 100, 60000
 
 
-def _suite(suit, fids=None, difficulty='easy', subset='all'):
+def _suite(suit, fids=None, difficulty='easy', subset='all', dim=DIM):
     from metabox_b200 import problem as mp
     from oracle import bbob as ob
-    tr, te = mp.BBOB_Dataset.get_datasets(suit, DIM, 5, difficulty=difficulty)
+    tr, te = mp.BBOB_Dataset.get_datasets(suit, dim, 5, difficulty=difficulty)
     probs = te.data if subset == 'test' else tr.data + te.data
-    otr, ote = ob.make_suite(suit, DIM, 5.0)
+    otr, ote = ob.make_suite(suit, dim, 5.0)
     oin = {i.fid: i for i in otr + ote}
     if fids is not None:
         probs = [p for p in probs if p.fid in fids]
@@ -184,3 +184,90 @@ def test_rollout_distributions_match_the_oracle_over_51_runs():
             p_cost = _ks_p(np.log10(np.maximum(g_cost, 1e-12)), np.log10(np.maximum(o_cost, 1e-12)))
         p_fes = 1.0 if (np.ptp(o_fes) == 0 and np.ptp(g_fes) == 0 and o_fes[0] == g_fes[0]) else _ks_p(g_fes, o_fes)
         assert p_cost > 0.01 and p_fes > 0.01, (I.fid, p_cost, p_fes, np.median(g_cost), np.median(o_cost), g_fes.mean(), o_fes.mean())
+
+
+def test_dim_20_the_third_compiled_dimension_through_all_step_kernels():
+    """The reference takes any `--dim` (src/config.py:10); the library compiles a list of dimensions (csrc/mbx_launch.h MBX_FOR_BBOB_DIMS:
+    10, 20, 30).  dim = 20 through the RLEPSO, LDE and DE-DDQN step kernels (Philox replay by the oracle, as above) and through the persistent
+    DE-DDQN kernel and GLEET / Random_search (smoke: they run and keep their invariants)."""
+    import torch
+    from metabox_b200 import optimizer as mo, problem as mp
+    from oracle import bbob as ob, deddqn as od, lde as ol, rlepso as orl
+    from test_gpu_deddqn import _check as dd_check
+    from test_gpu_lde import _check as lde_check
+    from test_gpu_rlepso import _check as rl_check
+    dim, maxFEs = 20, 40000
+    probs, oins = _suite('bbob', fids=(1, 3, 7, 12, 16, 19, 21, 23), dim=dim)
+    nprobs, noins = _suite('bbob-noisy', fids=(103, 113, 126), dim=dim)
+    pack, npack = mp.InstancePack(probs), mp.InstancePack(nprobs)
+    g = np.random.RandomState(20)
+    # ---- RLEPSO
+    seed = 0x200
+    eng = mo.RLEPSO_Engine(pack, list(range(len(probs))), maxFEs, 50, seed=seed)
+    cfg = orl.Config(dim=dim, maxFEs=maxFEs)
+    eng.init_population()
+    for gen in range(6):
+        action = g.rand(len(probs), 35).astype(np.float32)
+        if gen == 3:
+            eng.pni += 40
+        prev = [eng.read_state(b) for b in range(len(probs))]
+        eng.update(torch.as_tensor(action).to(eng.device))
+        for b, I in enumerate(oins):
+            ev = lambda x, draws, I=I: ob.func_true(I, x)
+            p = prev[b]
+            S = orl.State(x=p['x'], v=p['v'], pbest_x=p['pbest_x'], c_cost=p['c_cost'], pbest=p['pbest'], pni=p['pni'],
+                          gbest_x=p['gbest_x'], gbest_val=np.float32(p['gbest_val']), gbest_idx=int(p['gbest_idx']),
+                          no_improve=0, fes=int(p['fes']), log_index=int(p['log_index']), curve=list(p['curve'][:int(p['curve_len'])]))
+            N, _, _, _ = orl.update(cfg, S, action[b], ev, I.optimum, -5., 5., orl.PhiloxTape(cfg.NP, dim, seed, b, gen))
+            rl_check(eng.read_state(b), N, f'rlepso d20 gen {gen} fid {I.fid}')
+    # ---- LDE (noisy functions, NP 50)
+    seed = 0x201
+    eng = mo.LDE_Engine(npack, list(range(len(nprobs))), maxFEs, 50, seed=seed, NP=50)
+    lcfg = ol.Config(dim=dim, maxFEs=maxFEs, NP=50)
+    eng.init_population()
+    for gen in range(5):
+        action = g.rand(len(nprobs), 100).astype(np.float32)
+        prev = [eng.read_state(b) for b in range(len(nprobs))]
+        fg, rg, dg = eng.update(torch.as_tensor(action).to(eng.device))
+        fg = fg.cpu().numpy()
+        for b, I in enumerate(noins):
+            ev = lambda x, draws, I=I: ob.apply_noise(I, ob.func_true(I, x), draws=draws)
+            p = prev[b]
+            S = ol.State(pop=p['pop'], fit=p['fit'], hist_sum=p['hist_sum'], hist_cnt=int(p['hist_cnt']), gbest=p['gbest'],
+                         fes=int(p['fes']), log_index=int(p['log_index']), curve=list(p['curve'][:int(p['curve_len'])]))
+            N, feat, reward, done = ol.update(lcfg, S, action[b], ev, I.optimum, -5., 5., ol.PhiloxTape(50, dim, seed, b, gen, I.noise))
+            lde_check(eng.read_state(b), N, fg[b], feat, f'lde d20 gen {gen} fid {I.fid}')
+    # ---- DE-DDQN
+    seed = 0x202
+    eng = mo.DE_DDQN_Engine(pack, list(range(len(probs))), maxFEs, 50, seed=seed)
+    dcfg = od.Config(dim=dim, maxFEs=maxFEs)
+    f = eng.init_population().cpu().numpy()
+    states = []
+    for b, I in enumerate(oins):
+        ev = lambda x, draws, I=I: ob.apply_noise(I, ob.func_true(I, x), draws=draws)
+        S, feat = od.init_population(dcfg, ev, I.optimum, -5., 5., od.PhiloxTape(dcfg.NP, dim, seed, b, 0xFFFFFFFF, I.noise))
+        dd_check(eng.read_state(b), S, f[b], feat, f'deddqn d20 init fid {I.fid}')
+        states.append(S)
+    for step in range(40):
+        action = g.randint(0, 4, size=len(probs)).astype(np.int32)
+        fg, rg, dg = eng.update(torch.as_tensor(action).to(eng.device))
+        fg = fg.cpu().numpy()
+        for b, I in enumerate(oins):
+            ev = lambda x, draws, I=I: ob.apply_noise(I, ob.func_true(I, x), draws=draws)
+            S = states[b]
+            S, feat, reward, done = od.update(dcfg, S, int(action[b]), ev, I.optimum, -5., 5., od.PhiloxTape(dcfg.NP, dim, seed, b, S.fes, I.noise))
+            st = eng.read_state(b)
+            dd_check(st, S, fg[b], feat, f'deddqn d20 step {step} fid {I.fid}')
+            S.cost = st['cost'].copy(); S.c_gbest, S.c_gworst = np.float32(st['c3'][0]), np.float32(st['c3'][1])
+            S.om_sum, S.om_max = st['om_sum'].copy(), st['om_max'].copy()
+            w = st['win'][:S.win_len]; S.win[:S.win_len] = w[np.argsort(w[:, 6])][:, :6]
+            states[b] = S
+    # ---- GLEET and Random_search: run and keep their invariants
+    ge = mo.GLEET_Engine(pack, list(range(len(probs))), maxFEs, 50, seed=5)
+    ge.init_population()
+    for _ in range(3):
+        ge.update(torch.rand(len(probs), 100, device=ge.device))
+    assert torch.all(ge.fes == 400) and torch.isfinite(ge.gbest_val).all() and torch.all(ge.gbest_val <= ge.pbest.min(dim=1).values + 0)
+    import argparse
+    rs = mo.Random_search(argparse.Namespace(dim=dim, maxFEs=2000, n_logpoint=50, log_interval=40)).run_lanes(pack, [0, 1], seed=3)
+    assert all(r['fes'] == 2000 and all(a >= b for a, b in zip(r['cost'], r['cost'][1:])) for r in rs)

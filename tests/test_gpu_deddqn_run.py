@@ -64,7 +64,7 @@ def _both(pack, lanes, maxFEs, seed, chunks, NP=None, lane_base=3):
     return A, Bn
 
 
-@pytest.mark.parametrize('dim', [10, 30])
+@pytest.mark.parametrize('dim', [10, 20, 30])
 def test_persistent_kernel_equals_policy_plus_step_bit_for_bit(dim):
     from metabox_b200 import problem as mp
     cases = [('bbob', 1), ('bbob', 7), ('bbob', 16), ('bbob', 21), ('bbob-noisy', 104), ('bbob-noisy', 118), ('bbob-noisy', 129),

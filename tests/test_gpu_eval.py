@@ -18,7 +18,7 @@ def _all(dim):
     return out
 
 
-@pytest.mark.parametrize('dim', [10, 30])
+@pytest.mark.parametrize('dim', [10, 20, 30])
 def test_bbob_eval_f64_matches_reference(dim):
     """float64 in / float64 out: |f - f_ref| <= 1e-9 rel (observed ~1e-14), cost within 1e-6 rel + 64 ulp(bias)."""
     from metabox_b200 import problem as mp
@@ -41,7 +41,7 @@ def test_bbob_eval_f64_matches_reference(dim):
     assert worst < 1e-11
 
 
-@pytest.mark.parametrize('dim', [10, 30])
+@pytest.mark.parametrize('dim', [10, 20, 30])
 def test_bbob_eval_f32_io(dim):
     """float32 in / float32 out (the storage contract): equals float32(reference on the same points)."""
     from metabox_b200 import problem as mp
@@ -58,7 +58,7 @@ def test_bbob_eval_f32_io(dim):
                                    atol=64 * np.spacing(abs(probs[f].bias) + 1.0), err_msg=f'fid {f}')
 
 
-@pytest.mark.parametrize('dim', [10, 30])
+@pytest.mark.parametrize('dim', [10, 20, 30])
 def test_noisy_eval_with_replayed_draws(dim):
     """Noise models: feed the reference's own draws (regenerated from the recorded seed) through the tape."""
     from metabox_b200 import problem as mp

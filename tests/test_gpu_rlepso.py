@@ -238,7 +238,7 @@ def test_done_lanes_are_frozen_and_empty_batch():
     e0.init_population(); e0.update(torch.zeros(0, 35).to(eng.device))
 
 
-@pytest.mark.parametrize('dim', [10, 30])
+@pytest.mark.parametrize('dim', [10, 20, 30])
 def test_fdr_targets_exact_incl_ties_duplicates_and_converged_swarms(dim):
     """FDR target indices (rlepso_optimizer.py:97-103) must equal np.argmin of the float64 quotients exactly.  The kernel
     screens in float32 and re-does ambiguous items with the reference's float64 divisions: crafted swarms hit both

@@ -16,7 +16,7 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-@pytest.fixture(scope='module', params=[10, 30])
+@pytest.fixture(scope='module', params=[10, 20, 30])
 def suite(request):
     dim = request.param
     G = load(f'bbob_d{dim}.npz')
