@@ -696,7 +696,10 @@ def main():
                        'lanes_per_gpu': n_local, 'lane_order': args.lane_order, 'state': 'float32 HBM / float64 registers', 'policy': wsrc,
                        'launch': launch,
                        'l2': f'per-GPU state {state_mb:.0f} MB vs 126 MB L2' + (' (inputs larger than L2)' if state_mb > 126 else ' (L2 resident; the kernel is not DRAM bound)'),
-                       'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep'},
+                       'parallelism': f'lanes sharded over {world} GPU(s), one NCCL all-gather per sweep',
+                       'e2e': 'the plug-in call with HOST buffers: the packed instance table + lane table go host -> device from pinned memory and the '
+                              'result rows (cost curve, fes, return per lane) device -> host inside the timed region, every step; populations '
+                              'are born on the device (Philox), so there are no candidate buffers to upload'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_note': traffic_note,
                          'kernel': W['kernel'], 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,

@@ -27,7 +27,8 @@ extern "C" {
 #define MBX_OK 0
 #define MBX_EINVAL -1   /* bad argument (shape, id, null pointer)            */
 #define MBX_ECUDA -2    /* CUDA runtime error (launch / attribute)           */
-#define MBX_EUNSUP -3   /* combination not compiled (e.g. dim > MBX_MAX_DIM) */
+#define MBX_EUNSUP -3   /* (kind, dim) not compiled: the library carries BBOB dims 10, 20, 30 (+ one -DMBX_DIM_EXTRA=<even d <= 32> at build
+                           time, csrc/mbx_launch.h) and protein dim 12; the reference's `--dim` is free (src/config.py:10) */
 
 #define MBX_MAX_DIM 64
 #define MBX_MAX_NP 128
@@ -42,7 +43,7 @@ extern "C" {
 #define MBX_NOISE_UNIFORM 2
 #define MBX_NOISE_CAUCHY 3
 
-/* One problem instance.  Built on the host by metabox_b200/pack.py from the instance constants that
+/* One problem instance.  Built on the host by metabox_b200/problem.py (`pack_host`, `BBOB_Problem.header` / `const_block`) from the instance constants that
  * problem/bbob.py:31-45 + the per-class constructors (bbob.py:149-890) or
  * problem/protein_docking.py:163-181 produce; `off` is the instance's offset (in doubles) into the
  * constants buffer.  BBOB constants layout at `off`:
@@ -62,7 +63,7 @@ typedef struct MbxInstance {
     double lb, ub, bias, optimum;
     double bh_coef;        /* boundaryHandling(x) = bh_coef * pen(x)             */
     double n_alpha, n_beta, n_p;   /* noise parameters                           */
-    double sc[8];          /* function-specific scalars, see pack.py             */
+    double sc[8];          /* function-specific scalars (problem.py header())    */
     int64_t off;
 } MbxInstance;
 

@@ -391,8 +391,14 @@ class GLEET_Trainer(_PPOTrainer):
         (bl + rl).backward()
 
     def _apply(self):
-        for group in self.optimizer.param_groups:
-            torch.nn.utils.clip_grad_norm_(group['params'], GLEET_MAX_GRAD_NORM, norm_type=2)
+        norms = [torch.nn.utils.clip_grad_norm_(group['params'], GLEET_MAX_GRAD_NORM, norm_type=2) for group in self.optimizer.param_groups]
+        # GLEET's state divides costs by `max_cost` = the MINIMUM of the initial costs (gleet_optimizer.py:49, reproduced), so features reach
+        # 1e4 on badly scaled functions at dim 30 and a batch of such lanes can overflow the backward pass.  One non-finite gradient would
+        # turn every weight into NaN (clip_grad_norm_ scales by NaN): such an update is skipped and counted instead.
+        if not all(bool(torch.isfinite(n)) for n in norms):
+            self.skipped_updates = getattr(self, 'skipped_updates', 0) + 1
+            self.optimizer.zero_grad(set_to_none=True)
+            return
         self.optimizer.step()
         if self._fused is not None:
             self._fused.refresh()
