@@ -663,7 +663,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = (k_fes * W['bytes_per_eval']) / (k_ms / 1000.0) / 1e9 if k_ms > 0 else None
-        traffic, traffic_note = None, 'no ncu --set full capture recorded for this kernel'
+        traffic, traffic_note, tr = None, 'no ncu --set full capture recorded for this kernel', None
         try:                                                    # DRAM bytes per launch from the committed ncu capture
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(W['kernel'])
             if tr:
@@ -673,6 +673,20 @@ def main():
                                 f"{n_local * NP * W['bytes_per_eval']:.4g}")
         except Exception:
             pass
+        # second roofline for kernels that are bound by instruction ISSUE, not bytes: warp instructions per evaluation from the committed ncu
+        # capture x the measured evaluation rate of the step launches, against 4 issue slots per SM-cycle at the sampled SM clock
+        issue = None
+        try:
+            if tr and tr.get('warp_instructions_per_launch') and k_ms > 0:
+                wipe = tr['warp_instructions_per_launch'] / tr['evals_per_launch']
+                props = torch.cuda.get_device_properties(dev)
+                mhz = (clk or {}).get('sm_mhz') or 1965.0
+                peak_issue = 4.0 * props.multi_processor_count * mhz * 1e6
+                ach = (k_fes / (k_ms / 1000.0)) * wipe
+                issue = {'warp_instructions_per_eval': wipe, 'achieved_warp_instr_per_s': ach, 'peak_warp_instr_per_s': peak_issue,
+                         'frac': ach / peak_issue, 'source': tr.get('issue_source')}
+        except Exception:
+            issue = None
         state_mb = {'rlepso': n_local * (3 * NP * dim + 3 * NP) * 4, 'protein': n_local * (3 * NP * dim + 3 * NP) * 4,
                     'lde': n_local * (NP * dim + NP) * 4, 'gleet': n_local * (3 * NP * dim + 3 * NP + 9 * NP) * 4,
                     'deddqn': n_local * ((NP * dim + NP) * 4 + 8800)}[args.workload] / 1e6
@@ -703,7 +717,7 @@ def main():
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_note': traffic_note,
                          'kernel': W['kernel'], 'avg_launch_ms': k_ms / max(1, k_n), 'launches_timed': k_n,
-                         'kernel_share_of_step': (k_ms / k_sweep_ms) if k_sweep_ms else None, 'peak_source': peak_src,
+                         'kernel_share_of_step': (k_ms / k_sweep_ms) if k_sweep_ms else None, 'peak_source': peak_src, 'issue': issue,
                          'timed': 'separate instrumented (eager, unstriped) sweep of the same workload right after the timed region; '
                                   'kernel_share_of_step = step-kernel time / duration of that sweep',
                          'note': f'algorithmic bytes = {W["bytes_per_eval"]} B/eval x evals charged by the step launches; see DESIGN.md section 4 '
