@@ -87,12 +87,14 @@ def parse():
     ap.add_argument('--lane-order', default=None, choices=['instance-major', 'run-major', 'stripe-balanced'],
                     help='order of the (instance, run) lanes inside a GPU (default: instance-major; lde: stripe-balanced = every '
                          'stripe gets ~runs/stripes runs of every function, instance-major inside)')
+    ap.add_argument('--poll', type=int, default=None, help='deddqn (persistent): function evaluations per launch (default 250)')
+    ap.add_argument('--launches-per-poll', type=int, default=None, help='deddqn (persistent): launches issued back to back between two host polls of `done` (default 16)')
     ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
     if a.runs is None:
         a.runs = WORKLOADS[a.workload].get('runs', 256)          # C3: 256 runs in lockstep; C5: 51 runs
     if a.stripes is None:
-        a.stripes = 6 if (a.workload == 'deddqn' and a.torch_policy) else (1 if a.workload == 'deddqn' else 3)       # the 1-FE-per-step chain is latency bound: more chains in flight
+        a.stripes = 6 if (a.workload == 'deddqn' and a.torch_policy) else 3   # deddqn persistent: 576 CTAs on 444 resident slots -- 3 streams fill each other's last wave       # the 1-FE-per-step chain is latency bound: more chains in flight
     if a.lane_order is None:
         a.lane_order = 'stripe-balanced' if a.workload == 'lde' else 'instance-major'     # measured: profiles/, DESIGN.md section 6
     return a
@@ -582,6 +584,11 @@ def main():
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
     gkw = {} if args.steps_per_graph is None else {'steps_per_graph': args.steps_per_graph}
+    if args.workload == 'deddqn' and not args.torch_policy:
+        if args.poll is not None:
+            gkw['poll'] = args.poll
+        if args.launches_per_poll is not None:
+            gkw['launches_per_poll'] = args.launches_per_poll
     sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph, **gkw)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -694,8 +701,8 @@ def main():
         if args.no_graph:
             launch = 'eager'
         elif args.workload == 'deddqn' and not args.torch_policy:
-            launch = ('persistent kernel (mbx_deddqn_run): 500 function evaluations per launch, Q-network inside the kernel, lane state resident '
-                      f'in shared memory; {args.stripes} lane stripe(s) on separate streams')
+            launch = (f'persistent kernel (mbx_deddqn_run): {args.poll or 250} function evaluations per launch, {args.launches_per_poll or 16} launches between host polls, '
+                      f'Q-network inside the kernel, lane state resident in shared memory; {args.stripes} lane stripe(s) on separate streams')
         else:
             launch = f'policy forward + fused step replayed from one CUDA graph per {spg} step(s); {args.stripes} lane stripe(s) on separate streams'
         lanes_txt = (f'{len(problems)} instances x {args.runs} runs = {n_global} lanes sharded over {world} GPU(s) (strong scaling: a fixed job)'

@@ -203,18 +203,25 @@ class LDE_Sweep(_Sweep):
 class DE_DDQN_Sweep(_Sweep):
     """DE_DDQN_Agent.rollout_episode (de_ddqn_agent.py:108-117): greedy argmax of the Q-network, one FE per step.
 
-    With the single-kernel twin of the Q-network (`agent.DE_DDQN_FusedNet`) the sweep is PERSISTENT by default: `poll` environment steps
+    With the single-kernel twin of the Q-network (`agent.DE_DDQN_FusedNet`) the sweep is PERSISTENT by default: `poll` (250) environment steps
     per launch of `mbx_deddqn_run` (Q-network inside the kernel, lane state resident in shared memory; bit-identical to `poll` x (policy
     kernel, step kernel)).  `persistent=False` keeps one policy launch + one step launch per function evaluation (CUDA graph of
     `steps_per_graph` steps); a torch module as the policy always runs that way."""
 
-    def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=500, time_kernels=False,
-                 graph=True, steps_per_graph=10, persistent=None):
+    def __init__(self, pack, lane_inst, net, maxFEs, n_logpoint=50, seed=0, lane_base=0, poll=None, time_kernels=False,
+                 graph=True, steps_per_graph=10, persistent=None, launches_per_poll=16):
+        """`launches_per_poll` (persistent mode): launches of `poll` steps issued back to back before the host looks at `done` again.  A
+        launch of ceil(B / 8) CTAs rarely fills a whole number of waves (C3: 576 CTAs on 444 resident slots); with several launches in
+        flight per stream and several striped sweeps on different streams, the next launch's CTAs fill the slots the last wave leaves
+        idle.  Finished lanes cost nothing (their warps skip the launch)."""
         eng = DE_DDQN_Engine(pack, lane_inst, maxFEs, n_logpoint, seed=seed, lane_base=lane_base)
+        self.launches_per_poll = max(1, int(launches_per_poll))
         fused = bool(getattr(net, 'fused_action', False))
         if persistent and not fused:
             raise ValueError('persistent=True needs agent.DE_DDQN_FusedNet (the packed Q-network) as the policy')
         self.persistent = fused if persistent is None else bool(persistent)
+        if poll is None:                 # persistent: 250 evaluations per launch (measured: profiles/r2r_deddqn_launch_tuning.txt); else a poll every 500 steps
+            poll = 250 if self.persistent else 500
         super().__init__(eng, maxFEs - eng.NP, poll, graph and not self.persistent, steps_per_graph, time_kernels)
         self.net = net
         self.kernels_per_step = 2 if fused else 1
@@ -228,19 +235,20 @@ class DE_DDQN_Sweep(_Sweep):
     def _advance(self):
         if not self.persistent:
             return super()._advance()
-        n = min(self.poll, self.max_steps - self.steps)
-        if n <= 0:
-            return
-        if self.time_kernels:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            self.engine.run_steps(self.net.packed, self.ret, n)
-            e1.record()
-            self.kernel_events.append((e0, e1))
-        else:
-            self.engine.run_steps(self.net.packed, self.ret, n)
-        self.launches += 1
-        self.steps += n
+        for _ in range(self.launches_per_poll):
+            n = min(self.poll, self.max_steps - self.steps)
+            if n <= 0:
+                return
+            if self.time_kernels:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.engine.run_steps(self.net.packed, self.ret, n)
+                e1.record()
+                self.kernel_events.append((e0, e1))
+            else:
+                self.engine.run_steps(self.net.packed, self.ret, n)
+            self.launches += 1
+            self.steps += n
 
 
 class DEDQN_Sweep(_Sweep):
