@@ -87,7 +87,7 @@ def parse():
     ap.add_argument('--lane-order', default=None, choices=['instance-major', 'run-major', 'stripe-balanced'],
                     help='order of the (instance, run) lanes inside a GPU (default: instance-major; lde: stripe-balanced = every '
                          'stripe gets ~runs/stripes runs of every function, instance-major inside)')
-    ap.add_argument('--poll', type=int, default=None, help='deddqn (persistent): function evaluations per launch (default 250)')
+    ap.add_argument('--poll', type=int, default=None, help='environment steps between two host polls of the done flags (default 64 generations; deddqn persistent: evaluations per launch, default 250)')
     ap.add_argument('--launches-per-poll', type=int, default=None, help='deddqn (persistent): launches issued back to back between two host polls of `done` (default 16)')
     ap.add_argument('--no-graph', action='store_true', help='launch policy + step kernels eagerly instead of replaying a CUDA graph')
     a = ap.parse_args()
@@ -584,11 +584,10 @@ def main():
 
     # ---- value: inputs resident in HBM; policy forward + fused step replayed from a CUDA graph ------------------
     gkw = {} if args.steps_per_graph is None else {'steps_per_graph': args.steps_per_graph}
-    if args.workload == 'deddqn' and not args.torch_policy:
-        if args.poll is not None:
-            gkw['poll'] = args.poll
-        if args.launches_per_poll is not None:
-            gkw['launches_per_poll'] = args.launches_per_poll
+    if args.poll is not None:
+        gkw['poll'] = args.poll
+    if args.workload == 'deddqn' and not args.torch_policy and args.launches_per_poll is not None:
+        gkw['launches_per_poll'] = args.launches_per_poll
     sw = make_sweep(args.workload, pack, inst, net, seed, lane_base, NP, stripes=args.stripes, graph=not args.no_graph, **gkw)
     clocks = ClockSampler(local_rank)
     if rank == 0:

@@ -63,9 +63,24 @@ def _dist():
     return 0, 1
 
 
+def _check_policy(algo, policy):
+    """A policy object of the WRONG backbone (e.g. an RLEPSO actor handed to the NRLPSO sweep) used to fail deep inside torch with a dtype
+    error; the known policy classes are checked against the backbone up front.  Unknown callables (user policies) pass."""
+    from . import agent as ma
+    known = {'rlepso': (ma.RLEPSO_Actor, ma.RLEPSO_FusedActor), 'lde': (ma.LDE_PolicyNet,), 'deddqn': (ma.DE_DDQN_Net, ma.DE_DDQN_FusedNet),
+             'gleet': (ma.GLEET_Actor, ma.GLEET_FusedActor), 'rl_pso': (ma.RL_PSO_PolicyNet, ma.RL_PSO_FusedPolicy),
+             'qlpso': (ma.QLPSO_QTable, ma.QLPSO_FusedQTable), 'nrlpso': (ma.QLPSO_QTable, ma.QLPSO_FusedQTable),
+             'rl_hpsde': (ma.QLPSO_QTable, ma.QLPSO_FusedQTable), 'dedqn': (ma.DEDQN_Net,), 'l2l': (ma.L2L_PolicyNet,)}
+    every = tuple({c for cs in known.values() for c in cs})
+    if algo in known and isinstance(policy, every) and not isinstance(policy, known[algo]):
+        raise ValueError(f'{type(policy).__name__} is not a policy of the {algo} backbone (expected one of '
+                         f'{[c.__name__ for c in known[algo]]})')
+
+
 def _make_sweep(algo, pack, lanes, policy, config, seed, lane_base, stripes):
     from . import sweep as ms
     n_log = config.n_logpoint
+    _check_policy(algo, policy)
 
     def make(ln, lb):
         if algo == 'rlepso':

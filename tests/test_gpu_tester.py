@@ -80,5 +80,7 @@ def test_rollout_writes_reference_layout(tmp_path):
         assert len(ck) == 2 and all(len(runs) == 2 and len(runs[0]) == 51 for runs in ck)
         assert all(isinstance(r, float) for runs in P['return'][p]['RLEPSO_Agent'] for r in runs)
     with pytest.raises(ValueError):
-        mt.rollout(cfg, {'RL_DAS_Agent': nets})
+        mt.rollout(cfg, {'RL_DAS_Agent': nets})                 # no B200 backbone of that name
+    with pytest.raises(ValueError):
+        mt.rollout(cfg, {'NRLPSO_Agent': nets})                 # a backbone that exists, handed the policy of another one
     assert R.keys() == P.keys()
