@@ -211,13 +211,25 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     const uint32_t gen = (uint32_t)S.gen[b], lane = (uint32_t)(cfg.lane_base + b);
     const int fes0 = S.fes[b];
     Philox ph(cfg.seed);
+    // the population rows are requested now (NP * D / 128 <= D values per thread) and scattered into rank order after the rank barrier:
+    // their DRAM latency hides behind the constant staging and the rank computation
+    float popr[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int e = tid + k * MBX_NT;
+        popr[k] = e < NP * D ? __ldcs(S.pop + base + e) : 0.f;
+    }
     // ---- P0: order_by_f (:160) -- the stored state is sorted already, re-ranked for safety -------------------
     if (tid < NP) V.nfit[tid] = S.fit[pb + tid];
     __syncthreads();
     lde_rank(V.nfit, V.rank, NP);
     __syncthreads();
     if (tid < NP) { V.fit[V.rank[tid]] = V.nfit[tid]; V.src[V.rank[tid]] = (unsigned char)tid; }
-    for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; V.ps[V.rank[i] * D + (e - i * D)] = S.pop[base + e]; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int e = tid + k * MBX_NT;
+        if (e < NP * D) { const int i = e / D; V.ps[V.rank[i] * D + (e - i * D)] = popr[k]; }
+    }
     // ---- P1: per-individual parameters and draws (:164-167, :88-123) ---------------------------------------------
     if (tid < NP) {
         const int i = tid;

@@ -46,8 +46,8 @@ struct RlLayout {
             oXs = (oUr + 15) & ~(size_t)15;                      // fbl u16 [NP*D]
             oF = oXs + sizeof(unsigned short) * NPp * D;         // pf32 only
             oPni = oF + sizeof(float) * NPp;
-            oMask = oPni;
-            oRed = (oMask + 15) & ~(size_t)15;
+            oMask = oPni;                                        // particle -> coefficient group u8 [NP]
+            oRed = (oMask + NPp + 15) & ~(size_t)15;
             bytes = oRed + 96;
             return;
         }
@@ -284,6 +284,16 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b];
     Philox ph(cfg.seed);
+    // the pbest_x rows are requested NOW (NP * D / 128 <= D values per thread, NP <= 128) and scattered into their rank order after P0b:
+    // their DRAM latency hides behind the constant staging, P0 and the rank loop instead of being exposed between two barriers
+    float pbx[D];
+    if (PH != RL_EVAL) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int e = tid + k * MBX_NT;
+            pbx[k] = e < NP * D ? __ldcs(S.pbest_x + base + e) : 0.f;
+        }
+    }
     // ---- P0: per-particle scalars, draws, coefficients (:112-132) -------------------------------------------
     if (PH != RL_EVAL)
         for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
@@ -310,6 +320,10 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         }
         if (PH != RL_MOVE) V.a0c[tid] = a[0] * 0.01f;                 // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
     }
+    if (PH != RL_EVAL && tid < NP) {                                 // coefficient group of every particle, 20 % of the swarm each (:113-118): the
+        const int per = NP / 5;                                       // run-time division happens once per particle here, not once per (i, d) in P2
+        V.mask[tid] = (unsigned char)min(tid / per, 4);
+    }
     if (PH == RL_EVAL)                                                // the positions the move kernel wrote
         for (int e = tid; e < NP * D; e += MBX_NT) V.xs[e] = S.x[base + e];
     __syncthreads();
@@ -327,7 +341,11 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     }
     if (tid == 0) *V.nfb = 0;
     __syncthreads();
-    for (int e = tid; e < NP * D; e += MBX_NT) { const int i = e / D; spx[V.rank[i] * D + (e - i * D)] = S.pbest_x[base + e]; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int e = tid + k * MBX_NT;
+        if (e < NP * D) { const int i = e / D; spx[V.rank[i] * D + (e - i * D)] = pbx[k]; }
+    }
     __syncthreads();
     PROF_MARK(1);
     // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5), first minimum   (:97-103) ----
@@ -413,9 +431,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         const double r1 = cfg.use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = cfg.use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
         const double v_pbest = r1 * (pxi - x);
         const double v_gbest = r2 * (V.gx[d] - x);
-        const int per = NP / 5;
-        int g = i / per; if (g > 4) g = 4;
-        const double* gc = V.gco + g * 5;
+        const double* gc = V.gco + V.mask[i] * 5;                      // group of particle i (table written in P0; `mask` is free until P4)
         double nv = gc[0] * v + gc[1] * v_clpso + gc[2] * v_fdr + gc[3] * v_gbest + gc[4] * v_pbest;
         nv = fmin(fmax(nv, -vmax), vmax);
         double nx = fmin(fmax(x + nv, lb), ub);
