@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_rlepso.py tests/test_gpu_benchmark_shapes.py tests/test_gpu_edge_sizes.py tests/test_gpu_configs.py -q -m gpu -p no:cacheprovider -k "rlepso or c2 or c5 or dim_20 or edge" ) 2>&1 | tail -2
+for i in 1 2; do ( timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ) 2>gpurun_out/r2v.err | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2), 'M evals/s', round(d['ms_per_step'],1), 'ms; step kernel', round(d['roofline']['avg_launch_ms'],4))"; done
+( timeout 300 python bench.py --workload protein --steps 5 --warmup 3 --no-cpu-baseline ) 2>gpurun_out/r2v.err | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('protein', round(d['value']/1e6,2), 'M evals/s', round(d['ms_per_step'],1), 'ms')"
