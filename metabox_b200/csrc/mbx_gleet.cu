@@ -215,7 +215,13 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
         V.cb[i] = GL_C * (1.f - a);
         if (!cfg.use_tape) { uint4 w4 = ph((uint32_t)i, gen, lane, MBX_TAG_GLEET_P); V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
     }
-    for (int e = tid; e < NP * D; e += MBX_NT) V.pbx[e] = S.pbest_x[base + e];
+    {   // all row loads of a thread are issued before the first shared-memory store (NP * D / 128 <= D values per thread)
+        float pr[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const int e = tid + k * MBX_NT; pr[k] = e < NP * D ? S.pbest_x[base + e] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const int e = tid + k * MBX_NT; if (e < NP * D) V.pbx[e] = pr[k]; }
+    }
     __syncthreads();
     const MbxInstance& h = *V.h;
     const double lb = h.lb, ub = h.ub, vmax = 0.1 * (ub - lb), w = *V.sw;
@@ -274,12 +280,22 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     if (gb_better) { gbest = v; gidx = ix; }
     const int no_improve = gb_better ? 0 : S.no_improve[b] + 1;
     // the evaluation scratch is free again: rebuild the pbest tile (old rows from HBM/L2, improved rows from xs)
-    for (int e = tid; e < NP * D; e += MBX_NT) {
-        const int i = e / D;
-        float pv;
-        if (V.better[i]) { pv = V.xs[e]; S.pbest_x[base + e] = pv; }
-        else pv = S.pbest_x[base + e];
-        V.pbx[e] = pv;
+    {   // loads first, stores after: S.pbest_x is read and written through the same pointer, so interleaved iterations would serialise
+        float pv[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int e = tid + k * MBX_NT;
+            pv[k] = 0.f;
+            if (e < NP * D) pv[k] = V.better[e / D] ? V.xs[e] : S.pbest_x[base + e];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int e = tid + k * MBX_NT;
+            if (e < NP * D) {
+                if (V.better[e / D]) S.pbest_x[base + e] = pv[k];
+                V.pbx[e] = pv[k];
+            }
+        }
     }
     if (gb_better)
         for (int d = tid; d < D; d += MBX_NT) { V.gx[d] = (double)V.xs[ix * D + d]; S.gbest_x[(size_t)b * D + d] = V.xs[ix * D + d]; }
