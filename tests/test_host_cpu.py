@@ -1414,3 +1414,34 @@ def test_fused_policy_headers_with_random_weights():
         act = np.empty(7, np.float32)
         assert L.rpp_host_forward(xs.ctypes.data_as(fp), w.ctypes.data_as(fp), nz.ctypes.data_as(fp), act.ctypes.data_as(fp), None, None, 7, 2 * dim) == 0
         np.testing.assert_allclose(act, rp(torch.as_tensor(xs), noise=torch.as_tensor(nz)[:, None]).numpy()[:, 0], rtol=1e-5, atol=2e-6)
+
+
+def test_tester_checks_policy_classes_against_the_backbone():
+    """A policy object of another backbone is rejected up front (it used to fail deep inside torch with a dtype error); unknown callables
+    (user policies) pass."""
+    from metabox_b200 import agent as ma, tester as mt
+    with pytest.raises(ValueError):
+        mt._check_policy('nrlpso', ma.RLEPSO_Actor())
+    with pytest.raises(ValueError):
+        mt._check_policy('rlepso', ma.DE_DDQN_Net())
+    mt._check_policy('rlepso', ma.RLEPSO_Actor())
+    mt._check_policy('qlpso', ma.QLPSO_QTable(np.zeros((4, 4))))
+    mt._check_policy('nrlpso', ma.QLPSO_QTable(np.zeros((4, 4))))
+    mt._check_policy('gleet', lambda state: state[..., 0])
+
+
+def test_gather_results_rejects_more_rows_than_promised():
+    """`n_max` is the caller's promise about the largest per-rank row count: breaking it is an error, not a truncated gather."""
+    import torch
+    import torch.distributed as dist
+    from metabox_b200 import sweep
+    res = dict(curve=torch.zeros(5, 51), fes=torch.zeros(5, dtype=torch.int32), ret=torch.zeros(5))
+    assert sweep.gather_results(res, 1, n_max=3).shape == (5, 53)          # world 1: no collective, nothing to check
+    if not (dist.is_available() and dist.is_initialized()):
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29577')
+        dist.init_process_group('gloo', rank=0, world_size=1)
+        try:
+            with pytest.raises(ValueError):
+                sweep.gather_results(res, 2, n_max=3)
+        finally:
+            dist.destroy_process_group()
