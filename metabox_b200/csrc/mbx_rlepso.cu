@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include "mbx_eval.cuh"
 #include "mbx_launch.h"
+#include "mbx_fdr.cuh"
 
 
 #ifdef MBX_PROFILE
@@ -133,84 +134,13 @@ __device__ __forceinline__ bool log_and_done(const MbxRunConfig& cfg, bool has_o
     return done;
 }
 
-// FDR pass 1: float32 screening (see the comment at the call site).  Work item = (pair of 2-rank blocks {m, nb-1-m},
-// pair of dimensions): every item scans ~NP candidates.  Sign convention: a = pf[s]-pf[r] <= 0; the carried best is
-// (nab, bb) = (-a_best, q_best); candidate wins iff  a*bb + nab*q < 0.
 // Compile-time tuning knobs (defaults = the measured configuration; scripts/variant_sweep.sh builds and benches alternatives):
-#ifndef MBX_FDR_UNROLL
-#define MBX_FDR_UNROLL 2            // unroll factor of the FDR candidate scan
-#endif
 #ifndef MBX_RLEPSO_MIN_CTAS
 #define MBX_RLEPSO_MIN_CTAS 4       // __launch_bounds__ minimum CTAs per SM of the step kernel (4 -> 128 registers)
 #endif
 #ifndef MBX_RLEPSO_P2_CH
 #define MBX_RLEPSO_P2_CH 12         // elements per thread whose x / v loads are issued ahead in the velocity phase
 #endif
-#define MBX_PRAGMA_(x) _Pragma(#x)
-#define MBX_UNROLL(n) MBX_PRAGMA_(unroll n)
-#define FDR_TAU 1e-6f
-#define FDR_TINY 1e-35f
-#define FDR_NEAR 2e-4f
-struct FdrChain {          // two ranks x two dims
-    float2 nab, bb;
-    int jx, jy;
-    bool amb;
-};
-__device__ __forceinline__ void fdr_visit(FdrChain& c, const float2 s2, const float2 x2, const float2 npf, const float2 npx, const int s) {
-    const float2 a = __fadd2_rn(s2, npf);
-    const float2 dq = __fadd2_rn(x2, npx);
-    const float2 q = make_float2(fabsf(dq.x) + 1e-5f, fabsf(dq.y) + 1e-5f);
-    const float2 nr = __fmul2_rn(c.nab, q);
-    const float2 m = __ffma2_rn(a, c.bb, nr);
-    const float2 t = __ffma2_rn(nr, make_float2(FDR_TAU, FDR_TAU), make_float2(FDR_TINY, FDR_TINY));
-    c.amb = c.amb || !(fabsf(m.x) > t.x) || !(fabsf(m.y) > t.y);
-    if (m.x < 0.f) { c.nab.x = -a.x; c.bb.x = q.x; c.jx = s; }
-    if (m.y < 0.f) { c.nab.y = -a.y; c.bb.y = q.y; c.jy = s; }
-}
-template <int D>
-__device__ __forceinline__ void fdr_screen(const int NP, const int tid, const float* __restrict__ spx, const float2* __restrict__ spf2,
-                                           const unsigned char* __restrict__ order, unsigned char* tgt, unsigned short* fbl, int* nfb) {
-    static_assert(D % 2 == 0, "the packed FDR scan pairs adjacent dimensions");
-    constexpr int DP = D / 2;
-    const int nb = (NP + 1) / 2, npair = (nb + 1) / 2;
-    const float pf0 = spf2[0].x;
-    for (int w = tid; w < npair * DP; w += MBX_NT) {
-        const int pq = w / DP, d = 2 * (w - pq * DP);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int m = half ? nb - 1 - pq : pq;
-            if (half && m == pq) break;
-            const int ra = 2 * m, rb = ra + 1;
-            const bool hasb = rb < NP;
-            const float2 pxa = *reinterpret_cast<const float2*>(spx + ra * D + d), pfa = spf2[ra];
-            const float2 pxb = hasb ? *reinterpret_cast<const float2*>(spx + rb * D + d) : pxa, pfb = hasb ? spf2[rb] : pfa;
-            const float2 npxa = make_float2(-pxa.x, -pxa.y), npfa = make_float2(-pfa.x, -pfa.y);
-            const float2 npxb = make_float2(-pxb.x, -pxb.y), npfb = make_float2(-pfb.x, -pfb.y);
-            FdrChain A{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), ra, ra, false};      // start from j = i (ratio 0)
-            FdrChain B{make_float2(0.f, 0.f), make_float2(1e-5f, 1e-5f), rb, rb, false};
-            MBX_UNROLL(MBX_FDR_UNROLL)
-            for (int s = 0; s < ra; ++s) {
-                const float2 x2 = *reinterpret_cast<const float2*>(spx + s * D + d), s2 = spf2[s];
-                fdr_visit(A, s2, x2, npfa, npxa, s);
-                fdr_visit(B, s2, x2, npfb, npxb, s);
-            }
-            if (hasb) fdr_visit(B, pfa, pxa, npfb, npxb, ra);                  // candidate s = ra for the block's second rank
-            // best-cost group (pf[r] == pf[0]): every candidate ties with j = i at quotient 0, np.argmin takes the lowest
-            // original index = sorted position 0 (stable sort).  Plateaus (Gallagher, step functions) make this group large.
-            if (pfa.x == pf0) { A.jx = A.jy = 0; A.amb = false; }
-            if (pfb.x == pf0) { B.jx = B.jy = 0; B.amb = false; }
-            const int oa = order[ra] * D + d;
-            tgt[oa] = (unsigned char)A.jx; tgt[oa + 1] = (unsigned char)A.jy;
-            if (A.amb) { const int k = atomicAdd(nfb, 2); fbl[k] = (unsigned short)(ra * D + d); fbl[k + 1] = (unsigned short)(ra * D + d + 1); }
-            if (hasb) {
-                const int ob = order[rb] * D + d;
-                tgt[ob] = (unsigned char)B.jx; tgt[ob + 1] = (unsigned char)B.jy;
-                if (B.amb) { const int k = atomicAdd(nfb, 2); fbl[k] = (unsigned short)(rb * D + d); fbl[k + 1] = (unsigned short)(rb * D + d + 1); }
-            }
-        }
-    }
-}
-
 // =====================================================================================================
 template <int D, int KIND>
 __global__ void __launch_bounds__(MBX_NT)

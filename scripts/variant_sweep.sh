@@ -3,7 +3,7 @@
 #   step 2 (GPU box):                   bash scripts/variant_sweep.sh bench     -> gpurun_out/variants.txt
 # Every variant must pass the bit-exact RLEPSO device tests before its number counts (the `bench` step runs them first).
 set -e
-VARIANTS="fdr1:-DMBX_FDR_UNROLL=1 fdr4:-DMBX_FDR_UNROLL=4 ctas3:-DMBX_RLEPSO_MIN_CTAS=3 fdr4ctas3:-DMBX_FDR_UNROLL=4,-DMBX_RLEPSO_MIN_CTAS=3 p2ch6:-DMBX_RLEPSO_P2_CH=6 p2ch24:-DMBX_RLEPSO_P2_CH=24"
+VARIANTS=${VARIANTS:-"fdr1:-DMBX_FDR_UNROLL=1 fdr4:-DMBX_FDR_UNROLL=4 ctas3:-DMBX_RLEPSO_MIN_CTAS=3 fdr4ctas3:-DMBX_FDR_UNROLL=4,-DMBX_RLEPSO_MIN_CTAS=3 p2ch6:-DMBX_RLEPSO_P2_CH=6 p2ch24:-DMBX_RLEPSO_P2_CH=24"}
 if [ "$1" = "build" ]; then
   for v in $VARIANTS; do
     name=${v%%:*}; defs=$(echo ${v#*:} | tr ',' ' ')
