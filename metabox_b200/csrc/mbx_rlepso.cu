@@ -281,16 +281,15 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     // ---- P1: FDR targets  argmin_j (pf[j]-pf[i]) / (|px[j,d]-px[i,d]|+1e-5), first minimum   (:97-103) ----
     // The minimum is <= 0 (j = i gives 0), so only particles with a strictly better pbest -- the ones BEFORE i in the
     // sorted order -- can win (equal costs tie with j = i at ratio 0 and are resolved by the index rule).
-    // Pass 1 (all items): float32 screening by cross-multiplication  a/q < a'/q'  <=>  a q' < a' q  (q, q' > 0) on the
-    // float32 inputs, packed f32x2 over two adjacent dimensions, two ranks per thread (4 independent chains).  Every
-    // comparison whose margin is below TAU (>= 3x the worst-case float32 rounding of both sides), or is NaN, marks the
-    // (rank, d) item ambiguous.  Pass 2 (ambiguous items only, compacted): the reference's own float64 divisions and
-    // first-index argmin.  An unambiguous float32 winner beats every other candidate by > 1e-6 relative, so the float64
-    // quotients are ordered the same way and the result equals np.argmin exactly.
+    // Pass 1 (all items): float32 screening (mbx_fdr.cuh: quotient keys a * rcp(q) carrying the candidate's position, smallest and second
+    // smallest key per item); an item whose two smallest keys are closer than the rounding bound, or whose costs leave the range the bound
+    // covers, is marked ambiguous.  Pass 2 (ambiguous items only, compacted): the reference's own float64 divisions and first-index argmin.
+    // An unambiguous float32 winner beats every other candidate by more than the error of both keys, so the float64 quotients are ordered
+    // the same way and the result equals np.argmin exactly.
     fdr_screen<D>(NP, tid, spx, spf2, V.order, V.tgt, V.fbl, V.nfb);
     __syncthreads();
     {
-        // Pass 2, eight lanes per ambiguous item: the float32 winner js sits within ~1e-4 (100 replacements x 5.4e-7) of the
+        // Pass 2, eight lanes per ambiguous item: the float32 winner js sits within 3.3e-5 (two key errors) of the
         // true minimum, so only candidates whose float32 quotient is within FDR_NEAR of it can be the float64 argmin; those
         // (a handful) get the reference's float64 division, and the (quotient, original index) minimum is reduced by shuffles.
         const int nfb = *V.nfb, grp = tid >> 3, gl = tid & 7;
@@ -299,14 +298,16 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             const int k = k0 + grp;
             const bool on = k < nfb;
             const int item = on ? V.fbl[k] : 0, r = item / D, d = item - r * D;
-            const int jb = V.tgt[V.order[r] * D + d];                 // float32 winner (sorted position, == r for "self")
+            const int jt = V.tgt[V.order[r] * D + d];                 // float32 winner (sorted position, == r for "self")
+            const bool every = jt == FDR_NO_WINNER;                   // no usable winner: the float64 division for every candidate
+            const int jb = every ? r : jt;
             const float pxr = spx[r * D + d], pfr = spf2[r].x;
             const float ab = spf2[jb].x - pfr, qb = fabsf(spx[jb * D + d] - pxr) + 1e-5f;
             double best = 0.; int bs = r, bo = V.order[r];            // j = i: quotient 0
             for (int s = gl; s < r && on; s += 8) {
                 const float a = spf2[s].x - pfr, dq = spx[s * D + d] - pxr, q = fabsf(dq) + 1e-5f;
                 const float lhs = a * qb, rhs = ab * q;               // a/q vs ab/qb (both <= 0)
-                if (!(fabsf(lhs - rhs) > fmaf(fabsf(rhs), FDR_NEAR, FDR_TINY)) || s == jb) {
+                if (every || !(fabsf(lhs - rhs) > fmaf(fabsf(rhs), FDR_NEAR, FDR_TINY)) || s == jb) {
                     const double a64 = (double)spf2[s].x - (double)pfr;
                     const double q64 = a64 == 0. ? 0. : a64 / (fabs((double)spx[s * D + d] - (double)pxr) + 1e-5);
                     const int o = V.order[s];

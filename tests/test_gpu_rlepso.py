@@ -262,6 +262,16 @@ def test_fdr_targets_exact_incl_ties_duplicates_and_converged_swarms(dim):
     cases.append(('huge costs', px, g.uniform(0, 1, NP) * 1e30))
     cases.append(('tiny costs', px, g.uniform(0, 1, NP) * 1e-30))
     pf8 = pf.copy(); pf8[0:99:3] = pf8[1:100:3]; px8 = np.round(px * 4) / 4; cases.append(('grid positions + cost ties', px8, pf8))
+    # near ties: equal distances (grid) and costs a few float32 ulps apart -> quotients 1e-7 .. 1e-5 apart, inside the resolution of the
+    # screening keys (7 mantissa bits carry the candidate's position) but distinct in float64: every such item must go through pass 2
+    base9 = np.float32(40.0); ulp = np.spacing(base9)
+    pf9 = (base9 + ulp * g.randint(0, 400, NP)).astype(np.float32).astype(np.float64); pf9[::7] = g.uniform(50, 60, len(pf9[::7]))
+    cases.append(('grid positions + costs ulps apart', np.round(px * 2) / 2, pf9))
+    # the same on a continuous cloud: quotients of different candidates within 1e-5 relative by construction of the costs
+    px10 = g.uniform(-5, 5, (NP, dim)); r10 = np.abs(px10[:, :1] - px10[0, 0]) + 1e-5
+    pf10 = 100.0 - r10[:, 0] * (1.0 + 1e-5 * g.uniform(-1, 1, NP)); pf10[0] = 100.0; cases.append(('quotients within 1e-5', px10, pf10))
+    cases.append(('costs of both signs, spread over 12 decades', px, np.sign(g.uniform(-1, 1, NP)) * 10.0 ** g.uniform(-6, 6, NP)))
+    cases.append(('costs up to the float32 maximum', px, g.uniform(0, 1, NP) * 3e38))
     B = len(cases)
     eng = mo.RLEPSO_Engine(pack, [0] * B, 2000 * dim, 50, seed=1)
     eng.init_population()
