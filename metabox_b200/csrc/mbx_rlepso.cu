@@ -26,32 +26,8 @@ extern "C" int mbx_prof_read(unsigned long long* h16, int reset) {
 struct RlLayout {
     int NP, NPp;
     size_t oConst, oA, oSpf, oR1, oR2, oGco, oRank, oOrder, oTileEnd, oGx, oTmpf, oUr, oXs, oF, oPni, oMask, oRed, bytes;
-    // `move_only`: the layout of rlepso_move_kernel (P0-P2 only: no instance constants, no evaluation scratch, no cost arrays besides
-    // pf32); the list of ambiguous FDR items gets its own region (NP*D u16)
-    __host__ __device__ RlLayout(int np, int D, int kConst, bool protein, bool move_only = false) {
+    __host__ __device__ RlLayout(int np, int D, int kConst, bool protein) {
         NP = np; NPp = (np + 3) & ~3;
-        if (move_only) {
-            oConst = 0;
-            oA = 0;                                              // spx f32 [NP*D] | tgt u8 [NP*D]
-            oSpf = oA + (sizeof(float) + 1) * (size_t)NPp * D;
-            oSpf = (oSpf + 15) & ~(size_t)15;
-            oR1 = oSpf + sizeof(float2) * NPp;
-            oR2 = oR1 + 4 * NPp;
-            oGco = (oR2 + 4 * NPp + 7) & ~(size_t)7;
-            oRank = oGco + sizeof(double) * 26;
-            oOrder = oRank + NPp;
-            oTileEnd = oOrder + NPp;
-            oGx = (oTileEnd + 7) & ~(size_t)7;
-            oTmpf = oGx + sizeof(double) * D;
-            oUr = oTmpf;
-            oXs = (oUr + 15) & ~(size_t)15;                      // fbl u16 [NP*D]
-            oF = oXs + sizeof(unsigned short) * NPp * D;         // pf32 only
-            oPni = oF + sizeof(float) * NPp;
-            oMask = oPni;                                        // particle -> coefficient group u8 [NP]
-            oRed = (oMask + NPp + 15) & ~(size_t)15;
-            bytes = oRed + 96;
-            return;
-        }
         const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)(D + 1) * NPp;   // bbob_eval_cta tile [NP][D+1]
         const size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
@@ -186,38 +162,33 @@ rlepso_init_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 }
 
 // =====================================================================================================
-// PH selects the phases of a generation the kernel runs: RL_ALL = the fused step (P0-P6, one launch per generation); RL_MOVE = P0-P2 (ranks,
-// FDR targets, velocity / position: no fitness code, no instance constants -> 24 KB of shared memory and fewer registers, so more CTAs per SM
-// for the part of the step that is bound by instruction issue and latency); RL_EVAL = P3-P6 (fitness of the positions RL_MOVE wrote, pbest /
-// gbest, re-initialisation, log).  MOVE followed by EVAL leaves exactly the bits of ALL: same code, same order, the hand-over is the HBM state.
-#define RL_ALL 0
-#define RL_MOVE 1
-#define RL_EVAL 2
-#ifndef MBX_RLEPSO_MOVE_MIN_CTAS
-#define MBX_RLEPSO_MOVE_MIN_CTAS 6
-#endif
-template <int D, int KIND, int PH>
-__global__ void __launch_bounds__(MBX_NT, PH == RL_MOVE ? MBX_RLEPSO_MOVE_MIN_CTAS : MBX_RLEPSO_MIN_CTAS)
+// TEST = true is the instantiation the parity tests drive: draws may come from a tape of the oracle's float64 uniforms (cfg.use_tape) and
+// the FDR targets can be written out (dbg).  TEST = false, what every sweep launches, contains neither: the tape's loads, 64-bit address
+// arithmetic and branches were issued (predicated off) for every element of the product path before.  Same source otherwise; the device
+// tests compare the two instantiations bit for bit on Philox draws (tests/test_gpu_rlepso.py).
+template <int D, int KIND, bool TEST>
+__global__ void __launch_bounds__(MBX_NT, MBX_RLEPSO_MIN_CTAS)
 rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__ consts, const int32_t* __restrict__ lane_inst,
                    MbxRunConfig cfg, MbxRlepsoState S, MbxRlepsoTape T, const double* __restrict__ pci,
                    const float* __restrict__ action, float* __restrict__ feature, float* __restrict__ reward,
                    int32_t* __restrict__ dbg) {
     const int b = blockIdx.x;
-    if (S.done[b]) { if (PH != RL_MOVE && threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
+    if (S.done[b]) { if (threadIdx.x == 0) reward[b] = 0.f; return; }      // finished lane: state frozen, reward 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PROF_INIT
     const int NP = cfg.NP, tid = threadIdx.x;
-    const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN, PH == RL_MOVE);
+    const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN);
     RlepsoViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
-    if (PH != RL_MOVE) stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b];
     Philox ph(cfg.seed);
     // the pbest_x rows are requested NOW (NP * D / 128 <= D values per thread, NP <= 128) and scattered into their rank order after P0b:
     // their DRAM latency hides behind the constant staging, P0 and the rank loop instead of being exposed between two barriers
     float pbx[D];
-    if (PH != RL_EVAL) {
+    {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             const int e = tid + k * MBX_NT;
@@ -225,21 +196,19 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         }
     }
     // ---- P0: per-particle scalars, draws, coefficients (:112-132) -------------------------------------------
-    if (PH != RL_EVAL)
-        for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
+    for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
     if (tid < NP) {
         const int i = tid;
         V.pf32[i] = S.pbest[pb + i];
-        if (PH != RL_MOVE) { V.cc[i] = S.c_cost[pb + i]; V.pni[i] = S.pni[pb + i]; }
-        if (!cfg.use_tape) {                                          // tape mode reads its float64 draws from the tape directly
+        V.cc[i] = S.c_cost[pb + i]; V.pni[i] = S.pni[pb + i];
+        if (!use_tape) {                                          // tape mode reads its float64 draws from the tape directly
             uint4 w4 = ph((uint32_t)i, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_P);
-            if (PH != RL_EVAL) { V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
-            if (PH != RL_MOVE) V.uru[i] = w4.z;
+            V.r1u[i] = w4.x; V.r2u[i] = w4.y; V.uru[i] = w4.z;
         }
     }
     if (tid < 5) {                                                   // float32 coefficient math (numpy-2 promotion)
         const float* a = action + (size_t)b * 35 + tid * 5;
-        if (PH != RL_EVAL) {
+        {
             const float a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6];
             const float w = a1 * 0.8f + 0.1f;
             float ssum = a3 + a4; ssum = ssum + a5; ssum = ssum + a6; ssum = ssum + 1e-5f;
@@ -248,18 +217,16 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             gc[0] = (double)w; gc[1] = (double)(scale * a3); gc[2] = (double)(scale * a4);
             gc[3] = (double)(scale * a5); gc[4] = (double)(scale * a6);
         }
-        if (PH != RL_MOVE) V.a0c[tid] = a[0] * 0.01f;                 // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
+        V.a0c[tid] = a[0] * 0.01f;                 // c_mutation = float32(a0 * 0.01) * per_no_improve (:119)
     }
-    if (PH != RL_EVAL && tid < NP) {                                 // coefficient group of every particle, 20 % of the swarm each (:113-118): the
+    if (tid < NP) {                                                  // coefficient group of every particle, 20 % of the swarm each (:113-118): the
         const int per = NP / 5;                                       // run-time division happens once per particle here, not once per (i, d) in P2
         V.mask[tid] = (unsigned char)min(tid / per, 4);
     }
-    if (PH == RL_EVAL)                                                // the positions the move kernel wrote
-        for (int e = tid; e < NP * D; e += MBX_NT) V.xs[e] = S.x[base + e];
     __syncthreads();
     PROF_MARK(0);
-    const double lb = PH == RL_MOVE ? gi->lb : V.h->lb, ub = PH == RL_MOVE ? gi->ub : V.h->ub, vmax = 0.1 * (ub - lb);
-    if (PH != RL_EVAL) {
+    const double lb = V.h->lb, ub = V.h->ub, vmax = 0.1 * (ub - lb);
+    {
     // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
     float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
     float2* spf2 = V.spf2;                               // sorted pbest, duplicated (f, f) for the packed FDR scan
@@ -344,7 +311,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         if (e >= NP * D) break;
         const int i = e / D, d = e - i * D;
         double ru, fu; int t0, t1;
-        if (cfg.use_tape) {
+        if (use_tape) {
             ru = T.clpso_u[base + e]; fu = T.fdr_u[base + e];
             t0 = T.tour[(base + e) * 2]; t1 = T.tour[(base + e) * 2 + 1];
         } else {
@@ -357,9 +324,9 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         const double own = (ru > pci[i]) ? pxi : (double)spx[V.rank[tsel] * D + d];
         const double v_clpso = ru * (own - x);
         const int tg = V.tgt[e];                                       // sorted position of the FDR target
-        if (dbg) dbg[base + e] = V.order[tg];
+        if (TEST && dbg) dbg[base + e] = V.order[tg];
         const double v_fdr = fu * ((double)spx[tg * D + d] - pxi);
-        const double r1 = cfg.use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = cfg.use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
+        const double r1 = use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
         const double v_pbest = r1 * (pxi - x);
         const double v_gbest = r2 * (V.gx[d] - x);
         const double* gc = V.gco + V.mask[i] * 5;                      // group of particle i (table written in P0; `mask` is free until P4)
@@ -367,18 +334,17 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         nv = fmin(fmax(nv, -vmax), vmax);
         double nx = fmin(fmax(x + nv, lb), ub);
         const float nx32 = (float)nx;
-        if (PH == RL_ALL) V.xs[e] = nx32;
+        V.xs[e] = nx32;
         S.x[base + e] = nx32; S.v[base + e] = (float)nv;
     }
     }
-    }   // PH != RL_EVAL
-    if (PH == RL_MOVE) return;
+    }
     const MbxInstance& h = *V.h;
     __syncthreads();
     PROF_MARK(3);
     // ---- P3: fitness of the NP new positions (:68-74, :198) ---------------------------------------------
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, (uint32_t)(cfg.lane_base + b),
-                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP, nullptr, L.NPp,
+                                         MBX_TAG_NOISE, use_tape && T.noise ? T.noise + (size_t)b * 6 * NP : nullptr, NP, nullptr, L.NPp,
                                          V.tile, V.tile_bytes);   // P0-P2 per-particle scratch is dead here: Gallagher peak-table staging tile
     __syncthreads();
     PROF_MARK(4);
@@ -403,7 +369,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         const int per = NP / 5;
         int g = i / per; if (g > 4) g = 4;
         const double cm = (double)V.a0c[g] * (double)pni0;            // float32 coefficient x per_no_improve of the old state
-        const double ur = cfg.use_tape ? T.reinit_u[pb + i] : u01(V.uru[i]);
+        const double ur = use_tape ? T.reinit_u[pb + i] : u01(V.uru[i]);
         mymask = ur < cm * 0.01 * (double)pni;
         V.mask[i] = mymask;
     }
@@ -424,7 +390,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             const int i = e / D;
             if (!V.mask[i]) continue;
             double up, uv;
-            if (cfg.use_tape) { up = T.reinit_pos_u[base + e]; uv = T.reinit_vel_u[base + e]; }
+            if (use_tape) { up = T.reinit_pos_u[base + e]; uv = T.reinit_vel_u[base + e]; }
             else { uint4 w = ph((uint32_t)e, gen, (uint32_t)(cfg.lane_base + b), MBX_TAG_REINIT); up = u01(w.x); uv = u01(w.y); }
             const float p = (float)(lb + (ub - lb) * up);
             const float vv = (float)(-vmax + (vmax - (-vmax)) * uv);
@@ -439,7 +405,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         __syncthreads();
         cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, c2, true, ph, gen, (uint32_t)(cfg.lane_base + b),
                                              MBX_TAG_NOISE2,
-                                             cfg.use_tape && T.noise ? T.noise + (size_t)b * 6 * NP + 3 * NP : nullptr, NP,
+                                             use_tape && T.noise ? T.noise + (size_t)b * 6 * NP + 3 * NP : nullptr, NP,
                                              noisy ? nullptr : V.mask, L.NPp, V.tile, V.tile_bytes);
         __syncthreads();
         int nmask = 0;
@@ -496,51 +462,31 @@ static int launch_init_t(const MbxInstance* inst, const double* consts, const in
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
-// One generation = the fused kernel, or the move kernel followed by the evaluation kernel (same bits; see RL_MOVE above).
-// MBX_RLEPSO_SPLIT=0/1 in the environment overrides the default (read once per process; A/B measurements).
-#ifndef MBX_RLEPSO_SPLIT_DEFAULT
-#define MBX_RLEPSO_SPLIT_DEFAULT 0
-#endif
-static int rl_split() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MBX_RLEPSO_SPLIT"); v = e ? (atoi(e) != 0) : MBX_RLEPSO_SPLIT_DEFAULT; }
-    return v;
+template <int D, int KIND, bool TEST>
+static int launch_step_tt(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                          const MbxRlepsoState* s, const MbxRlepsoTape& t, const double* pci, const float* action,
+                          float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
+    const size_t full = RlLayout(cfg->NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN).bytes;
+    auto kern = rlepso_step_kernel<D, KIND, TEST>;
+    static MbxPerDevice attr_done;
+    if (!attr_done.get()) {
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done.set();
+    }
+    kern<<<B, MBX_NT, full, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
+    MBX_CUDA(cudaGetLastError());
+    return MBX_OK;
 }
+// One generation = one launch.  A tape or a debug buffer selects the TEST instantiation (see the kernel).
 template <int D, int KIND>
 static int launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
                          const MbxRlepsoState* s, const MbxRlepsoTape* tape, const double* pci, const float* action,
                          float* feature, float* reward, int32_t* dbg, int B, cudaStream_t st) {
     MbxRlepsoTape t{};
     if (tape) t = *tape;
-    const size_t full = RlLayout(cfg->NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN).bytes;
-    if (!rl_split()) {
-        auto kern = rlepso_step_kernel<D, KIND, RL_ALL>;
-        static MbxPerDevice attr_done;
-        if (!attr_done.get()) {
-            MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            attr_done.set();
-        }
-        kern<<<B, MBX_NT, full, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
-        MBX_CUDA(cudaGetLastError());
-        return MBX_OK;
-    }
-    auto kmove = rlepso_step_kernel<D, KIND, RL_MOVE>;
-    auto keval = rlepso_step_kernel<D, KIND, RL_EVAL>;
-    static MbxPerDevice attr_done2;
-    if (!attr_done2.get()) {
-        MBX_CUDA(cudaFuncSetAttribute(kmove, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MBX_CUDA(cudaFuncSetAttribute(keval, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MBX_CUDA(cudaFuncSetAttribute(kmove, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        MBX_CUDA(cudaFuncSetAttribute(keval, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done2.set();
-    }
-    const size_t mv = RlLayout(cfg->NP, D, 0, false, true).bytes;
-    kmove<<<B, MBX_NT, mv, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
-    MBX_CUDA(cudaGetLastError());
-    keval<<<B, MBX_NT, full, st>>>(inst, consts, lane_inst, *cfg, *s, t, pci, action, feature, reward, dbg);
-    MBX_CUDA(cudaGetLastError());
-    return MBX_OK;
+    if (cfg->use_tape || dbg) return launch_step_tt<D, KIND, true>(inst, consts, lane_inst, cfg, s, t, pci, action, feature, reward, dbg, B, st);
+    return launch_step_tt<D, KIND, false>(inst, consts, lane_inst, cfg, s, t, pci, action, feature, reward, dbg, B, st);
 }
 
 #define MBX_DISPATCH(FN, ...)                                                                         \

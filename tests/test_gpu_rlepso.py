@@ -283,3 +283,31 @@ def test_fdr_targets_exact_incl_ties_duplicates_and_converged_swarms(dim):
     for b, (name, _, _) in enumerate(cases):
         want = orl.fdr_targets(PX[b].astype(np.float64), PF[b].astype(np.float64))
         np.testing.assert_array_equal(got[b], want, err_msg=f'FDR targets: {name} (dim {dim})')
+
+
+@pytest.mark.parametrize('dim', [10, 30])
+def test_product_and_test_instantiations_of_the_step_kernel_agree_bit_for_bit(dim):
+    """The step kernel is compiled twice (csrc/mbx_rlepso.cu): TEST = true accepts a tape / writes the FDR targets out and is what the
+    oracle parity tests above drive; TEST = false is what every sweep launches.  Same source otherwise -- on Philox draws the two must leave
+    identical bits in every state array, including re-initialisations, noise and lanes that finish."""
+    import torch
+    from metabox_b200 import optimizer as mo, problem as mp
+    probs = []
+    for suit, fids in (('bbob', (1, 7, 16, 21, 24)), ('bbob-noisy', (104, 118, 129))):
+        tr, te = mp.BBOB_Dataset.get_datasets(suit, dim, 5)
+        probs += [[p for p in tr.data + te.data if p.fid == f][0] for f in fids]
+    pack = mp.InstancePack(probs)
+    lanes = list(range(len(probs))) * 3
+    A = mo.RLEPSO_Engine(pack, lanes, 4000, 50, seed=0xA11CE)
+    Bn = mo.RLEPSO_Engine(pack, lanes, 4000, 50, seed=0xA11CE)
+    A.init_population(); Bn.init_population()
+    dbg = torch.full((A.B, A.NP, dim), -1, dtype=torch.int32, device=A.device)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    for gen in range(42):                                   # 4000 FEs: every lane finishes inside the loop
+        action = torch.rand(A.B, 35, generator=g).to(A.device)
+        A.update(action)                                    # TEST = false
+        Bn.update(action, dbg=dbg)                          # TEST = true (debug buffer)
+        for k in ('x', 'v', 'pbest_x', 'pbest', 'c_cost', 'pni', 'gbest_x', 'gbest_val', 'gbest_idx', 'no_improve', 'fes', 'curve',
+                  'curve_len', 'done', 'feature', 'reward'):
+            assert torch.equal(getattr(A, k), getattr(Bn, k)), f'{k} differs after generation {gen}'
+    assert bool((A.done != 0).all()) and int(dbg.min()) >= 0
