@@ -92,11 +92,20 @@ struct Philox {
     }
 };
 
-__device__ __forceinline__ double u01(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+// w / 2^32.  The integer -> float64 conversion instruction (I2F.F64.U32) runs at a quarter of the FP64 rate; 2^52 + w is exact in float64
+// (w sits in the low mantissa bits), so one DADD gives the same value bit for bit.
+__device__ __forceinline__ double u32_to_double(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(0x43300000, (int)w) - 4503599627370496.0;
+#else
+    return (double)w;
+#endif
+}
+__device__ __forceinline__ double u01(uint32_t w) { return u32_to_double(w) * (1.0 / 4294967296.0); }
 __device__ __forceinline__ int bounded(uint32_t w, int high) { return (int)__umulhi(w, (uint32_t)high); }
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& n0, double& n1) {
-    double ua = ((double)wa + 1.0) * (1.0 / 4294967296.0);
-    double ub = (double)wb * (1.0 / 4294967296.0);
+    double ua = (u32_to_double(wa) + 1.0) * (1.0 / 4294967296.0);
+    double ub = u32_to_double(wb) * (1.0 / 4294967296.0);
     double r = sqrt(-2.0 * log(ua));
     double t = 6.283185307179586 * ub;
     double s, c;

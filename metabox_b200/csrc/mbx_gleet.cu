@@ -182,7 +182,9 @@ gleet_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
 }
 
 // =====================================================================================================
-template <int D, int KIND>
+// TEST = true: the instantiation the parity tests drive (tape of the oracle's uniforms); TEST = false: what the sweeps launch, without the
+// tape's loads / address arithmetic / branches (see rlepso_step_kernel)
+template <int D, int KIND, bool TEST>
 #ifndef MBX_GLEET_MIN_CTAS
 #define MBX_GLEET_MIN_CTAS 4        // compile-time knob: minimum CTAs per SM of the step kernel (A/B builds: python -m metabox_b200.build --variant)
 #endif
@@ -198,6 +200,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     GlViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
     stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b], lane = (uint32_t)(cfg.lane_base + b);
     Philox ph(cfg.seed);
@@ -213,7 +216,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
         const float a = action[pb + i];
         V.ca[i] = GL_C * a;
         V.cb[i] = GL_C * (1.f - a);
-        if (!cfg.use_tape) { uint4 w4 = ph((uint32_t)i, gen, lane, MBX_TAG_GLEET_P); V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
+        if (!use_tape) { uint4 w4 = ph((uint32_t)i, gen, lane, MBX_TAG_GLEET_P); V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
     }
     {   // all row loads of a thread are issued before the first shared-memory store (NP * D / 128 <= D values per thread)
         float pr[D];
@@ -242,7 +245,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
             if (e >= NP * D) break;
             const int i = e / D, d = e - i * D;
             const double x = (double)xr[k], v = (double)vr[k];
-            const double r1 = cfg.use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = cfg.use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
+            const double r1 = use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
             double nv = w * v + (double)V.ca[i] * r1 * ((double)V.pbx[e] - x) + (double)V.cb[i] * r2 * (V.gx[d] - x);
             nv = fmin(fmax(nv, -vmax), vmax);
             const double nx = fmin(fmax(x + nv, lb), ub);
@@ -254,7 +257,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     __syncthreads();
     // ---- P2: fitness (:224) ------------------------------------------------------------------------------------------------------
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.xs, NP, 0, V.A, V.nc, true, ph, gen, lane, MBX_TAG_NOISE,
-                                         cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP, nullptr, 0,
+                                         use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP, nullptr, 0,
                                          V.tile, V.tile_bytes);
     __syncthreads();
     // ---- P3: pbest / gbest / patience (:227-274) ------------------------------------------------------------------------------
@@ -360,11 +363,11 @@ static int gl_launch_init_t(const MbxInstance* inst, const double* consts, const
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
-template <int D, int KIND>
-static int gl_launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
-                            const MbxGleetState* s, const MbxGleetTape* tape, const float* action, float* state, float* reward,
-                            int B, cudaStream_t st) {
-    auto kern = gleet_step_kernel<D, KIND>;
+template <int D, int KIND, bool TEST>
+static int gl_launch_step_tt(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                             const MbxGleetState* s, const MbxGleetTape* tape, const float* action, float* state, float* reward,
+                             int B, cudaStream_t st) {
+    auto kern = gleet_step_kernel<D, KIND, TEST>;
     static MbxPerDevice attr_done;
     if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -376,6 +379,13 @@ static int gl_launch_step_t(const MbxInstance* inst, const double* consts, const
     kern<<<B, MBX_NT, gl_layout<D, KIND>(cfg->NP).bytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, action, state, reward);
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
+}
+template <int D, int KIND>
+static int gl_launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                            const MbxGleetState* s, const MbxGleetTape* tape, const float* action, float* state, float* reward,
+                            int B, cudaStream_t st) {
+    if (cfg->use_tape) return gl_launch_step_tt<D, KIND, true>(inst, consts, lane_inst, cfg, s, tape, action, state, reward, B, st);
+    return gl_launch_step_tt<D, KIND, false>(inst, consts, lane_inst, cfg, s, tape, action, state, reward, B, st);
 }
 
 #define MBX_DISPATCH(FN, ...)                                                                         \

@@ -191,7 +191,9 @@ lde_init_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
 }
 
 // =====================================================================================================
-template <int D, int KIND>
+// TEST = true: the instantiation the parity tests drive (tape of the oracle's uniforms, debug buffer); TEST = false: what the sweeps launch,
+// without the tape's loads / address arithmetic / branches (see rlepso_step_kernel)
+template <int D, int KIND, bool TEST>
 #ifndef MBX_LDE_MIN_CTAS
 #define MBX_LDE_MIN_CTAS 4        // compile-time knob: minimum CTAs per SM of the step kernel (A/B builds: python -m metabox_b200.build --variant)
 #endif
@@ -207,6 +209,7 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     LdeViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
     stage_instance<D, KIND>(gi, consts, V.h, V.sC);
+    const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b], lane = (uint32_t)(cfg.lane_base + b);
     const int fes0 = S.fes[b];
@@ -235,7 +238,7 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
         const int i = tid;
         V.sf[i] = action[(size_t)b * 2 * NP + i];
         V.cr[i] = action[(size_t)b * 2 * NP + NP + i];
-        if (cfg.use_tape) {
+        if (use_tape) {
             V.pidx[i] = T.pbest_idx[pb + i]; V.r1[i] = T.r1[pb + i]; V.r2[i] = T.r2[pb + i]; V.jr[i] = T.jrand[pb + i];
         } else {
             const double pmin = 2.0 / (double)NP;                          // P_NUM_MIN / NP
@@ -267,26 +270,26 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
         double mu = xi;
         if (p != i) mu = (double)(1.f - sff) * xi + sf * (double)V.ps[p * D + d];
         mu = mu + sf * ((double)V.ps[V.r1[i] * D + d] - (double)V.ps[V.r2[i] * D + d]);
-        double u = cfg.use_tape ? T.cross_u[base + e] : u01(ph((uint32_t)e, gen, lane, MBX_TAG_LDE_PD).x);
+        double u = use_tape ? T.cross_u[base + e] : u01(ph((uint32_t)e, gen, lane, MBX_TAG_LDE_PD).x);
         if (d == V.jr[i]) u = 0.;
         double t = (u <= (double)V.cr[i]) ? mu : xi;
         if (t < lb) t = (xi + lb) / 2.;
         else if (t > ub) t = (xi + ub) / 2.;
         const float t32 = (float)t;
         V.ts[e] = t32;
-        if (dbg) dbg[(size_t)b * NP * (D + 1) + e] = t32;
+        if (TEST && dbg) dbg[(size_t)b * NP * (D + 1) + e] = t32;
     }
     __syncthreads();
     // ---- P3: fitness of the trials (:54) -------------------------------------------------------------------------------
     // (the evaluation scratch overwrites the parents' shared-memory copy; P5 re-reads the surviving parents from HBM/L2)
     cta_eval_tile<D, KIND, float, float>(h, V.sC, consts + gi->off, V.ts, NP, 0, V.scr, V.tfit, true, ph, gen, lane,
-                                         MBX_TAG_NOISE, cfg.use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP,
+                                         MBX_TAG_NOISE, use_tape && T.noise ? T.noise + (size_t)b * 3 * NP : nullptr, NP,
                                          nullptr, 0, V.tile, V.tile_bytes);
     __syncthreads();
     // ---- P4: selection `<=` (:59-61), reward (:170-173) ------------------------------------------------------------------
     if (tid < NP) {
         const float tf = V.tfit[tid];
-        if (dbg) dbg[(size_t)b * NP * (D + 1) + NP * D + tid] = tf;
+        if (TEST && dbg) dbg[(size_t)b * NP * (D + 1) + NP * D + tid] = tf;
         V.nfit[tid] = (tf <= V.fit[tid]) ? tf : V.fit[tid];
     }
     __syncthreads();
@@ -353,11 +356,11 @@ static int lde_launch_init_t(const MbxInstance* inst, const double* consts, cons
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
 }
-template <int D, int KIND>
-static int lde_launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
-                             const MbxLdeState* s, const MbxLdeTape* tape, const float* action, float* feature, float* reward,
-                             float* dbg, int B, cudaStream_t st) {
-    auto kern = lde_step_kernel<D, KIND>;
+template <int D, int KIND, bool TEST>
+static int lde_launch_step_tt(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                              const MbxLdeState* s, const MbxLdeTape* tape, const float* action, float* feature, float* reward,
+                              float* dbg, int B, cudaStream_t st) {
+    auto kern = lde_step_kernel<D, KIND, TEST>;
     static MbxPerDevice attr_done;
     if (!attr_done.get()) {
         MBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -369,6 +372,13 @@ static int lde_launch_step_t(const MbxInstance* inst, const double* consts, cons
     kern<<<B, MBX_NT, lde_layout<D, KIND>(cfg->NP).bytes, st>>>(inst, consts, lane_inst, *cfg, *s, t, action, feature, reward, dbg);
     MBX_CUDA(cudaGetLastError());
     return MBX_OK;
+}
+template <int D, int KIND>
+static int lde_launch_step_t(const MbxInstance* inst, const double* consts, const int32_t* lane_inst, const MbxRunConfig* cfg,
+                             const MbxLdeState* s, const MbxLdeTape* tape, const float* action, float* feature, float* reward,
+                             float* dbg, int B, cudaStream_t st) {
+    if (cfg->use_tape || dbg) return lde_launch_step_tt<D, KIND, true>(inst, consts, lane_inst, cfg, s, tape, action, feature, reward, dbg, B, st);
+    return lde_launch_step_tt<D, KIND, false>(inst, consts, lane_inst, cfg, s, tape, action, feature, reward, dbg, B, st);
 }
 
 #define MBX_DISPATCH(FN, ...)                                                                         \
