@@ -25,6 +25,15 @@
 #define FDR_NEAR 2e-4f              // pass 2 re-divides the candidates whose float32 quotient is within FDR_NEAR of the screening winner's
 #define FDR_TINY 1e-35f
 
+// the sorted costs live in the float2 array `spf2` of the step kernel: as (f, f) pairs for the packed cross-multiplication scan, as plain
+// consecutive floats for the key scan (two candidates' costs in one 8-byte load)
+#if MBX_FDR_RCP
+#define FDR_COST(spf2, r) (reinterpret_cast<const float*>(spf2)[r])
+__device__ __forceinline__ void fdr_store_cost(float2* spf2, const int r, const float f) { reinterpret_cast<float*>(spf2)[r] = f; }
+#else
+#define FDR_COST(spf2, r) ((spf2)[r].x)
+__device__ __forceinline__ void fdr_store_cost(float2* spf2, const int r, const float f) { spf2[r] = make_float2(f, f); }
+#endif
 // flag the two items (r, d), (r, d + 1) for pass 2
 __device__ __forceinline__ void fdr_flag(unsigned short* fbl, int* nfb, const int item) {
     const int k = atomicAdd(nfb, 2);
@@ -78,9 +87,10 @@ __device__ __forceinline__ void fdr_screen(const int NP, const int tid, const fl
                                            const unsigned char* __restrict__ order, unsigned char* tgt, unsigned short* fbl, int* nfb) {
     static_assert(D % 2 == 0, "the FDR scan pairs adjacent dimensions");
     constexpr int DP = D / 2;
+    const float* __restrict__ spf = reinterpret_cast<const float*>(spf2);
     const int nb = (NP + 1) / 2, npair = (nb + 1) / 2;
-    const float pf0 = spf2[0].x;
-    const int row1 = min(1, NP - 1), rowl = max(NP - 2, 0);
+    const float pf0 = spf[0];
+    const int row1 = min(1, NP - 1);
     for (int w = tid; w < npair * DP; w += MBX_NT) {
         const int pq = w / DP, d = 2 * (w - pq * DP);
 #pragma unroll 1
@@ -90,9 +100,9 @@ __device__ __forceinline__ void fdr_screen(const int NP, const int tid, const fl
             const int ra = 2 * m, rb = ra + 1;
             const bool hasb = rb < NP;
             const float2 pxa = *reinterpret_cast<const float2*>(spx + ra * D + d);
-            const float pfa = spf2[ra].x;
+            const float pfa = spf[ra];
             const float2 pxb = hasb ? *reinterpret_cast<const float2*>(spx + rb * D + d) : pxa;
-            const float pfb = hasb ? spf2[rb].x : pfa;
+            const float pfb = hasb ? spf[rb] : pfa;
             const float2 npxa = make_float2(-pxa.x, -pxa.y), npxb = make_float2(-pxb.x, -pxb.y);
             // j = i: quotient 0, key = the position bits (a +denormal)
             FdrKeys A{__uint_as_float((unsigned)ra), __uint_as_float((unsigned)ra), INFINITY, INFINITY};
@@ -102,17 +112,20 @@ __device__ __forceinline__ void fdr_screen(const int NP, const int tid, const fl
             float2 ka1, ka2, kb1, kb2;
             {
                 const float2 x2 = *reinterpret_cast<const float2*>(spx + d), y2 = *reinterpret_cast<const float2*>(spx + row1 * D + d);
-                const float fs = spf2[0].x, gs = spf2[row1].x;
+                const float fs = spf[0], gs = spf[row1];
                 ka1 = fdr_keys(fs, x2, -pfa, npxa, 0u); ka2 = fdr_keys(gs, y2, -pfa, npxa, 1u);
                 kb1 = fdr_keys(fs, x2, -pfb, npxb, 0u); kb2 = fdr_keys(gs, y2, -pfb, npxb, 1u);
             }
+            const float* px = spx + 2 * D + d;                                  // rows s + 2, s + 3
+            const float* pf = spf + 2;
 #pragma unroll 1
-            for (int s = 0; s < ra; s += 2) {
-                const int sn = min(s + 2, rowl);                                // the last look-ahead is computed and dropped
-                const float2 x2 = *reinterpret_cast<const float2*>(spx + sn * D + d), y2 = *reinterpret_cast<const float2*>(spx + (sn + 1) * D + d);
-                const float fs = spf2[sn].x, gs = spf2[sn + 1].x;
-                const float2 na1 = fdr_keys(fs, x2, -pfa, npxa, (unsigned)sn), na2 = fdr_keys(gs, y2, -pfa, npxa, (unsigned)sn + 1);
-                const float2 nb1 = fdr_keys(fs, x2, -pfb, npxb, (unsigned)sn), nb2 = fdr_keys(gs, y2, -pfb, npxb, (unsigned)sn + 1);
+            for (unsigned s = 2; s <= (unsigned)ra; s += 2, px += 2 * D, pf += 2) {
+                // the look-ahead of the last trip (rows ra, ra + 1 <= NP: at most one row past the sorted copy, still inside the CTA's region
+                // A / cost array) is computed and dropped
+                const float2 x2 = *reinterpret_cast<const float2*>(px), y2 = *reinterpret_cast<const float2*>(px + D);
+                const float2 fg = *reinterpret_cast<const float2*>(pf);
+                const float2 na1 = fdr_keys(fg.x, x2, -pfa, npxa, s), na2 = fdr_keys(fg.y, y2, -pfa, npxa, s + 1);
+                const float2 nb1 = fdr_keys(fg.x, x2, -pfb, npxb, s), nb2 = fdr_keys(fg.y, y2, -pfb, npxb, s + 1);
                 fdr_push2(A.bx, A.sx, ka1.x, ka2.x); fdr_push2(A.by, A.sy, ka1.y, ka2.y);
                 fdr_push2(B.bx, B.sx, kb1.x, kb2.x); fdr_push2(B.by, B.sy, kb1.y, kb2.y);
                 ka1 = na1; ka2 = na2; kb1 = nb1; kb2 = nb2;

@@ -229,12 +229,12 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     {
     // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
     float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
-    float2* spf2 = V.spf2;                               // sorted pbest, duplicated (f, f) for the packed FDR scan
+    float2* spf2 = V.spf2;                               // sorted pbest costs (layout: mbx_fdr.cuh, FDR_COST)
     if (tid < NP) {
         const float fi = V.pf32[tid];
         int r = 0;
         for (int j = 0; j < NP; ++j) { const float fj = V.pf32[j]; r += (fj < fi || (fj == fi && j < tid)) ? 1 : 0; }
-        V.rank[tid] = (unsigned char)r; V.order[r] = (unsigned char)tid; spf2[r] = make_float2(fi, fi);
+        V.rank[tid] = (unsigned char)r; V.order[r] = (unsigned char)tid; fdr_store_cost(spf2, r, fi);
     }
     if (tid == 0) *V.nfb = 0;
     __syncthreads();
@@ -268,14 +268,14 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             const int jt = V.tgt[V.order[r] * D + d];                 // float32 winner (sorted position, == r for "self")
             const bool every = jt == FDR_NO_WINNER;                   // no usable winner: the float64 division for every candidate
             const int jb = every ? r : jt;
-            const float pxr = spx[r * D + d], pfr = spf2[r].x;
-            const float ab = spf2[jb].x - pfr, qb = fabsf(spx[jb * D + d] - pxr) + 1e-5f;
+            const float pxr = spx[r * D + d], pfr = FDR_COST(spf2, r);
+            const float ab = FDR_COST(spf2, jb) - pfr, qb = fabsf(spx[jb * D + d] - pxr) + 1e-5f;
             double best = 0.; int bs = r, bo = V.order[r];            // j = i: quotient 0
             for (int s = gl; s < r && on; s += 8) {
-                const float a = spf2[s].x - pfr, dq = spx[s * D + d] - pxr, q = fabsf(dq) + 1e-5f;
+                const float a = FDR_COST(spf2, s) - pfr, dq = spx[s * D + d] - pxr, q = fabsf(dq) + 1e-5f;
                 const float lhs = a * qb, rhs = ab * q;               // a/q vs ab/qb (both <= 0)
                 if (every || !(fabsf(lhs - rhs) > fmaf(fabsf(rhs), FDR_NEAR, FDR_TINY)) || s == jb) {
-                    const double a64 = (double)spf2[s].x - (double)pfr;
+                    const double a64 = (double)FDR_COST(spf2, s) - (double)pfr;
                     const double q64 = a64 == 0. ? 0. : a64 / (fabs((double)spx[s * D + d] - (double)pxr) + 1e-5);
                     const int o = V.order[s];
                     if (q64 < best || (q64 == best && o < bo)) { best = q64; bs = s; bo = o; }
@@ -299,11 +299,14 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
 #pragma unroll 1
     for (int k0 = 0; k0 * MBX_NT < NP * D; k0 += P2_CH) {
     float xr[P2_CH], vr[P2_CH];
+    // one 64-bit pointer per array and chunk; the elements of the chunk sit at compile-time offsets from it
+    float* const xg = S.x + base + tid + k0 * MBX_NT;
+    float* const vg = S.v + base + tid + k0 * MBX_NT;
 #pragma unroll
     for (int k = 0; k < P2_CH; ++k) {
         const int e = tid + (k0 + k) * MBX_NT;
         xr[k] = 0.f; vr[k] = 0.f;
-        if (e < NP * D) { xr[k] = __ldcs(S.x + base + e); vr[k] = __ldcs(S.v + base + e); }
+        if (e < NP * D) { xr[k] = __ldcs(xg + k * MBX_NT); vr[k] = __ldcs(vg + k * MBX_NT); }
     }
 #pragma unroll
     for (int k = 0; k < P2_CH; ++k) {
@@ -331,11 +334,13 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         const double v_gbest = r2 * (V.gx[d] - x);
         const double* gc = V.gco + V.mask[i] * 5;                      // group of particle i (table written in P0; `mask` is free until P4)
         double nv = gc[0] * v + gc[1] * v_clpso + gc[2] * v_fdr + gc[3] * v_gbest + gc[4] * v_pbest;
-        nv = fmin(fmax(nv, -vmax), vmax);
-        double nx = fmin(fmax(x + nv, lb), ub);
+        // np.clip as two compares and selects each (fmin / fmax add NaN handling the reference does not have: np.clip keeps a NaN)
+        nv = nv < -vmax ? -vmax : nv; nv = nv > vmax ? vmax : nv;
+        double nx = x + nv;
+        nx = nx < lb ? lb : nx; nx = nx > ub ? ub : nx;
         const float nx32 = (float)nx;
         V.xs[e] = nx32;
-        S.x[base + e] = nx32; S.v[base + e] = (float)nv;
+        xg[k * MBX_NT] = nx32; vg[k * MBX_NT] = (float)nv;
     }
     }
     }

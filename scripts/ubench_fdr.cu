@@ -33,7 +33,7 @@ fdr_bench(const float* __restrict__ gx, const float* __restrict__ gf, unsigned l
     int* nfb = reinterpret_cast<int*>(fbl + NP * D);
     const int tid = threadIdx.x, b = blockIdx.x;
     for (int e = tid; e < NP * D; e += 128) spx[e] = gx[(size_t)(b % 64) * NP * D + e];
-    if (tid < NP) { const float f = gf[(b % 64) * NP + tid]; spf2[tid] = make_float2(f, f); order[tid] = (unsigned char)tid; }
+    if (tid < NP) { const float f = gf[(b % 64) * NP + tid]; fdr_store_cost(spf2, tid, f); order[tid] = (unsigned char)tid; }
     unsigned long long acc = 0; int amb = 0;
     for (int r = 0; r < REP; ++r) {
         if (tid == 0) *nfb = 0;
