@@ -292,7 +292,7 @@ __device__ __forceinline__ float dd_step_core(const MbxRunConfig& cfg, const Mbx
         else if (a == 1) v = x(r0) + F * (x(r1) - x(r2) + x(r3) - x(r4));
         else if (a == 2) v = x(r0) + F * ((double)Xg[d] - x(r0) + x(r1) - x(r2) + x(r3) - x(r4));
         else v = x(p) + F * (x(r0) - x(p) + x(r1) - x(r2));
-        v = fmin(fmax(v, lb), ub);
+        v = v < lb ? lb : v; v = v > ub ? ub : v;               // np.clip (keeps a NaN, unlike fmin / fmax)
         const float t32 = (float)v;
         trial[d] = t32;
         if (dbg) dbg[d] = t32;

@@ -233,11 +233,14 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
 #pragma unroll 1
     for (int k0 = 0; k0 * MBX_NT < NP * D; k0 += CH) {
         float xr[CH], vr[CH];
+        // one 64-bit pointer per array and chunk; the elements of the chunk sit at compile-time offsets from it
+        float* const xg = S.x + base + tid + k0 * MBX_NT;
+        float* const vg = S.v + base + tid + k0 * MBX_NT;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
             const int e = tid + (k0 + k) * MBX_NT;
             xr[k] = 0.f; vr[k] = 0.f;
-            if (e < NP * D) { xr[k] = __ldcs(S.x + base + e); vr[k] = __ldcs(S.v + base + e); }
+            if (e < NP * D) { xr[k] = __ldcs(xg + k * MBX_NT); vr[k] = __ldcs(vg + k * MBX_NT); }
         }
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
@@ -247,11 +250,13 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
             const double x = (double)xr[k], v = (double)vr[k];
             const double r1 = use_tape ? T.rand1[pb + i] : u01(V.r1u[i]), r2 = use_tape ? T.rand2[pb + i] : u01(V.r2u[i]);
             double nv = w * v + (double)V.ca[i] * r1 * ((double)V.pbx[e] - x) + (double)V.cb[i] * r2 * (V.gx[d] - x);
-            nv = fmin(fmax(nv, -vmax), vmax);
-            const double nx = fmin(fmax(x + nv, lb), ub);
+            // np.clip as two compares and selects each (fmin / fmax add NaN handling the reference does not have: np.clip keeps a NaN)
+            nv = nv < -vmax ? -vmax : nv; nv = nv > vmax ? vmax : nv;
+            double nx = x + nv;
+            nx = nx < lb ? lb : nx; nx = nx > ub ? ub : nx;
             const float nx32 = (float)nx;
             V.xs[e] = nx32;
-            S.x[base + e] = nx32; S.v[base + e] = (float)nv;
+            xg[k * MBX_NT] = nx32; vg[k * MBX_NT] = (float)nv;
         }
     }
     __syncthreads();

@@ -182,7 +182,8 @@ qlpso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
         const double x = (double)xs[i * D + d], v = (double)S.v[row + d], pbx = (double)S.pbest_x[row + d];
         const double nbx = (double)xs[nb * D + d];
         const double nv = QL_W * v + QL_C * r1 * (nbx - x) + QL_C * r2 * (pbx - x);
-        const double nx = fmin(fmax(x + nv, lb), ub);
+        double nx = x + nv;
+        nx = nx < lb ? lb : nx; nx = nx > ub ? ub : nx;
         const float nx32 = (float)nx;
         trial[d] = nx32;
         S.x[row + d] = nx32; S.v[row + d] = (float)nv;

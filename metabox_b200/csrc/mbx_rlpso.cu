@@ -113,8 +113,9 @@ rlpso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
         const double x = (double)S.x[row + d], v = (double)S.v[row + d], pbx = (double)S.pbest_x[row + d];
         const double gx = (double)S.gbest_x[(size_t)b * D + d];
         double nv = w * v + RP_C * rand1 * (pbx - x) + (double)c2 * (gx - x);
-        nv = fmin(fmax(nv, -vmax), vmax);
-        const double nx = fmin(fmax(x + nv, lb), ub);
+        nv = nv < -vmax ? -vmax : nv; nv = nv > vmax ? vmax : nv;      // np.clip (keeps a NaN, unlike fmin / fmax)
+        double nx = x + nv;
+        nx = nx < lb ? lb : nx; nx = nx > ub ? ub : nx;
         const float nx32 = (float)nx;
         trial[d] = nx32;
         S.x[row + d] = nx32; S.v[row + d] = (float)nv;
