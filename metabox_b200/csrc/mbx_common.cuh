@@ -113,6 +113,34 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& n0,
     n0 = r * c; n1 = r * s;
 }
 
+// Order-preserving 32-bit key of a float32 cost for an ascending sort: -0 == +0, NaN last (np.argsort puts NaN at the end).
+__device__ __forceinline__ unsigned order_key(const float f) {
+    if (f != f) return 0xFFFFFFFFu;
+    const unsigned u = __float_as_uint(f + 0.f);                       // -0 + 0 = +0
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// Stable ascending rank of one float32 cost per thread (threads >= n do not take part in the order) by a bitonic network over the 128
+// threads of a CTA: the items are (order_key, thread index) in 64 bits, so the order is total and ties resolve by index like a stable
+// sort.  25 of the 28 compare-exchange stages are warp shuffles; the 3 with a partner in another warp go through `xch` (128 x 8 bytes of
+// shared memory that is dead at the call site).  ~10 instructions per stage instead of ~14 per PAIR of the all-pairs count it replaces.
+// All 128 threads must call.  Returns the index of the item that ends at position threadIdx.x (valid for threadIdx.x < n).
+__device__ __forceinline__ int block_sort_order_128(const float f, const int n, unsigned long long* xch) {
+    const int t = threadIdx.x;
+    unsigned long long v = t < n ? ((unsigned long long)order_key(f) << 32) | (unsigned)t : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long o;
+            if (j < 32) o = __shfl_xor_sync(0xffffffffu, v, j);
+            else { xch[t] = v; __syncthreads(); o = xch[t ^ j]; __syncthreads(); }
+            const bool takemin = ((t & j) == 0) == ((t & k) == 0);   // lower item of an ascending pair / upper item of a descending one
+            v = ((o < v) == takemin) ? o : v;
+        }
+    }
+    return (int)(unsigned)(v & 0xFFFFFFFFull);
+}
+
 // (value, index) lexicographic minimum == np.argmin first-occurrence rule
 __device__ __forceinline__ void argmin_pair(float& v, int& i, float ov, int oi) {
     if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }

@@ -223,9 +223,16 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
         popr[k] = e < NP * D ? __ldcs(S.pop + base + e) : 0.f;
     }
     // ---- P0: order_by_f (:160) -- the stored state is sorted already, re-ranked for safety -------------------
-    if (tid < NP) V.nfit[tid] = S.fit[pb + tid];
-    __syncthreads();
-    lde_rank(V.nfit, V.rank, NP);
+    {
+        // the stored state IS sorted (P5 below and the init kernel write it in rank order): the rank is the identity unless some pair of
+        // neighbours is out of order (a state written by somebody else), and only then is it computed
+        const float fi = tid < NP ? S.fit[pb + tid] : 0.f;
+        if (tid < NP) V.nfit[tid] = fi;
+        __syncthreads();
+        const bool bad = tid > 0 && tid < NP && lde_before(fi, tid, V.nfit[tid - 1], tid - 1);
+        if (__syncthreads_or(bad ? 1 : 0)) lde_rank(V.nfit, V.rank, NP);
+        else if (tid < NP) V.rank[tid] = tid;
+    }
     __syncthreads();
     if (tid < NP) { V.fit[V.rank[tid]] = V.nfit[tid]; V.src[V.rank[tid]] = (unsigned char)tid; }
 #pragma unroll
@@ -298,7 +305,11 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     const int fes = fes0 + NP;
     const bool done = h.has_optimum ? (fes >= cfg.maxFEs || (double)nmin <= 1e-8) : (fes >= cfg.maxFEs);
     // ---- P5: re-sort the survivors (__get_feature :146) and write the state back --------------------------------------------
-    lde_rank(V.nfit, V.rank, NP);
+    {
+        // (the evaluation scratch is dead: exchange buffer of the sorting network)
+        const int at = block_sort_order_128(tid < NP ? V.nfit[tid] : 0.f, NP, reinterpret_cast<unsigned long long*>(V.scr));
+        if (tid < NP) V.rank[at] = tid;
+    }
     __syncthreads();
     {
         // survivors: trial if tfit <= fit else the parent, whose row is re-read from the stored (old) population; every
