@@ -230,11 +230,10 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     // ---- P0b: stable rank of the pbest costs; sorted float32 copies of pbest / pbest_x (both ARE float32 in HBM) ----
     float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
     float2* spf2 = V.spf2;                               // sorted pbest costs (layout: mbx_fdr.cuh, FDR_COST)
-    if (tid < NP) {
-        const float fi = V.pf32[tid];
-        int r = 0;
-        for (int j = 0; j < NP; ++j) { const float fj = V.pf32[j]; r += (fj < fi || (fj == fi && j < tid)) ? 1 : 0; }
-        V.rank[tid] = (unsigned char)r; V.order[r] = (unsigned char)tid; fdr_store_cost(spf2, r, fi);
+    {
+        // 128-thread sorting network on (order key, index) items (mbx_common.cuh); `xs` is dead until P2: exchange buffer
+        const int at = block_sort_order_128(tid < NP ? V.pf32[tid] : 0.f, NP, reinterpret_cast<unsigned long long*>(V.xs));
+        if (tid < NP) { V.rank[at] = (unsigned char)tid; V.order[tid] = (unsigned char)at; fdr_store_cost(spf2, tid, V.pf32[at]); }
     }
     if (tid == 0) *V.nfb = 0;
     __syncthreads();
