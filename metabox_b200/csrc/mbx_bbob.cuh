@@ -39,8 +39,8 @@ __device__ __forceinline__ double pen_x(const XA& X, double ub) {               
     double p = 0.;
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
-        double t = fmax(0., fabs(X(d)) - ub);
-        p += t * t;
+        const double t = fabs(X(d)) - ub;                  // max(0, .) as a compare: 0 * 0 added to p changes nothing
+        if (t > 0.) p += t * t;
     }
     return p;
 }

@@ -247,7 +247,7 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
     auto pen_row = [&]() {                                           // bbob.py:85-93 for candidate tid
         double p = 0.;
 #pragma unroll 1
-        for (int d = 0; d < D; ++d) { const double t = fmax(0., fabs((double)xr[d]) - ub); p += t * t; }
+        for (int d = 0; d < D; ++d) { const double t = fabs((double)xr[d]) - ub; if (t > 0.) p += t * t; }   // max(0, .) as a compare
         return p;
     };
     double bh = 0.;
@@ -488,8 +488,8 @@ __device__ double bbob_eval_cta(const MbxInstance& h, const double* __restrict__
                 prev = z0;
                 z = 100. * (c.cv0[d] * (z - c.cv1[d]) + c.cv1[d]);
                 f += zr[d];
-                const double t = fmax(0., fabs(z / 100.) - ub);
-                pen += t * t;
+                const double t = fabs(z / 100.) - ub;
+                if (t > 0.) pen += t * t;
             }
         }
         return 4.189828872724339 - 0.01 * (f / (double)D) + 100. * pen + bias;

@@ -84,7 +84,7 @@ eval_stream_kernel(const MbxInstance* __restrict__ inst, const double* __restric
         if (bhc != 0. && base == 8) {                                // boundary handling (pen_row): base 8 only, like case 8's `+ bh`
             double p = 0.;
 #pragma unroll
-            for (int d = 0; d < D; ++d) { const double t = fmax(0., fabs(xr_(d)) - ub); p += t * t; }
+            for (int d = 0; d < D; ++d) { const double t = fabs(xr_(d)) - ub; if (t > 0.) p += t * t; }
             bh = (bhc == 1.) ? p : bhc * p;
         }
         if (base == 8) {                                             // Rosenbrock (case 8)
@@ -109,8 +109,8 @@ eval_stream_kernel(const MbxInstance* __restrict__ inst, const double* __restric
                 prev = z0;
                 z = 100. * (__ldg(cv0 + d) * (z - __ldg(cv1 + d)) + __ldg(cv1 + d));
                 fs += z * sin(sqrt(fabs(z)));
-                const double t = fmax(0., fabs(z / 100.) - ub);
-                pen += t * t;
+                const double t = fabs(z / 100.) - ub;
+                if (t > 0.) pen += t * t;
             }
             f = 4.189828872724339 - 0.01 * (fs / (double)D) + 100. * pen + bias;
         }

@@ -21,6 +21,7 @@ struct LdeLayout {
         size_t scr = (size_t)scratchDoubles;
         const size_t psd = ((size_t)NPp * D * sizeof(float) + 7) / 8;
         if (psd > scr) scr = psd;
+        if (scr < MBX_NT) scr = MBX_NT;                      // >= 128 x 8 bytes: exchange buffer of the sorting network (P5)
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
         oScr = oConst + sizeof(double) * kConst;             // P0-P2: parents f32 [NP*D] (sorted)  /  P3: eval scratch f64
         oTs = oScr + sizeof(double) * scr;                   // trial population f32 [NP*D]

@@ -29,7 +29,8 @@ struct RlLayout {
     __host__ __device__ RlLayout(int np, int D, int kConst, bool protein) {
         NP = np; NPp = (np + 3) & ~3;
         const size_t scratch = protein ? (size_t)(MBX_NT / 32) * MBX_PROT_WARP_SCRATCH : (size_t)(D + 1) * NPp;   // bbob_eval_cta tile [NP][D+1]
-        const size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
+        size_t regionA = scratch > (size_t)NPp * D ? scratch : (size_t)NPp * D;
+        if (regionA < MBX_NT) regionA = MBX_NT;              // >= 128 x 8 bytes: exchange buffer of the sorting network (block_sort_order_128)
         oConst = (sizeof(MbxInstance) + 15) & ~(size_t)15;
         oA = oConst + sizeof(double) * kConst;               // spx f32 [NP*D] | tgt u8 [NP*D]   /   eval scratch f64
         oSpf = oA + sizeof(double) * regionA;                // sorted pbest duplicated (f, f) float2 [NP]
@@ -231,8 +232,8 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     float* spx = V.spx;                                  // pbest_x rows in ascending-pbest order [NP*D]
     float2* spf2 = V.spf2;                               // sorted pbest costs (layout: mbx_fdr.cuh, FDR_COST)
     {
-        // 128-thread sorting network on (order key, index) items (mbx_common.cuh); `xs` is dead until P2: exchange buffer
-        const int at = block_sort_order_128(tid < NP ? V.pf32[tid] : 0.f, NP, reinterpret_cast<unsigned long long*>(V.xs));
+        // 128-thread sorting network on (order key, index) items (mbx_common.cuh); region A is written after this: exchange buffer
+        const int at = block_sort_order_128(tid < NP ? V.pf32[tid] : 0.f, NP, reinterpret_cast<unsigned long long*>(V.A));
         if (tid < NP) { V.rank[at] = (unsigned char)tid; V.order[tid] = (unsigned char)at; fdr_store_cost(spf2, tid, V.pf32[at]); }
     }
     if (tid == 0) *V.nfb = 0;
