@@ -19,9 +19,20 @@ struct EvalTraits {
 template <int D, int KIND>
 __device__ __forceinline__ void stage_instance(const MbxInstance* __restrict__ inst, const double* __restrict__ consts,
                                                MbxInstance* sh, double* sC) {
-    const int n = EvalTraits<D, KIND>::kConstDoubles;
+    constexpr int n = EvalTraits<D, KIND>::kConstDoubles;
     const double* src = consts + inst->off;
-    for (int k = MBX_TID; k < n; k += MBX_BDIM) sC[k] = __ldg(src + k);
+    // every load of the thread is issued before the first store (n / 128 <= 32 values in registers): one exposed L2 / DRAM latency for the
+    // whole block of constants instead of one per unrolled group of four
+    constexpr int PER = (n + MBX_NT - 1) / MBX_NT;
+    if (MBX_BDIM == MBX_NT && PER <= 32) {
+        double r[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int k = MBX_TID + q * MBX_NT; r[q] = k < n ? __ldg(src + k) : 0.; }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int k = MBX_TID + q * MBX_NT; if (k < n) sC[k] = r[q]; }
+    } else {
+        for (int k = MBX_TID; k < n; k += MBX_BDIM) sC[k] = __ldg(src + k);
+    }
     const int* hs = reinterpret_cast<const int*>(inst);
     int* hd = reinterpret_cast<int*>(sh);
     for (int k = MBX_TID; k < (int)(sizeof(MbxInstance) / 4); k += MBX_BDIM) hd[k] = hs[k];

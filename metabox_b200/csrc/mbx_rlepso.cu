@@ -181,7 +181,6 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
     const RlLayout L(NP, D, EvalTraits<D, KIND>::kConstDoubles, KIND == MBX_KIND_PROTEIN);
     RlepsoViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
-    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b];
@@ -196,6 +195,7 @@ rlepso_step_kernel(const MbxInstance* __restrict__ inst, const double* __restric
             pbx[k] = e < NP * D ? __ldcs(S.pbest_x + base + e) : 0.f;
         }
     }
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);          // (after the row requests: its stores wait for its own loads)
     // ---- P0: per-particle scalars, draws, coefficients (:112-132) -------------------------------------------
     for (int d = tid; d < D; d += MBX_NT) V.gx[d] = (double)S.gbest_x[(size_t)b * D + d];
     if (tid < NP) {
