@@ -209,7 +209,6 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
     const LdeLayout L = lde_layout<D, KIND>(NP);
     LdeViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
-    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
     const uint32_t gen = (uint32_t)S.gen[b], lane = (uint32_t)(cfg.lane_base + b);
@@ -223,6 +222,7 @@ lde_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict__
         const int e = tid + k * MBX_NT;
         popr[k] = e < NP * D ? __ldcs(S.pop + base + e) : 0.f;
     }
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);          // (after the row requests: its stores wait for its own loads)
     // ---- P0: order_by_f (:160) -- the stored state is sorted already, re-ranked for safety -------------------
     {
         // the stored state IS sorted (P5 below and the init kernel write it in rank order): the rank is the identity unless some pair of
