@@ -199,9 +199,13 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     const GlLayout L = gl_layout<D, KIND>(NP);
     GlViews<D, KIND> V(smem_raw, L);
     const MbxInstance* gi = inst + lane_inst[b];
-    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const bool use_tape = TEST && cfg.use_tape;
     const size_t base = (size_t)b * NP * D, pb = (size_t)b * NP;
+    // the pbest rows are requested first (NP * D / 128 <= D values per thread): their DRAM latency hides behind the constant staging and P0
+    float pr[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { const int e = tid + k * MBX_NT; pr[k] = e < NP * D ? __ldcs(S.pbest_x + base + e) : 0.f; }
+    stage_instance<D, KIND>(gi, consts, V.h, V.sC);
     const uint32_t gen = (uint32_t)S.gen[b], lane = (uint32_t)(cfg.lane_base + b);
     Philox ph(cfg.seed);
     // ---- P0: scalars, coefficients (float32 like numpy-2's promotion of `self.c * action`), draws, pbest tile ----------------
@@ -218,10 +222,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
         V.cb[i] = GL_C * (1.f - a);
         if (!use_tape) { uint4 w4 = ph((uint32_t)i, gen, lane, MBX_TAG_GLEET_P); V.r1u[i] = w4.x; V.r2u[i] = w4.y; }
     }
-    {   // all row loads of a thread are issued before the first shared-memory store (NP * D / 128 <= D values per thread)
-        float pr[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) { const int e = tid + k * MBX_NT; pr[k] = e < NP * D ? S.pbest_x[base + e] : 0.f; }
+    {
 #pragma unroll
         for (int k = 0; k < D; ++k) { const int e = tid + k * MBX_NT; if (e < NP * D) V.pbx[e] = pr[k]; }
     }
@@ -270,6 +271,10 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
     const float pre_gbest = S.gbest_val[b];
     float gbest = pre_gbest;
     float v = INFINITY; int ix = tid;
+    // the particle's carried exploration features (read in P4 unless it improved) are requested now: one DRAM latency behind the whole of P3
+    float pfe[GL_NFEAT];
+#pragma unroll
+    for (int k = 0; k < GL_NFEAT; ++k) pfe[k] = tid < NP ? S.pbest_feature[(pb + tid) * GL_NFEAT + k] : 0.f;
     if (tid < NP) {
         const int i = tid;
         const float ncv = V.nc[i];
@@ -325,7 +330,7 @@ gleet_step_kernel(const MbxInstance* __restrict__ inst, const double* __restrict
             const float fk = (float)f[k];
             o[k] = fk;
             if (fresh) { pfeat[k] = fk; o[GL_NFEAT + k] = fk; }
-            else o[GL_NFEAT + k] = pfeat[k];
+            else o[GL_NFEAT + k] = pfe[k];
         }
         if (i == gidx) {
 #pragma unroll
